@@ -1,0 +1,83 @@
+"""Drop-in for the reference's native module ``fake_spectra._spectra_priv`` (py_module.cpp:358-375)
+on the hot path: ``_Particle_Interpolate`` and ``_near_lines`` with the same positional arguments,
+dtype/shape checks and exceptions, implemented by the C-ABI host entry points of libfsb200.so
+(host buffers in, host buffer out; the copies and the sm_100a kernels are inside the call).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+# module-level defaults that the host classes may override (Spectra(precision=..., voigt=...))
+DEFAULT_PRECISION = _lib.PRECISION_FP64
+DEFAULT_VOIGT = _lib.VOIGT_FAST
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _is_f32(a):
+    return isinstance(a, np.ndarray) and a.dtype == np.float32
+
+
+def _Particle_Interpolate(compute_tau, nbins, kernel, box, velfac, atime, lambda_cm, gamma, fosc, amumass, tautail,
+                          pos, vel, dens, temp, h, axis, cofm, precision=None, voigt=None):
+    """Optical depth (compute_tau != 0) or column density on every sightline.
+
+    Arguments, order and units as py_module.cpp:115; returns a new float64 array [NumLos, nbins].
+    Raises TypeError / ValueError on the same conditions as py_module.cpp:122-151."""
+    for a in (pos, vel, dens, temp, h):
+        if not _is_f32(a):
+            raise TypeError("One of the data arrays does not have 32-bit float type")
+    if not (isinstance(cofm, np.ndarray) and cofm.dtype == np.float64):
+        raise TypeError("Sightline positions must have 64-bit float type")
+    if not (isinstance(axis, np.ndarray) and axis.dtype == np.int32):
+        raise TypeError("Axis must be a 32-bit integer")
+    numlos = cofm.shape[0]
+    npart = pos.shape[0]
+    if npart != dens.shape[0] or npart != h.shape[0]:
+        raise ValueError(" Dens, pos and h must have the same length")
+    if cofm.ndim != 2 or numlos != axis.shape[0] or cofm.shape[1] != 3:
+        raise ValueError("cofm must have dimensions (np.size(axis),3) ")
+    if compute_tau and (vel.shape[0] != npart or temp.shape[0] != npart):
+        raise ValueError(" Vel and temp must have the same length as pos when computing tau")
+    pos, dens, h = (np.ascontiguousarray(a) for a in (pos, dens, h))
+    cofm, axis = np.ascontiguousarray(cofm), np.ascontiguousarray(axis)
+    p = _lib.make_params(nbins, kernel, box, velfac, atime, lambda_cm, gamma, fosc, amumass, tautail,
+                         precision=DEFAULT_PRECISION if precision is None else precision,
+                         voigt=DEFAULT_VOIGT if voigt is None else voigt)
+    out = np.empty((numlos, int(nbins)), dtype=np.float64)
+    lib = _lib.load()
+    if compute_tau:
+        vel, temp = np.ascontiguousarray(vel), np.ascontiguousarray(temp)
+        pvel, ptemp = _ptr(vel), _ptr(temp)
+    else:
+        pvel = ptemp = None
+    rc = lib.fsb_particle_interpolate_host(1 if compute_tau else 0, C.byref(p), _ptr(pos), pvel, _ptr(dens), ptemp,
+                                           _ptr(h), npart, _ptr(axis), _ptr(cofm), numlos, _ptr(out))
+    _lib.check(rc, "_Particle_Interpolate")
+    return out
+
+
+def _near_lines(box, pos, hh, axis, cofm):
+    """Sorted int32 indices of the particles whose kernel reaches at least one sightline
+    (py_module.cpp:25-99, same checks)."""
+    if not isinstance(cofm, np.ndarray) or cofm.ndim < 2 or not isinstance(axis, np.ndarray) or axis.ndim < 1:
+        raise ValueError("cofm must have dimensions (np.size(axis),3) ")
+    if cofm.shape[0] != axis.shape[0] or cofm.shape[1] != 3:
+        raise ValueError("cofm must have dimensions (np.size(axis),3) ")
+    if cofm.dtype != np.float64 or axis.dtype != np.int32:
+        raise ValueError("cofm must have 64-bit float type and axis must be a 32-bit integer")
+    if not _is_f32(pos) or not _is_f32(hh):
+        raise TypeError("pos and h must have 32-bit float type")
+    pos, hh = np.ascontiguousarray(pos), np.ascontiguousarray(hh)
+    cofm, axis = np.ascontiguousarray(cofm), np.ascontiguousarray(axis)
+    npart = pos.shape[0]
+    out = np.empty(max(npart, 1), dtype=np.int32)
+    count = C.c_int64(0)
+    rc = _lib.load().fsb_near_lines_host(float(box), _ptr(pos), _ptr(hh), npart, _ptr(axis), _ptr(cofm), cofm.shape[0],
+                                         _ptr(out), C.byref(count))
+    _lib.check(rc, "_near_lines")
+    return out[:count.value].copy()

@@ -1,0 +1,259 @@
+// C-ABI glue of libfsb200 (include/fsb200.h): argument validation, derived constants, the
+// one-shot and host-pointer entry points that mirror the reference's Python boundary
+// (py_module.cpp:25-233).
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstring>
+
+#include "fsb_common.cuh"
+
+namespace fsb {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int Scratch::alloc(size_t bytes, cudaStream_t s)
+{
+    stream = s;
+    if (bytes == 0) bytes = 8;
+    cudaError_t e = cudaMallocAsync(&ptr, bytes, s);
+    if (e != cudaSuccess) {
+        ptr = nullptr;
+        set_error("cudaMallocAsync(%zu bytes): %s", bytes, cudaGetErrorString(e));
+        return e == cudaErrorMemoryAllocation ? FSB_ENOMEM : FSB_ECUDA;
+    }
+    return FSB_OK;
+}
+
+Scratch::~Scratch()
+{
+    if (ptr) cudaFreeAsync(ptr, stream);
+}
+
+// LineAbsorption ctor: absorption.cpp:152-161.
+static int make_consts(const fsb_index *idx, const fsb_params *p, int nlines, InterpConsts &c)
+{
+    FSB_REQUIRE(idx != nullptr && p != nullptr, "NULL index or params");
+    FSB_REQUIRE(nlines >= 1 && nlines <= kMaxFused, "between 1 and 4 fused lines / weight columns per call");
+    FSB_REQUIRE(p->nbins > 0, "nbins must be positive");
+    FSB_REQUIRE(p->kernel >= 0 && p->kernel <= 3, "kernel id must be 0..3 (singleabs.h:9-12)");
+    FSB_REQUIRE(p->box > 0 && p->velfac > 0, "box and velfac must be positive");
+    FSB_REQUIRE(p->box == idx->box, "params.box differs from the box the index was built with");
+    FSB_REQUIRE(p->amumass > 0, "amumass must be positive");
+    FSB_REQUIRE(p->gamma >= 0, "gamma must be non-negative");
+    c.nbins = p->nbins;
+    c.kernel = p->kernel;
+    c.nlos = idx->nlos;
+    c.nlines = nlines;
+    c.box = p->box;
+    c.velfac = p->velfac;
+    c.vbox = p->box * p->velfac;
+    c.bfac = sqrt(2.0 * kBoltzmann / (p->amumass * kProtonMass)) / 1e5;
+    c.tautail = p->tautail;
+    c.bintov = c.vbox / p->nbins;                 // absorption.cpp:239
+    c.boxtokpc = c.vbox / p->nbins / p->velfac;   // absorption.cpp:188
+    c.voigt = p->voigt;
+    c.seg_pairs = p->seg_pairs;
+    return FSB_OK;
+}
+
+static void line_consts(const fsb_params &p, LineConsts &l)
+{
+    l.sigma_a = sqrt(3.0 * kPi * kSigmaT / 8.0) * p.lambda_cm * p.fosc;
+    l.voigt_fac = p.gamma * p.lambda_cm / (4. * kPi) / 1e5;
+}
+
+}  // namespace fsb
+
+using namespace fsb;
+
+extern "C" int fsb_abi_version(void) { return FSB_ABI_VERSION; }
+
+extern "C" const char *fsb_last_error(void) { return g_err; }
+
+extern "C" const char *fsb_strerror(int code)
+{
+    switch (code) {
+    case FSB_OK: return "ok";
+    case FSB_EINVAL: return "invalid argument";
+    case FSB_ECUDA: return "CUDA error";
+    case FSB_ENOMEM: return "out of device memory";
+    case FSB_EVORONOI: return "Voronoi cell ownership is not contiguous along a sightline";
+    case FSB_ENODEV: return "no usable CUDA device";
+    default: return "unknown error";
+    }
+}
+
+extern "C" int fsb_device_info(int32_t *sm_count, int32_t *clock_khz, int32_t *cc_major, int32_t *cc_minor)
+{
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) {
+        set_error("cudaGetDevice: %s", cudaGetErrorString(e));
+        return FSB_ENODEV;
+    }
+    int v = 0;
+    if (sm_count) { FSB_CUDA_TRY(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev)); *sm_count = v; }
+    if (clock_khz) { FSB_CUDA_TRY(cudaDeviceGetAttribute(&v, cudaDevAttrClockRate, dev)); *clock_khz = v; }
+    if (cc_major) { FSB_CUDA_TRY(cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMajor, dev)); *cc_major = v; }
+    if (cc_minor) { FSB_CUDA_TRY(cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMinor, dev)); *cc_minor = v; }
+    return FSB_OK;
+}
+
+extern "C" int fsb_compute_tau_multi(const fsb_index *idx, const fsb_params *p, int32_t nlines, const float *pos,
+                                     const float *vel, const float *dens, const float *temp, const float *h, double *tau,
+                                     fsb_counters *counters, void *stream_v)
+{
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    FSB_REQUIRE(nlines >= 1, "nlines must be >= 1");
+    FSB_REQUIRE(idx != nullptr && p != nullptr, "NULL index or params");
+    FSB_REQUIRE(idx->npairs == 0 || (pos && vel && dens && temp && h && tau), "NULL array");
+    FSB_REQUIRE(p[0].kernel != FSB_KERNEL_VORONOI, "Voronoi tau goes through fsb_particle_interpolate (needs fsb_assign_cells)");
+    for (int32_t i = 0; i < nlines; ++i) {
+        FSB_REQUIRE(p[i].nbins == p[0].nbins && p[i].kernel == p[0].kernel && p[i].box == p[0].box &&
+                    p[i].velfac == p[0].velfac && p[i].amumass == p[0].amumass && p[i].tautail == p[0].tautail,
+                    "fused lines must share nbins, kernel, box, velfac, amumass and tautail");
+        InterpConsts c;
+        FSB_TRY(make_consts(idx, &p[i], 1, c));
+        line_consts(p[i], c.line[0]);
+        FSB_TRY(launch_tau(idx, c, pos, vel, dens, temp, h, nullptr, tau + (size_t) i * (size_t) idx->nlos * (size_t) c.nbins,
+                           counters, p[i].precision, stream));
+    }
+    return FSB_OK;
+}
+
+extern "C" int fsb_compute_tau(const fsb_index *idx, const fsb_params *p, const float *pos, const float *vel,
+                               const float *dens, const float *temp, const float *h, double *tau, fsb_counters *counters,
+                               void *stream)
+{
+    return fsb_compute_tau_multi(idx, p, 1, pos, vel, dens, temp, h, tau, counters, stream);
+}
+
+extern "C" int fsb_compute_colden(const fsb_index *idx, const fsb_params *p, const float *pos, const float *dens,
+                                  int32_t nweights, const float *h, double *colden, fsb_counters *counters, void *stream_v)
+{
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    FSB_REQUIRE(idx != nullptr && p != nullptr, "NULL index or params");
+    FSB_REQUIRE(nweights >= 1, "nweights must be >= 1");
+    FSB_REQUIRE(idx->npairs == 0 || (pos && dens && h && colden), "NULL array");
+    FSB_REQUIRE(p->kernel != FSB_KERNEL_VORONOI, "Voronoi colden goes through fsb_particle_interpolate (needs fsb_assign_cells)");
+    for (int32_t w0 = 0; w0 < nweights; w0 += kMaxFused) {
+        const int nw = std::min<int32_t>(kMaxFused, nweights - w0);
+        InterpConsts c;
+        FSB_TRY(make_consts(idx, p, nw, c));
+        FSB_TRY(launch_colden(idx, c, pos, dens + (size_t) w0 * (size_t) idx->npart, idx->npart, h, nullptr,
+                              colden + (size_t) w0 * (size_t) idx->nlos * (size_t) c.nbins, counters, stream));
+    }
+    return FSB_OK;
+}
+
+extern "C" int fsb_particle_interpolate(int32_t compute_tau, const fsb_params *p, const float *pos, const float *vel,
+                                        const float *dens, const float *temp, const float *h, int64_t npart,
+                                        const int32_t *axis, const double *cofm, int32_t nlos, double *out, void *stream_v)
+{
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    FSB_REQUIRE(p != nullptr, "params is NULL");
+    FSB_REQUIRE(p->nbins > 0, "nbins must be positive");
+    fsb_index *idx = nullptr;
+    FSB_TRY(fsb_index_build(p->box, cofm, axis, nlos, pos, h, npart, stream, &idx));
+    int rc = FSB_OK;
+    if (p->kernel == FSB_KERNEL_VORONOI) {
+        Scratch cells;
+        rc = cells.alloc(sizeof(float) * 2 * (size_t) std::max<int64_t>(idx->npairs, 1), stream);
+        if (rc == FSB_OK) rc = fsb_assign_cells(idx, p->box, cofm, axis, pos, cells.as<float>(), stream);
+        if (rc == FSB_OK) {
+            InterpConsts c;
+            rc = make_consts(idx, p, 1, c);
+            if (rc == FSB_OK) {
+                line_consts(*p, c.line[0]);
+                rc = compute_tau ? launch_tau(idx, c, pos, vel, dens, temp, h, cells.as<float>(), out, nullptr, p->precision, stream)
+                                 : launch_colden(idx, c, pos, dens, npart, h, cells.as<float>(), out, nullptr, stream);
+            }
+        }
+    } else if (compute_tau) {
+        rc = fsb_compute_tau(idx, p, pos, vel, dens, temp, h, out, nullptr, stream);
+    } else {
+        rc = fsb_compute_colden(idx, p, pos, dens, 1, h, out, nullptr, stream);
+    }
+    fsb_index_free(idx, stream);
+    return rc;
+}
+
+namespace {
+struct DevBuf {
+    void *ptr = nullptr;
+    ~DevBuf() { if (ptr) cudaFree(ptr); }
+    int upload(const void *host, size_t bytes, cudaStream_t s)
+    {
+        if (bytes == 0) bytes = 8, host = nullptr;
+        FSB_CUDA_TRY(cudaMalloc(&ptr, bytes));
+        if (host) FSB_CUDA_TRY(cudaMemcpyAsync(ptr, host, bytes, cudaMemcpyHostToDevice, s));
+        return FSB_OK;
+    }
+};
+}  // namespace
+
+extern "C" int fsb_particle_interpolate_host(int32_t compute_tau, const fsb_params *p, const float *pos, const float *vel,
+                                             const float *dens, const float *temp, const float *h, int64_t npart,
+                                             const int32_t *axis, const double *cofm, int32_t nlos, double *out)
+{
+    FSB_REQUIRE(p != nullptr && out != nullptr, "params/out NULL");
+    FSB_REQUIRE(nlos >= 0 && npart >= 0 && p->nbins > 0, "bad sizes");
+    cudaStream_t s = nullptr;
+    DevBuf dpos, dvel, ddens, dtemp, dh, daxis, dcofm, dout;
+    const size_t np = (size_t) npart, nl = (size_t) nlos;
+    FSB_TRY(dpos.upload(pos, sizeof(float) * 3 * np, s));
+    FSB_TRY(ddens.upload(dens, sizeof(float) * np, s));
+    FSB_TRY(dh.upload(h, sizeof(float) * np, s));
+    if (compute_tau) {
+        FSB_REQUIRE(npart == 0 || (vel && temp), "vel/temp NULL with compute_tau");
+        FSB_TRY(dvel.upload(vel, sizeof(float) * 3 * np, s));
+        FSB_TRY(dtemp.upload(temp, sizeof(float) * np, s));
+    }
+    FSB_TRY(daxis.upload(axis, sizeof(int32_t) * nl, s));
+    FSB_TRY(dcofm.upload(cofm, sizeof(double) * 3 * nl, s));
+    const size_t out_bytes = sizeof(double) * nl * (size_t) p->nbins;
+    FSB_TRY(dout.upload(nullptr, out_bytes, s));
+    FSB_CUDA_TRY(cudaMemsetAsync(dout.ptr, 0, std::max<size_t>(out_bytes, 8), s));
+    FSB_TRY(fsb_particle_interpolate(compute_tau, p, (const float *) dpos.ptr, (const float *) dvel.ptr, (const float *) ddens.ptr,
+                                     (const float *) dtemp.ptr, (const float *) dh.ptr, npart, (const int32_t *) daxis.ptr,
+                                     (const double *) dcofm.ptr, nlos, (double *) dout.ptr, s));
+    if (out_bytes) FSB_CUDA_TRY(cudaMemcpyAsync(out, dout.ptr, out_bytes, cudaMemcpyDeviceToHost, s));
+    FSB_CUDA_TRY(cudaStreamSynchronize(s));
+    return FSB_OK;
+}
+
+extern "C" int fsb_near_lines_host(double box, const float *pos, const float *h, int64_t npart, const int32_t *axis,
+                                   const double *cofm, int32_t nlos, int32_t *out_index, int64_t *count)
+{
+    FSB_REQUIRE(count != nullptr, "count is NULL");
+    *count = 0;
+    FSB_REQUIRE(nlos >= 0 && npart >= 0, "negative size");
+    if (npart == 0 || nlos == 0) return FSB_OK;
+    cudaStream_t s = nullptr;
+    DevBuf dpos, dh, daxis, dcofm, dout;
+    FSB_TRY(dpos.upload(pos, sizeof(float) * 3 * (size_t) npart, s));
+    FSB_TRY(dh.upload(h, sizeof(float) * (size_t) npart, s));
+    FSB_TRY(daxis.upload(axis, sizeof(int32_t) * (size_t) nlos, s));
+    FSB_TRY(dcofm.upload(cofm, sizeof(double) * 3 * (size_t) nlos, s));
+    FSB_TRY(dout.upload(nullptr, sizeof(int32_t) * (size_t) npart, s));
+    FSB_TRY(fsb_near_lines(box, (const float *) dpos.ptr, (const float *) dh.ptr, npart, (const int32_t *) daxis.ptr,
+                           (const double *) dcofm.ptr, nlos, (int32_t *) dout.ptr, count, s));
+    if (*count > 0) FSB_CUDA_TRY(cudaMemcpy(out_index, dout.ptr, sizeof(int32_t) * (size_t) *count, cudaMemcpyDeviceToHost));
+    return FSB_OK;
+}
+
+extern "C" int fsb_voigt_profile(const double *x, const double *y, double *out, int64_t n, int32_t voigt, void *stream)
+{
+    FSB_REQUIRE(n >= 0, "negative n");
+    FSB_REQUIRE(n == 0 || (x && y && out), "NULL array");
+    return launch_voigt(x, y, out, n, voigt, static_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,573 @@
+// Candidate index: which particles reach which sightline (replaces IndexTable, index_table.cpp).
+//
+// The reference sorts sightlines by one perpendicular coordinate in two std::multimap and walks a
+// key range per particle.  Here sightlines are binned on a 2-D grid over the plane perpendicular
+// to their axis (one grid per axis value 1,2,3), particles are streamed once per pass with
+// coalesced loads, and every (particle, line) pair that survives the grid walk is tested with the
+// EXACT predicate of index_table.cpp:22-113 (same float/double mix, no FMA contraction), so the
+// candidate sets are bit-identical to the reference's.  Passes:
+//   lines:  classify -> per-cell counts -> scan -> scatter (cell-sorted line table)
+//   pairs:  count per line (atomics) -> scan to int64 offsets -> fill -> per-line sort by
+//           particle index (restores std::map order and run-to-run determinism) + dr^2
+#include <algorithm>
+#include <vector>
+
+#include "fsb_common.cuh"
+#include "fsb_scan.cuh"
+
+namespace fsb {
+
+namespace {
+
+constexpr int kMaxGrid = 1024;
+
+struct AxisGrid {
+    int32_t G;          // cells per side (0 when the group has no lines)
+    int32_t cell_base;  // offset of this group's cells in cell_start
+    double inv_cs;      // G / box
+};
+
+struct LineTable {
+    AxisGrid grid[3];          // axis 1, 2, 3
+    const int32_t *cell_start; // [total_cells + 1] -> slot range in the arrays below
+    const int32_t *line_id;    // [nlos] sightline index, cell-sorted
+    const double *key;         // [nlos] primary perpendicular coordinate
+    const double *proj2;       // [nlos] secondary perpendicular coordinate
+    double box;
+};
+
+// Perpendicular coordinates of a sightline: (primary key, secondary), index_table.cpp:10-15,29-40.
+__device__ __forceinline__ void line_coords(const double *cofm, int l, int ax, double &key, double &proj2)
+{
+    if (ax == 1) {
+        key = cofm[3 * l + 1];
+        proj2 = cofm[3 * l + 2];
+    } else if (ax == 3) {
+        key = cofm[3 * l];
+        proj2 = cofm[3 * l + 1];
+    } else {
+        key = cofm[3 * l];
+        proj2 = cofm[3 * l + 2];
+    }
+}
+
+// Monotone map coordinate -> cell; the same function bins lines and bounds particle walks, so a
+// line inside a coordinate interval is always inside the corresponding cell interval.
+__device__ __forceinline__ int cell_of(double v, double inv_cs, int G)
+{
+    const double c = floor(v * inv_cs);
+    if (!(c > 0.0)) return 0;  // also NaN
+    if (c >= (double) G) return G - 1;
+    return (int) c;
+}
+
+__device__ __forceinline__ int group_of_axis(int ax) { return ax == 1 ? 0 : (ax == 2 ? 1 : 2); }
+
+__global__ void k_line_cells(const double *__restrict__ cofm, const int32_t *__restrict__ axis, int nlos,
+                             AxisGrid g0, AxisGrid g1, AxisGrid g2, int32_t *__restrict__ cell_of_line,
+                             int32_t *__restrict__ cell_count)
+{
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= nlos) return;
+    const int ax = axis[l];
+    const int grp = group_of_axis(ax);
+    const AxisGrid g = grp == 0 ? g0 : (grp == 1 ? g1 : g2);
+    double key, proj2;
+    line_coords(cofm, l, ax, key, proj2);
+    const int cell = g.cell_base + cell_of(key, g.inv_cs, g.G) * g.G + cell_of(proj2, g.inv_cs, g.G);
+    cell_of_line[l] = cell;
+    atomicAdd(&cell_count[cell], 1);
+}
+
+__global__ void k_line_scatter(const double *__restrict__ cofm, const int32_t *__restrict__ axis, int nlos,
+                               const int32_t *__restrict__ cell_of_line, const int32_t *__restrict__ cell_start,
+                               int32_t *__restrict__ cursor, int32_t *__restrict__ line_id, double *__restrict__ key,
+                               double *__restrict__ proj2)
+{
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= nlos) return;
+    const int cell = cell_of_line[l];
+    const int slot = cell_start[cell] + atomicAdd(&cursor[cell], 1);
+    double k, p2;
+    line_coords(cofm, l, axis[l], k, p2);
+    line_id[slot] = l;
+    key[slot] = k;
+    proj2[slot] = p2;
+}
+
+// Union of up to three closed cell intervals -> disjoint ascending intervals (no cell twice).
+struct Spans {
+    int lo[3], hi[3], n;
+    __device__ __forceinline__ void add(int a, int b)
+    {
+        if (a > b) return;
+        lo[n] = a;
+        hi[n] = b;
+        ++n;
+    }
+    __device__ __forceinline__ void normalise()
+    {
+        // insertion sort by lo, then merge touching/overlapping neighbours
+        for (int i = 1; i < n; ++i)
+            for (int j = i; j > 0 && lo[j] < lo[j - 1]; --j) {
+                int t = lo[j]; lo[j] = lo[j - 1]; lo[j - 1] = t;
+                t = hi[j]; hi[j] = hi[j - 1]; hi[j - 1] = t;
+            }
+        int m = 0;
+        for (int i = 0; i < n; ++i) {
+            if (m > 0 && lo[i] <= hi[m - 1] + 1) {
+                if (hi[i] > hi[m - 1]) hi[m - 1] = hi[i];
+            } else {
+                lo[m] = lo[i];
+                hi[m] = hi[i];
+                ++m;
+            }
+        }
+        n = m;
+    }
+};
+
+// MODE 0: count pairs per line.  MODE 1: fill the lists.  MODE 2: flag particles with >= 1 line.
+template <int MODE>
+__global__ void __launch_bounds__(256) k_pairs(LineTable T, const float *__restrict__ pos, const float *__restrict__ hh,
+                                               int64_t npart, int32_t *__restrict__ count,
+                                               const int64_t *__restrict__ offsets, int32_t *__restrict__ particle,
+                                               uint8_t *__restrict__ flag)
+{
+    const int64_t p = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npart) return;
+    const float px = pos[3 * p], py = pos[3 * p + 1], pz = pos[3 * p + 2];
+    const float h = hh[p];
+    const double box = T.box;
+    const double h2 = (double) __fmul_rn(h, h);  // float product: index_table.cpp:45
+    bool any = false;
+
+    #pragma unroll 1
+    for (int grp = 0; grp < 3; ++grp) {
+        const AxisGrid g = T.grid[grp];
+        if (g.G == 0) continue;
+        // axis 1: (y,z); axis 2: (x,z); axis 3: (x,y)   (index_table.cpp:29-40,120-125)
+        const float first = grp == 0 ? py : px;
+        const float second = grp == 2 ? py : pz;
+
+        // B1, index_table.cpp:89-113: float add, wrap in double then round to float.
+        float ffp = __fadd_rn(first, h);
+        if ((double) ffp > box) ffp = __double2float_rn(__dsub_rn((double) ffp, box));
+        float ffm = __fsub_rn(first, h);
+        if (ffm < 0) ffm = __double2float_rn(__dadd_rn((double) ffm, box));
+        const bool wrapped = !(ffm <= ffp);
+        const double dffm = (double) ffm, dffp = (double) ffp;
+        Spans P;
+        P.n = 0;
+        if (!wrapped) {
+            P.add(cell_of(dffm, g.inv_cs, g.G), cell_of(dffp, g.inv_cs, g.G));
+        } else {
+            P.add(0, cell_of(dffp, g.inv_cs, g.G));
+            P.add(cell_of(dffm, g.inv_cs, g.G), g.G - 1);
+        }
+        P.normalise();
+
+        // B2, index_table.cpp:52-68: wrap arithmetic stays in double here.
+        const float sfp = __fadd_rn(second, h);
+        const float sfm = __fsub_rn(second, h);
+        const double dsfp = (double) sfp, dsfm = (double) sfm;
+        const bool hi_wrap = dsfp > box;
+        const bool lo_wrap = sfm < 0;
+        const double wrap_hi = __dsub_rn(dsfp, box);  // lproj2 < sfp - box
+        const double wrap_lo = __dadd_rn(dsfm, box);  // lproj2 > sfm + box
+        Spans S;
+        S.n = 0;
+        S.add(cell_of(dsfm, g.inv_cs, g.G), cell_of(dsfp, g.inv_cs, g.G));
+        if (hi_wrap) S.add(0, cell_of(wrap_hi, g.inv_cs, g.G));
+        if (lo_wrap) S.add(cell_of(wrap_lo, g.inv_cs, g.G), g.G - 1);
+        S.normalise();
+
+        for (int ip = 0; ip < P.n && !(MODE == 2 && any); ++ip)
+            for (int row = P.lo[ip]; row <= P.hi[ip] && !(MODE == 2 && any); ++row)
+                for (int is = 0; is < S.n && !(MODE == 2 && any); ++is) {
+                    const int c0 = g.cell_base + row * g.G;
+                    const int beg = T.cell_start[c0 + S.lo[is]];
+                    const int end = T.cell_start[c0 + S.hi[is] + 1];
+                    for (int s = beg; s < end && !(MODE == 2 && any); ++s) {
+                        const double key = T.key[s];
+                        // B1: lower_bound on both ends -> [ffm, ffp)
+                        const bool in1 = !wrapped ? (key >= dffm && key < dffp) : (key < dffp || key >= dffm);
+                        if (!in1) continue;
+                        const double lp2 = T.proj2[s];
+                        bool in2 = false;
+                        if (hi_wrap && lp2 < wrap_hi) in2 = true;
+                        else if (lo_wrap && lp2 > wrap_lo) in2 = true;
+                        else in2 = (lp2 > dsfm && lp2 < dsfp);
+                        if (!in2) continue;
+                        // B3, index_table.cpp:70-87: separately rounded products and sum
+                        double d1 = fabs(__dsub_rn((double) first, key));
+                        if (d1 > 0.5 * box) d1 = __dsub_rn(box, d1);
+                        double d2 = fabs(__dsub_rn((double) second, lp2));
+                        if (d2 > 0.5 * box) d2 = __dsub_rn(box, d2);
+                        const double dr2 = __dadd_rn(__dmul_rn(d1, d1), __dmul_rn(d2, d2));
+                        if (!(dr2 <= h2)) continue;
+                        if (MODE == 0) {
+                            atomicAdd(&count[T.line_id[s]], 1);
+                        } else if (MODE == 1) {
+                            const int l = T.line_id[s];
+                            const int slot = atomicAdd(&count[l], 1);
+                            particle[offsets[l] + slot] = (int32_t) p;
+                        } else {
+                            any = true;
+                        }
+                    }
+                }
+        if (MODE == 2 && any) break;
+    }
+    if (MODE == 2) flag[p] = any ? 1 : 0;
+}
+
+// Squared periodic impact parameter of (particle, line): index_table.cpp:44,70-87.
+__device__ __forceinline__ double pair_dr2(const float *__restrict__ pos, int64_t p, const double *__restrict__ cofm,
+                                           int l, int ax, double box)
+{
+    double key, lp2;
+    line_coords(cofm, l, ax, key, lp2);
+    const float first = ax == 1 ? pos[3 * p + 1] : pos[3 * p];
+    const float second = ax == 3 ? pos[3 * p + 1] : pos[3 * p + 2];
+    double d1 = fabs(__dsub_rn((double) first, key));
+    if (d1 > 0.5 * box) d1 = __dsub_rn(box, d1);
+    double d2 = fabs(__dsub_rn((double) second, lp2));
+    if (d2 > 0.5 * box) d2 = __dsub_rn(box, d2);
+    return __dadd_rn(__dmul_rn(d1, d1), __dmul_rn(d2, d2));
+}
+
+// One CTA per sightline: bitonic sort of its particle list in shared memory (ascending particle
+// index = std::map iteration order, part_int.cpp:35), then dr^2 for each entry.
+__global__ void __launch_bounds__(256) k_sort_lists(const int64_t *__restrict__ offsets, int32_t *__restrict__ particle,
+                                                    double *__restrict__ dr2, const float *__restrict__ pos,
+                                                    const double *__restrict__ cofm, const int32_t *__restrict__ axis,
+                                                    double box, int cap /* power of two >= longest in-smem list */)
+{
+    extern __shared__ int32_t s_key[];
+    const int l = blockIdx.x;
+    const int64_t beg = offsets[l];
+    const int n = (int) (offsets[l + 1] - beg);
+    if (n == 0) return;
+    if (n <= cap) {
+        int m = 1;
+        while (m < n) m <<= 1;
+        for (int i = threadIdx.x; i < m; i += blockDim.x) s_key[i] = i < n ? particle[beg + i] : INT32_MAX;
+        __syncthreads();
+        for (int k = 2; k <= m; k <<= 1)
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int i = threadIdx.x; i < m; i += blockDim.x) {
+                    const int ixj = i ^ j;
+                    if (ixj > i) {
+                        const int32_t a = s_key[i], b = s_key[ixj];
+                        const bool up = (i & k) == 0;
+                        if ((a > b) == up) {
+                            s_key[i] = b;
+                            s_key[ixj] = a;
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+        const int ax = axis[l];
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const int32_t p = s_key[i];
+            particle[beg + i] = p;
+            dr2[beg + i] = pair_dr2(pos, p, cofm, l, ax, box);
+        }
+    }
+}
+
+// Lists longer than the shared-memory capacity (a single line through > 32768 particles; rare):
+// one CTA runs the same network in global memory over a copy padded to a power of two.
+__global__ void __launch_bounds__(1024) k_bitonic_global(int32_t *__restrict__ a, int64_t m)
+{
+    for (int64_t k = 2; k <= m; k <<= 1)
+        for (int64_t j = k >> 1; j > 0; j >>= 1) {
+            for (int64_t i = threadIdx.x; i < m; i += blockDim.x) {
+                const int64_t ixj = i ^ j;
+                if (ixj > i) {
+                    const int32_t x = a[i], y = a[ixj];
+                    const bool up = (i & k) == 0;
+                    if ((x > y) == up) {
+                        a[i] = y;
+                        a[ixj] = x;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+}
+
+__global__ void k_dr2_of_list(const int32_t *__restrict__ particle, double *__restrict__ dr2, int64_t n,
+                              const float *__restrict__ pos, const double *__restrict__ cofm,
+                              const int32_t *__restrict__ axis, int line, double box)
+{
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dr2[i] = pair_dr2(pos, particle[i], cofm, line, axis[line], box);
+}
+
+// Flag compaction for near_lines: per-block popcounts, then ordered scatter.
+__global__ void __launch_bounds__(1024) k_flag_block_counts(const uint8_t *__restrict__ flag, int64_t npart,
+                                                            int32_t *__restrict__ block_count)
+{
+    __shared__ int warp_cnt[32];
+    const int64_t p = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    const bool f = p < npart && flag[p];
+    const unsigned b = __ballot_sync(0xffffffffu, f);
+    if ((threadIdx.x & 31) == 0) warp_cnt[threadIdx.x >> 5] = __popc(b);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < 32; ++w) t += warp_cnt[w];
+        block_count[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(1024) k_flag_compact(const uint8_t *__restrict__ flag, int64_t npart,
+                                                       const int64_t *__restrict__ block_start,
+                                                       int32_t *__restrict__ out)
+{
+    __shared__ int warp_cnt[32];
+    const int64_t p = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    const bool f = p < npart && flag[p];
+    const unsigned b = __ballot_sync(0xffffffffu, f);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) warp_cnt[wid] = __popc(b);
+    __syncthreads();
+    int before = 0;
+    for (int w = 0; w < wid; ++w) before += warp_cnt[w];
+    if (f) out[block_start[blockIdx.x] + before + __popc(b & ((1u << lane) - 1u))] = (int32_t) p;
+}
+
+struct BuiltTable {
+    Scratch cell_start, line_id, key, proj2;
+    LineTable T;
+};
+
+// Bin the sightlines of each axis group on its perpendicular grid.
+int build_line_table(double box, const double *cofm, const int32_t *axis, int32_t nlos, cudaStream_t stream,
+                     BuiltTable &bt)
+{
+    // group sizes are needed on the host to pick the grids
+    std::vector<int32_t> h_axis(nlos > 0 ? nlos : 1);
+    FSB_CUDA_TRY(cudaMemcpyAsync(h_axis.data(), axis, sizeof(int32_t) * (size_t) nlos, cudaMemcpyDeviceToHost, stream));
+    FSB_CUDA_TRY(cudaStreamSynchronize(stream));
+    int64_t ngrp[3] = {0, 0, 0};
+    for (int32_t i = 0; i < nlos; ++i) {
+        if (h_axis[i] < 1 || h_axis[i] > 3) {
+            set_error("axis[%d] = %d: sightline axes are 1-based, 1..3 (spectra.py:681-683)", i, h_axis[i]);
+            return FSB_EINVAL;
+        }
+        ngrp[h_axis[i] - 1]++;
+    }
+    int32_t total_cells = 0;
+    for (int g = 0; g < 3; ++g) {
+        AxisGrid &ag = bt.T.grid[g];
+        if (ngrp[g] == 0) {
+            ag.G = 0;
+            ag.cell_base = total_cells;
+            ag.inv_cs = 0;
+            continue;
+        }
+        int G = (int) ceil(sqrt((double) ngrp[g]));
+        G = std::max(1, std::min(G, kMaxGrid));
+        ag.G = G;
+        ag.cell_base = total_cells;
+        ag.inv_cs = (double) G / box;
+        total_cells += G * G;
+    }
+    Scratch cell_of_line, cell_count, cursor;
+    FSB_TRY(cell_of_line.alloc(sizeof(int32_t) * (size_t) std::max(nlos, 1), stream));
+    FSB_TRY(cell_count.alloc(sizeof(int32_t) * (size_t) (total_cells + 1), stream));
+    FSB_TRY(cursor.alloc(sizeof(int32_t) * (size_t) (total_cells + 1), stream));
+    FSB_TRY(bt.cell_start.alloc(sizeof(int32_t) * (size_t) (total_cells + 2), stream));
+    FSB_TRY(bt.line_id.alloc(sizeof(int32_t) * (size_t) std::max(nlos, 1), stream));
+    FSB_TRY(bt.key.alloc(sizeof(double) * (size_t) std::max(nlos, 1), stream));
+    FSB_TRY(bt.proj2.alloc(sizeof(double) * (size_t) std::max(nlos, 1), stream));
+    FSB_CUDA_TRY(cudaMemsetAsync(cell_count.ptr, 0, sizeof(int32_t) * (size_t) (total_cells + 1), stream));
+    FSB_CUDA_TRY(cudaMemsetAsync(cursor.ptr, 0, sizeof(int32_t) * (size_t) (total_cells + 1), stream));
+    if (nlos > 0) {
+        const int threads = 256, blocks = (nlos + threads - 1) / threads;
+        k_line_cells<<<blocks, threads, 0, stream>>>(cofm, axis, nlos, bt.T.grid[0], bt.T.grid[1], bt.T.grid[2],
+                                                     cell_of_line.as<int32_t>(), cell_count.as<int32_t>());
+        k_scan_single<int32_t, int32_t><<<1, 1024, 0, stream>>>(cell_count.as<int32_t>(), bt.cell_start.as<int32_t>(),
+                                                                 total_cells, nullptr);
+        k_line_scatter<<<blocks, threads, 0, stream>>>(cofm, axis, nlos, cell_of_line.as<int32_t>(),
+                                                       bt.cell_start.as<int32_t>(), cursor.as<int32_t>(),
+                                                       bt.line_id.as<int32_t>(), bt.key.as<double>(), bt.proj2.as<double>());
+        FSB_CUDA_TRY(cudaGetLastError());
+    } else {
+        FSB_CUDA_TRY(cudaMemsetAsync(bt.cell_start.ptr, 0, sizeof(int32_t) * (size_t) (total_cells + 2), stream));
+    }
+    bt.T.cell_start = bt.cell_start.as<int32_t>();
+    bt.T.line_id = bt.line_id.as<int32_t>();
+    bt.T.key = bt.key.as<double>();
+    bt.T.proj2 = bt.proj2.as<double>();
+    bt.T.box = box;
+    return FSB_OK;
+}
+
+}  // namespace
+
+}  // namespace fsb
+
+using namespace fsb;
+
+static int index_build_impl(fsb_index *idx, double box, const double *cofm, const int32_t *axis, int32_t nlos,
+                            const float *pos, const float *h, int64_t npart, cudaStream_t stream)
+{
+    const size_t nl = (size_t) std::max(nlos, 1);
+    FSB_CUDA_TRY(cudaMallocAsync(&idx->offsets, sizeof(int64_t) * (nl + 1), stream));
+    FSB_CUDA_TRY(cudaMallocAsync(&idx->cofm, sizeof(double) * 3 * nl, stream));
+    FSB_CUDA_TRY(cudaMallocAsync(&idx->axis, sizeof(int32_t) * nl, stream));
+    if (nlos > 0) {
+        FSB_CUDA_TRY(cudaMemcpyAsync(idx->cofm, cofm, sizeof(double) * 3 * (size_t) nlos, cudaMemcpyDeviceToDevice, stream));
+        FSB_CUDA_TRY(cudaMemcpyAsync(idx->axis, axis, sizeof(int32_t) * (size_t) nlos, cudaMemcpyDeviceToDevice, stream));
+    }
+
+    BuiltTable bt;
+    FSB_TRY(build_line_table(box, cofm, axis, nlos, stream, bt));
+
+    Scratch count, max_list;
+    FSB_TRY(count.alloc(sizeof(int32_t) * (nl + 1), stream));
+    FSB_TRY(max_list.alloc(sizeof(int64_t), stream));
+    FSB_CUDA_TRY(cudaMemsetAsync(count.ptr, 0, sizeof(int32_t) * (nl + 1), stream));
+    const int threads = 256;
+    const unsigned pblocks = (unsigned) ((npart + threads - 1) / threads);
+    if (npart > 0 && nlos > 0) {
+        k_pairs<0><<<pblocks, threads, 0, stream>>>(bt.T, pos, h, npart, count.as<int32_t>(), nullptr, nullptr, nullptr);
+        FSB_CUDA_TRY(cudaGetLastError());
+    }
+    k_scan_single<int32_t, int64_t><<<1, 1024, 0, stream>>>(count.as<int32_t>(), idx->offsets, nlos, max_list.as<int64_t>());
+    FSB_CUDA_TRY(cudaGetLastError());
+    int64_t h_total = 0, h_max = 0;
+    FSB_CUDA_TRY(cudaMemcpyAsync(&h_total, idx->offsets + nlos, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
+    FSB_CUDA_TRY(cudaMemcpyAsync(&h_max, max_list.ptr, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
+    FSB_CUDA_TRY(cudaStreamSynchronize(stream));
+    idx->npairs = h_total;
+    idx->max_list = h_max;
+
+    const size_t np = (size_t) std::max<int64_t>(idx->npairs, 1);
+    FSB_CUDA_TRY(cudaMallocAsync(&idx->particle, sizeof(int32_t) * np, stream));
+    FSB_CUDA_TRY(cudaMallocAsync(&idx->dr2, sizeof(double) * np, stream));
+    if (idx->npairs == 0) return FSB_OK;
+
+    FSB_CUDA_TRY(cudaMemsetAsync(count.ptr, 0, sizeof(int32_t) * (nl + 1), stream));
+    k_pairs<1><<<pblocks, threads, 0, stream>>>(bt.T, pos, h, npart, count.as<int32_t>(), idx->offsets, idx->particle, nullptr);
+    FSB_CUDA_TRY(cudaGetLastError());
+    // in-smem sort capacity: next power of two of the longest list, at most 32768 entries (128 KB)
+    int cap = 32;
+    while (cap < idx->max_list && cap < 32768) cap <<= 1;
+    const size_t smem = sizeof(int32_t) * (size_t) cap;
+    FSB_CUDA_TRY(cudaFuncSetAttribute(k_sort_lists, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    k_sort_lists<<<nlos, 256, smem, stream>>>(idx->offsets, idx->particle, idx->dr2, pos, idx->cofm, idx->axis, box, cap);
+    FSB_CUDA_TRY(cudaGetLastError());
+    if (idx->max_list > cap) {
+        std::vector<int64_t> h_off((size_t) nlos + 1);
+        FSB_CUDA_TRY(cudaMemcpyAsync(h_off.data(), idx->offsets, sizeof(int64_t) * ((size_t) nlos + 1), cudaMemcpyDeviceToHost, stream));
+        FSB_CUDA_TRY(cudaStreamSynchronize(stream));
+        for (int32_t l = 0; l < nlos; ++l) {
+            const int64_t n = h_off[l + 1] - h_off[l];
+            if (n <= cap) continue;
+            int64_t m = 1;
+            while (m < n) m <<= 1;
+            Scratch pad;
+            FSB_TRY(pad.alloc(sizeof(int32_t) * (size_t) m, stream));
+            FSB_CUDA_TRY(cudaMemsetAsync(pad.ptr, 0x7f, sizeof(int32_t) * (size_t) m, stream));  // 0x7f7f7f7f > any index
+            FSB_CUDA_TRY(cudaMemcpyAsync(pad.ptr, idx->particle + h_off[l], sizeof(int32_t) * (size_t) n, cudaMemcpyDeviceToDevice, stream));
+            k_bitonic_global<<<1, 1024, 0, stream>>>(pad.as<int32_t>(), m);
+            FSB_CUDA_TRY(cudaMemcpyAsync(idx->particle + h_off[l], pad.ptr, sizeof(int32_t) * (size_t) n, cudaMemcpyDeviceToDevice, stream));
+            k_dr2_of_list<<<(unsigned) ((n + 255) / 256), 256, 0, stream>>>(idx->particle + h_off[l], idx->dr2 + h_off[l], n, pos,
+                                                                           idx->cofm, idx->axis, l, box);
+            FSB_CUDA_TRY(cudaGetLastError());
+        }
+    }
+    return FSB_OK;
+}
+
+extern "C" int fsb_index_build(double box, const double *cofm, const int32_t *axis, int32_t nlos, const float *pos,
+                               const float *h, int64_t npart, void *stream_v, fsb_index **out)
+{
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    FSB_REQUIRE(out != nullptr, "out is NULL");
+    *out = nullptr;
+    FSB_REQUIRE(nlos >= 0 && npart >= 0, "negative size");
+    FSB_REQUIRE(npart <= (int64_t) INT32_MAX, "npart exceeds int32 particle indices (index_table.cpp:145 uses int)");
+    FSB_REQUIRE(box > 0, "box must be positive");
+    FSB_REQUIRE(nlos == 0 || (cofm && axis), "cofm/axis NULL");
+    FSB_REQUIRE(npart == 0 || (pos && h), "pos/h NULL");
+    fsb_index *idx = new fsb_index();
+    idx->nlos = nlos;
+    idx->npart = npart;
+    idx->box = box;
+    const int rc = index_build_impl(idx, box, cofm, axis, nlos, pos, h, npart, stream);
+    if (rc != FSB_OK) {
+        fsb_index_free(idx, stream);
+        return rc;
+    }
+    *out = idx;
+    return FSB_OK;
+}
+
+extern "C" int fsb_index_free(fsb_index *idx, void *stream_v)
+{
+    if (!idx) return FSB_OK;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    void *ptrs[] = {idx->offsets, idx->particle, idx->dr2, idx->cofm, idx->axis};
+    for (void *p : ptrs)
+        if (p) cudaFreeAsync(p, stream);
+    delete idx;
+    return FSB_OK;
+}
+
+extern "C" int fsb_index_sizes(const fsb_index *idx, int32_t *nlos, int64_t *npairs, int64_t *max_list)
+{
+    FSB_REQUIRE(idx != nullptr, "index is NULL");
+    if (nlos) *nlos = idx->nlos;
+    if (npairs) *npairs = idx->npairs;
+    if (max_list) *max_list = idx->max_list;
+    return FSB_OK;
+}
+
+extern "C" int fsb_index_export(const fsb_index *idx, int64_t *offsets, int32_t *particle, double *dr2, void *stream_v)
+{
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    FSB_REQUIRE(idx != nullptr, "index is NULL");
+    if (offsets)
+        FSB_CUDA_TRY(cudaMemcpyAsync(offsets, idx->offsets, sizeof(int64_t) * ((size_t) idx->nlos + 1), cudaMemcpyDeviceToDevice, stream));
+    if (particle && idx->npairs > 0)
+        FSB_CUDA_TRY(cudaMemcpyAsync(particle, idx->particle, sizeof(int32_t) * (size_t) idx->npairs, cudaMemcpyDeviceToDevice, stream));
+    if (dr2 && idx->npairs > 0)
+        FSB_CUDA_TRY(cudaMemcpyAsync(dr2, idx->dr2, sizeof(double) * (size_t) idx->npairs, cudaMemcpyDeviceToDevice, stream));
+    return FSB_OK;
+}
+
+extern "C" int fsb_near_lines(double box, const float *pos, const float *h, int64_t npart, const int32_t *axis,
+                              const double *cofm, int32_t nlos, int32_t *out_index, int64_t *count, void *stream_v)
+{
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    FSB_REQUIRE(count != nullptr, "count is NULL");
+    *count = 0;
+    FSB_REQUIRE(nlos >= 0 && npart >= 0, "negative size");
+    FSB_REQUIRE(npart <= (int64_t) INT32_MAX, "npart exceeds int32 particle indices");
+    FSB_REQUIRE(box > 0, "box must be positive");
+    if (npart == 0 || nlos == 0) return FSB_OK;
+    FSB_REQUIRE(pos && h && axis && cofm && out_index, "NULL array");
+    BuiltTable bt;
+    FSB_TRY(build_line_table(box, cofm, axis, nlos, stream, bt));
+    Scratch flag, block_count, block_start;
+    const int threads = 1024;
+    const int64_t nblocks = (npart + threads - 1) / threads;
+    FSB_TRY(flag.alloc((size_t) npart, stream));
+    FSB_TRY(block_count.alloc(sizeof(int32_t) * (size_t) (nblocks + 1), stream));
+    FSB_TRY(block_start.alloc(sizeof(int64_t) * (size_t) (nblocks + 1), stream));
+    k_pairs<2><<<(unsigned) ((npart + 255) / 256), 256, 0, stream>>>(bt.T, pos, h, npart, nullptr, nullptr, nullptr, flag.as<uint8_t>());
+    k_flag_block_counts<<<(unsigned) nblocks, threads, 0, stream>>>(flag.as<uint8_t>(), npart, block_count.as<int32_t>());
+    k_scan_single<int32_t, int64_t><<<1, 1024, 0, stream>>>(block_count.as<int32_t>(), block_start.as<int64_t>(), nblocks, nullptr);
+    k_flag_compact<<<(unsigned) nblocks, threads, 0, stream>>>(flag.as<uint8_t>(), npart, block_start.as<int64_t>(), out_index);
+    FSB_CUDA_TRY(cudaGetLastError());
+    FSB_CUDA_TRY(cudaMemcpyAsync(count, block_start.as<int64_t>() + nblocks, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
+    FSB_CUDA_TRY(cudaStreamSynchronize(stream));
+    return FSB_OK;
+}

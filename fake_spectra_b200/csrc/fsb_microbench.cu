@@ -1,0 +1,64 @@
+// Roofline denominators measured on the box: sustained FP64 / FP32 FMA issue rate of the device.
+// (MEASURED_PEAKS.json only carries HBM copy bandwidth and bf16 GEMM throughput; the tau kernel is
+// bound by the FP64 pipe)
+#include "fsb_common.cuh"
+
+namespace fsb {
+namespace {
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_fma_peak(T *out, int iters, T a, T b)
+{
+    T x0 = (T) threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+        #pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            x0 = x0 * a + b; x1 = x1 * a + b; x2 = x2 * a + b; x3 = x3 * a + b;
+            x4 = x4 * a + b; x5 = x5 * a + b; x6 = x6 * a + b; x7 = x7 * a + b;
+        }
+    }
+    const T s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+    if (s == (T) 123456789) out[0] = s;  // never true; keeps the chain alive
+}
+
+template <typename T>
+int measure(double *tflops, double seconds_target, cudaStream_t stream)
+{
+    int sms = 0, dev = 0;
+    FSB_CUDA_TRY(cudaGetDevice(&dev));
+    FSB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    Scratch out;
+    FSB_TRY(out.alloc(sizeof(T) * 8, stream));
+    cudaEvent_t e0, e1;
+    FSB_CUDA_TRY(cudaEventCreate(&e0));
+    FSB_CUDA_TRY(cudaEventCreate(&e1));
+    const int blocks = sms * 8, threads = 256;
+    int iters = 2000;
+    double best = 0;
+    for (int rep = 0; rep < 6; ++rep) {
+        FSB_CUDA_TRY(cudaEventRecord(e0, stream));
+        k_fma_peak<T><<<blocks, threads, 0, stream>>>(out.as<T>(), iters, (T) 1.0000001, (T) 1e-9);
+        FSB_CUDA_TRY(cudaEventRecord(e1, stream));
+        FSB_CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0;
+        FSB_CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = 2.0 * 64.0 * (double) iters * (double) blocks * (double) threads;
+        const double tf = flops / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+        if (ms * 1e-3 < seconds_target / 4) iters *= 2;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *tflops = best;
+    return FSB_OK;
+}
+
+}  // namespace
+}  // namespace fsb
+
+extern "C" FSB_API int fsb_measure_fma_peak(int32_t fp64, double *tflops, void *stream)
+{
+    FSB_REQUIRE(tflops != nullptr, "tflops is NULL");
+    return fp64 ? fsb::measure<double>(tflops, 0.2, static_cast<cudaStream_t>(stream))
+                : fsb::measure<float>(tflops, 0.2, static_cast<cudaStream_t>(stream));
+}

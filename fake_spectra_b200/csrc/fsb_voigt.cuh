@@ -1,0 +1,162 @@
+// Device Voigt profile H(a,u) = Re w(u + i a), a >= 0  (consumer: singleabs.h:56-61).
+//
+// voigt_exact : restatement of the reference's Faddeeva::w real part (Faddeeva.cpp:679-971,
+//               relerr = DBL_EPSILON branch) — the parity anchor for every other strategy.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <float.h>
+#include <math.h>
+
+namespace fsb {
+
+// exp(-a2 n^2), a2 = 0.268657157075235951582, n = 1..51, then 0 (generated with mpmath, 40 digits).
+// Same role as the expa2n2 table of Faddeeva.cpp:622-675; the trailing zero also terminates the
+// series loops once every term has underflowed.
+__constant__ double c_expa2n2[52] = {
+    7.64405281671221563e-1, 3.41424527166548425e-1, 8.91072646929412548e-2,
+    1.35887299055460086e-2, 1.21085455253437481e-3, 6.30452613933449404e-5,
+    1.91805156577114683e-6, 3.40969447714832381e-8, 3.54175089099469393e-10,
+    2.14965079583260681e-12, 7.62368911833724355e-15, 1.57982797110681093e-17,
+    1.91294189103582676e-20, 1.3534465676420534e-23, 5.59535712428588719e-27,
+    1.35164257972401769e-30, 1.90784582843501168e-34, 1.5735192029144293e-38,
+    7.58312432328032848e-43, 2.13536275438697082e-47, 3.5135206378719577e-52,
+    3.37800830266396921e-57, 1.89769439468301001e-62, 6.22929926072668851e-68,
+    1.19481172006938723e-73, 1.33908181133005952e-79, 8.76924303483223948e-86,
+    3.35555576166254989e-92, 7.50264110688173025e-99, 9.80192200745410261e-106,
+    7.48265412822268965e-113, 3.33770122566809428e-120, 8.69934598159861142e-128,
+    1.32486951484088855e-135, 1.17898144201315251e-143, 6.13039120236180011e-152,
+    1.862587859508221e-160, 3.30668408201432789e-169, 3.43017280887946242e-178,
+    2.07915397775808218e-187, 7.3638454532398496e-197, 1.52394760394085743e-206,
+    1.84281935046532101e-216, 1.30209553802992926e-226, 5.37588903521080535e-237,
+    1.29689584599763147e-247, 1.82813078022866562e-258, 1.50576355348684241e-269,
+    7.24692320799294216e-281, 2.03797051314726835e-292, 3.34880215927873805e-304,
+    0.0};
+
+__device__ __forceinline__ double sinc_of(double x, double sinx)  // Faddeeva.cpp:609-611
+{
+    return fabs(x) < 1e-4 ? 1 - 0.1666666666666666666667 * x * x : sinx / x;
+}
+
+// Re w(xin + i y) for y >= 0.  erfcx_y = erfcx(y) is a per-particle constant, hoisted by callers
+// (the reference recomputes it per call, Faddeeva.cpp:905-907).
+__device__ double voigt_exact(double xin, double y, double erfcx_y)
+{
+    if (xin == 0.0) return erfcx_y;          // :681-683
+    if (y == 0.0) return exp(-xin * xin);    // :684-686
+    const double a = 0.518321480430085929872;
+    const double c = 0.329973702884629072537;
+    const double a2 = 0.268657157075235951582;
+    const double relerr = DBL_EPSILON;
+    const double x = fabs(xin);
+    double ret;
+    double sum1 = 0, sum2 = 0, sum3 = 0, sum5 = 0;
+
+    if (y > 7 || (x > 6 && (y > 0.1 || (x > 8 && y > 1e-10) || x > 28))) {  // :712-717
+        const double ispi = 0.56418958354775628694807945156;
+        if (x + y > 4000) {
+            if (x + y > 1e7) {  // w(z) ~ i/sqrt(pi)/z
+                if (x > y) {
+                    const double yax = y / x;
+                    const double denom = ispi / (x + yax * y);
+                    return denom * yax;
+                }
+                if (isinf(y)) return isnan(x) ? nan("") : 0.0;
+                const double xya = x / y;
+                return ispi / (xya * x + y);
+            }
+            const double dr = x * x - y * y - 0.5, di = 2 * x * y;
+            const double denom = ispi / (dr * dr + di * di);
+            return denom * (x * di - y * dr);
+        }
+        // Laplace continued fraction with the fitted term count nu(z), :758-772
+        double nu = floor(3.9 + 11.398 / (0.08254 * x + 0.1421 * y + 0.2023));
+        double wr = x, wi = y;
+        for (nu = 0.5 * (nu - 1); nu > 0.4; nu -= 0.5) {
+            const double denom = nu / (wr * wr + wi * wi);
+            wr = x - wr * denom;
+            wi = y + wi * denom;
+        }
+        const double denom = ispi / (wr * wr + wi * wi);
+        return denom * wi;
+    } else if (x < 10) {  // Algorithm-916 style exponential sums, :816-922
+        double prod2ax = 1, prodm2ax = 1;
+        double expx2;
+        if (isnan(y)) return y;
+        if (x < 5e-4) {  // :828-851
+            const double x2 = x * x;
+            expx2 = 1 - x2 * (1 - 0.5 * x2);
+            const double ax2 = 1.036642960860171859744 * x;
+            const double exp2ax = 1 + ax2 * (1 + ax2 * (0.5 + 0.166666666666666666667 * ax2));
+            const double expm2ax = 1 - ax2 * (1 - ax2 * (0.5 - 0.166666666666666666667 * ax2));
+            for (int n = 1;; ++n) {
+                const double coef = c_expa2n2[n - 1] * expx2 / (a2 * (n * n) + y * y);
+                prod2ax *= exp2ax;
+                prodm2ax *= expm2ax;
+                sum1 += coef;
+                sum2 += coef * prodm2ax;
+                sum3 += coef * prod2ax;
+                if (coef * prod2ax < relerr * sum3 || n >= 52) break;
+            }
+        } else {  // :852-867 — terminates on sum5 although only sum1..3 enter Re w
+            expx2 = exp(-x * x);
+            const double exp2ax = exp((2 * a) * x), expm2ax = 1 / exp2ax;
+            for (int n = 1;; ++n) {
+                const double coef = c_expa2n2[n - 1] * expx2 / (a2 * (n * n) + y * y);
+                prod2ax *= exp2ax;
+                prodm2ax *= expm2ax;
+                sum1 += coef;
+                sum2 += coef * prodm2ax;
+                sum3 += coef * prod2ax;
+                sum5 += (coef * prod2ax) * (a * n);
+                if ((coef * prod2ax) * (a * n) < relerr * sum5 || n >= 52) break;
+            }
+        }
+        const double expx2erfcxy = expx2 * erfcx_y;  // :905-907 (y > -6 always here)
+        if (y > 5) {  // :908-912
+            const double sinxy = sin(x * y);
+            ret = (expx2erfcxy - c * y * sum1) * cos(2 * x * y) + (c * x * expx2) * sinxy * sinc_of(x * y, sinxy);
+        } else {  // :913-921 (real part is even in x)
+            const double sinxy = sin(x * y);
+            const double cos2xy = cos(2 * x * y);
+            const double coef1 = expx2erfcxy - c * y * sum1;
+            const double coef2 = c * x * expx2;
+            ret = coef1 * cos2xy + coef2 * sinxy * sinc_of(x * y, sinxy);
+        }
+    } else {  // x >= 10 with y <= 1e-10: :923-967
+        if (isnan(x)) return x;
+        if (isnan(y)) return y;
+        ret = exp(-x * x);
+        const double n0 = floor(x / a + 0.5);
+        const double dx = a * n0 - x;
+        sum3 = exp(-dx * dx) / (a2 * (n0 * n0) + y * y);
+        sum5 = a * n0 * sum3;
+        const double exp1 = exp(4 * a * dx);
+        double exp1dn = 1;
+        int dn;
+        bool done = false;
+        for (dn = 1; n0 - dn > 0; ++dn) {
+            const double np = n0 + dn, nm = n0 - dn;
+            double tp = exp(-(a * dn + dx) * (a * dn + dx));
+            double tm = tp * (exp1dn *= exp1);
+            tp /= (a2 * (np * np) + y * y);
+            tm /= (a2 * (nm * nm) + y * y);
+            sum3 += tp + tm;
+            sum5 += a * (np * tp + nm * tm);
+            if (a * (np * tp + nm * tm) < relerr * sum5) {
+                done = true;
+                break;
+            }
+        }
+        while (!done) {
+            const double np = n0 + dn++;
+            const double tp = exp(-(a * dn + dx) * (a * dn + dx)) / (a2 * (np * np) + y * y);
+            sum3 += tp;
+            sum5 += a * np * tp;
+            if (a * np * tp < relerr * sum5) done = true;
+        }
+    }
+    return ret + (0.5 * c) * y * (sum2 + sum3);  // :968-970
+}
+
+}  // namespace fsb

@@ -1,0 +1,159 @@
+"""Device-resident interface to libfsb200.so: torch CUDA tensors in, torch CUDA tensors out.
+
+PyTorch is used only for device buffers and streams; all compute is in the library's own
+sm_100a kernels.  This layer lets callers keep particles and results resident in HBM and reuse
+one candidate index for several quantities (tau of several lines, column density, weighted
+fields), which the one-shot boundary in :mod:`_spectra_priv` cannot.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+
+def _dptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need(t, dtype, name):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == dtype and t.is_contiguous()):
+        raise TypeError("%s must be a contiguous CUDA tensor of dtype %s" % (name, dtype))
+    return t
+
+
+class CandidateIndex:
+    """Per-sightline candidate particle lists (replaces IndexTable + get_near_particles)."""
+
+    def __init__(self, box, cofm, axis, pos, h):
+        self.lib = _lib.load()
+        self.box = float(box)
+        _need(cofm, torch.float64, "cofm"), _need(axis, torch.int32, "axis")
+        _need(pos, torch.float32, "pos"), _need(h, torch.float32, "h")
+        self.nlos = cofm.shape[0]
+        self.npart = pos.shape[0]
+        self.device = pos.device
+        handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            rc = self.lib.fsb_index_build(self.box, _dptr(cofm), _dptr(axis), self.nlos, _dptr(pos), _dptr(h),
+                                          self.npart, _stream(), C.byref(handle))
+        _lib.check(rc, "fsb_index_build")
+        self.handle = handle
+        nlos, npairs, mx = C.c_int32(), C.c_int64(), C.c_int64()
+        _lib.check(self.lib.fsb_index_sizes(self.handle, C.byref(nlos), C.byref(npairs), C.byref(mx)), "fsb_index_sizes")
+        self.npairs, self.max_list = npairs.value, mx.value
+
+    def export(self):
+        """(offsets int64[nlos+1], particle int32[npairs], dr2 float64[npairs]) as CUDA tensors."""
+        off = torch.empty(self.nlos + 1, dtype=torch.int64, device=self.device)
+        part = torch.empty(max(self.npairs, 1), dtype=torch.int32, device=self.device)
+        dr2 = torch.empty(max(self.npairs, 1), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.fsb_index_export(self.handle, _dptr(off), _dptr(part), _dptr(dr2), _stream()),
+                       "fsb_index_export")
+        return off, part[:self.npairs], dr2[:self.npairs]
+
+    def free(self):
+        if getattr(self, "handle", None):
+            with torch.cuda.device(self.device):
+                self.lib.fsb_index_free(self.handle, _stream())
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    # -- accumulation --------------------------------------------------------------------------
+    def compute_tau(self, params, pos, vel, dens, temp, h, out=None, counters=None):
+        """params: one _lib.Params or a list of them (fused lines of one ion).
+        Returns float64 [nlos, nbins] (or [nlines, nlos, nbins]); accumulates into ``out`` if given."""
+        plist = params if isinstance(params, (list, tuple)) else [params]
+        nbins = plist[0].nbins
+        shape = (len(plist), self.nlos, nbins)
+        if out is None:
+            out = torch.zeros(shape, dtype=torch.float64, device=self.device)
+        arr = (_lib.Params * len(plist))(*plist)
+        with torch.cuda.device(self.device):
+            rc = self.lib.fsb_compute_tau_multi(self.handle, arr, len(plist), _dptr(pos), _dptr(vel), _dptr(dens),
+                                                _dptr(temp), _dptr(h), _dptr(out), _dptr(counters), _stream())
+        _lib.check(rc, "fsb_compute_tau")
+        return out.view(shape) if isinstance(params, (list, tuple)) else out.view(self.nlos, nbins)
+
+    def compute_colden(self, params, pos, dens, h, out=None, counters=None):
+        """dens: float32 [npart] or [nweights, npart].  Returns float64 [nlos, nbins] or
+        [nweights, nlos, nbins]."""
+        nw = 1 if dens.dim() == 1 else dens.shape[0]
+        shape = (nw, self.nlos, params.nbins)
+        if out is None:
+            out = torch.zeros(shape, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = self.lib.fsb_compute_colden(self.handle, C.byref(params), _dptr(pos), _dptr(dens), nw, _dptr(h),
+                                             _dptr(out), _dptr(counters), _stream())
+        _lib.check(rc, "fsb_compute_colden")
+        return out.view(shape) if dens.dim() == 2 else out.view(self.nlos, params.nbins)
+
+    def assign_cells(self, cofm, axis, pos):
+        """Voronoi cell extents, float32 [npairs, 2] (replaces IndexTable::assign_cells)."""
+        cells = torch.empty((max(self.npairs, 1), 2), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = self.lib.fsb_assign_cells(self.handle, self.box, _dptr(cofm), _dptr(axis), _dptr(pos), _dptr(cells),
+                                           _stream())
+        _lib.check(rc, "fsb_assign_cells")
+        return cells[:self.npairs]
+
+
+def particle_interpolate(compute_tau, params, pos, vel, dens, temp, h, axis, cofm, out=None):
+    """One-shot device call (index build + accumulation), device tensors in and out."""
+    lib = _lib.load()
+    nlos = cofm.shape[0]
+    if out is None:
+        out = torch.zeros((nlos, params.nbins), dtype=torch.float64, device=pos.device)
+    with torch.cuda.device(pos.device):
+        rc = lib.fsb_particle_interpolate(1 if compute_tau else 0, C.byref(params), _dptr(pos), _dptr(vel), _dptr(dens),
+                                          _dptr(temp), _dptr(h), pos.shape[0], _dptr(axis), _dptr(cofm), nlos,
+                                          _dptr(out), _stream())
+    _lib.check(rc, "fsb_particle_interpolate")
+    return out
+
+
+def near_lines(box, pos, h, axis, cofm):
+    """Ascending int32 indices (CUDA tensor) of particles near at least one sightline."""
+    lib = _lib.load()
+    out = torch.empty(max(pos.shape[0], 1), dtype=torch.int32, device=pos.device)
+    count = C.c_int64(0)
+    with torch.cuda.device(pos.device):
+        rc = lib.fsb_near_lines(float(box), _dptr(pos), _dptr(h), pos.shape[0], _dptr(axis), _dptr(cofm), cofm.shape[0],
+                                _dptr(out), C.byref(count), _stream())
+    _lib.check(rc, "fsb_near_lines")
+    return out[:count.value]
+
+
+def voigt_profile(x, y, voigt=_lib.VOIGT_FAST):
+    """Re w(x + i y) on the device (test hook)."""
+    lib = _lib.load()
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        rc = lib.fsb_voigt_profile(_dptr(x), _dptr(y), _dptr(out), x.numel(), int(voigt), _stream())
+    _lib.check(rc, "fsb_voigt_profile")
+    return out
+
+
+def device_info():
+    lib = _lib.load()
+    v = [C.c_int32() for _ in range(4)]
+    _lib.check(lib.fsb_device_info(*[C.byref(x) for x in v]), "fsb_device_info")
+    return {"sm_count": v[0].value, "clock_khz": v[1].value, "cc": (v[2].value, v[3].value)}
+
+
+def measure_fma_peak(fp64=True):
+    """Measured FMA throughput (TFLOP/s) of the current device; the tau kernel's roofline peak."""
+    lib = _lib.load()
+    v = C.c_double(0)
+    _lib.check(lib.fsb_measure_fma_peak(1 if fp64 else 0, C.byref(v), _stream()), "fsb_measure_fma_peak")
+    return v.value

@@ -1,0 +1,164 @@
+/* fsb200.h — C ABI of libfsb200.so: the B200-native (sm_100a) replacement for the native hot path
+ * of sbird/fake_spectra.  Plain pointers and sizes only; no torch / Python types.
+ *
+ * Every entry point cites the reference interface it replaces (paths relative to the reference's
+ * fake_spectra/ directory).  Unless a name ends in _host, all array pointers are DEVICE pointers
+ * on the current CUDA device and the call is asynchronous on `stream` (a cudaStream_t passed as
+ * void*; NULL = the legacy default stream) except where noted.  The library never frees or
+ * retains caller memory.  All functions return FSB_OK (0) or a negative FSB_E* code; the
+ * message of the last error on the calling thread is available from fsb_last_error().
+ * The library never calls exit()/abort() (the reference can: index_table.cpp:204-208).
+ */
+#ifndef FSB200_H
+#define FSB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FSB_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define FSB_API __attribute__((visibility("default")))
+#else
+#define FSB_API
+#endif
+
+/* status codes */
+#define FSB_OK 0
+#define FSB_EINVAL (-1)   /* bad argument (shape, kernel id, NULL pointer, nbins <= 0 ...)            */
+#define FSB_ECUDA (-2)    /* a CUDA runtime call or kernel failed; see fsb_last_error()              */
+#define FSB_ENOMEM (-3)   /* device allocation failed                                                */
+#define FSB_EVORONOI (-4) /* Voronoi cell ownership not contiguous (reference: exit(1))              */
+#define FSB_ENODEV (-5)   /* no CUDA device / not an sm_100 device                                   */
+
+/* kernel ids: singleabs.h:9-12 */
+#define FSB_KERNEL_TOPHAT 0
+#define FSB_KERNEL_CUBIC 1
+#define FSB_KERNEL_VORONOI 2
+#define FSB_KERNEL_QUINTIC 3
+
+/* arithmetic of the tau kernel */
+#define FSB_PRECISION_FP64 0 /* parity mode: <= 1e-10 relative to the reference C++               */
+#define FSB_PRECISION_FP32 1 /* fast path: <= 1e-5 absolute on flux exp(-tau)                      */
+
+/* Voigt evaluation strategy (FP64 only) */
+#define FSB_VOIGT_FAST 0     /* this library's own small-y expansion, falls back to EXACT outside its domain */
+#define FSB_VOIGT_EXACT 1    /* operation-for-operation restatement of Faddeeva.cpp:679-971      */
+
+/* Scalars of one absorption line + spectrum geometry.  Same quantities, units and meaning as the
+ * positional arguments of _Particle_Interpolate (py_module.cpp:103-115) and of the
+ * ParticleInterp / LineAbsorption constructors (part_int.h:27, absorption.cpp:152-161). */
+typedef struct fsb_params {
+    int32_t nbins;      /* pixels per spectrum                                                    */
+    int32_t kernel;     /* FSB_KERNEL_*                                                           */
+    double box;         /* box size, comoving kpc/h                                               */
+    double velfac;      /* km/s per comoving kpc/h                                                */
+    double atime;       /* scale factor (carried for parity of the argument list; unused)         */
+    double lambda_cm;   /* rest wavelength in cm                                                  */
+    double gamma;       /* damping constant 1/s (0 => pure Gaussian, spectra.py:669-672)          */
+    double fosc;        /* oscillator strength                                                    */
+    double amumass;     /* ion mass in amu                                                        */
+    double tautail;     /* per-particle tau below which the pixel march stops (spectra.py:135)    */
+    int32_t precision;  /* FSB_PRECISION_*                                                        */
+    int32_t voigt;      /* FSB_VOIGT_*                                                            */
+    int32_t seg_pairs;  /* pairs per work item; 0 = choose from the problem size                  */
+    int32_t reserved;
+} fsb_params;
+
+/* Counters a compute call can report (device-resident, uint64 each). */
+typedef struct fsb_counters {
+    uint64_t pairs;     /* candidate pairs visited                                                */
+    uint64_t pixels;    /* pixel contributions added                                              */
+    uint64_t voigt;     /* Voigt profile evaluations (singleabs.h:157 calls)                      */
+    uint64_t lanes;     /* lane-slots spent in the pixel march (pixels + discarded lanes)         */
+} fsb_counters;
+
+/* ---- library ------------------------------------------------------------------------------ */
+FSB_API int fsb_abi_version(void);
+FSB_API const char *fsb_strerror(int code);
+FSB_API const char *fsb_last_error(void);
+/* Device properties the bench reports: SM count, clock (kHz), compute capability major/minor. */
+FSB_API int fsb_device_info(int32_t *sm_count, int32_t *clock_khz, int32_t *cc_major, int32_t *cc_minor);
+
+/* ---- candidate index (replaces IndexTable: index_table.h:10-52) ---------------------------- */
+typedef struct fsb_index fsb_index;
+
+/* IndexTable ctor (index_table.cpp:7-18) + get_near_particles (:130-150).
+ * Builds, for every sightline, the ascending list of particles whose kernel support reaches it
+ * (exact predicate of index_table.cpp:22-113) and the periodic squared impact parameter.
+ * cofm[nlos*3] f64, axis[nlos] i32 (1-based), pos[npart*3] f32, h[npart] f32.
+ * Synchronises `stream` once (the pair count sizes the lists).  Free with fsb_index_free. */
+FSB_API int fsb_index_build(double box, const double *cofm, const int32_t *axis, int32_t nlos,
+                    const float *pos, const float *h, int64_t npart, void *stream, fsb_index **out);
+FSB_API int fsb_index_free(fsb_index *idx, void *stream);
+/* sizes: number of sightlines, total candidate pairs, longest single list */
+FSB_API int fsb_index_sizes(const fsb_index *idx, int32_t *nlos, int64_t *npairs, int64_t *max_list);
+/* Copies the lists out (device to device): offsets[nlos+1] i64, particle[npairs] i32 ascending
+ * within each line (the iteration order of std::map<int,double>, part_int.cpp:35), dr2[npairs] f64
+ * (the map's values).  Any of the three may be NULL. */
+FSB_API int fsb_index_export(const fsb_index *idx, int64_t *offsets, int32_t *particle, double *dr2, void *stream);
+
+/* ---- accumulation (replaces ParticleInterp::compute_tau / compute_colden) ------------------ */
+/* part_int.cpp:20-51.  tau[nlos*nbins] f64 row-major is ACCUMULATED into (callers zero it,
+ * py_module.cpp:194).  vel[npart*3], dens/temp/h[npart] f32.  counters may be NULL. */
+FSB_API int fsb_compute_tau(const fsb_index *idx, const fsb_params *p, const float *pos, const float *vel,
+                    const float *dens, const float *temp, const float *h, double *tau,
+                    fsb_counters *counters, void *stream);
+/* Same geometry, several lines of one ion in ONE pass (Lya+Lyb ...): lines differ only in
+ * lambda_cm, gamma, fosc (p[i].nbins/kernel/box/velfac/amumass/tautail must agree).
+ * tau[nlines][nlos*nbins]. */
+FSB_API int fsb_compute_tau_multi(const fsb_index *idx, const fsb_params *p, int32_t nlines, const float *pos,
+                          const float *vel, const float *dens, const float *temp, const float *h,
+                          double *tau, fsb_counters *counters, void *stream);
+/* part_int.cpp:53-84, with nweights density-like columns sharing one geometry pass
+ * (spectra.py:945-1024 issues one colden call per weight).  dens[nweights][npart] f32,
+ * colden[nweights][nlos*nbins] f64, accumulated into. */
+FSB_API int fsb_compute_colden(const fsb_index *idx, const fsb_params *p, const float *pos, const float *dens,
+                       int32_t nweights, const float *h, double *colden, fsb_counters *counters,
+                       void *stream);
+
+/* ---- one-shot boundary (replaces Py_Particle_Interpolation, py_module.cpp:103-233) --------- */
+/* compute_tau != 0: tau; else column density.  out[nlos*nbins] f64 accumulated into.
+ * vel/temp are ignored (may be NULL) when compute_tau == 0, as in spectra.py:570-571. */
+FSB_API int fsb_particle_interpolate(int32_t compute_tau, const fsb_params *p, const float *pos, const float *vel,
+                             const float *dens, const float *temp, const float *h, int64_t npart,
+                             const int32_t *axis, const double *cofm, int32_t nlos, double *out,
+                             void *stream);
+/* Same with HOST pointers: copies inputs to the device, runs, copies out[nlos*nbins] back
+ * (out is overwritten with the zero-initialised result, like the array the reference returns).
+ * Synchronous.  This is the call the reference's Python binding would make. */
+FSB_API int fsb_particle_interpolate_host(int32_t compute_tau, const fsb_params *p, const float *pos, const float *vel,
+                                  const float *dens, const float *temp, const float *h, int64_t npart,
+                                  const int32_t *axis, const double *cofm, int32_t nlos, double *out);
+
+/* ---- particle filter (replaces Py_near_lines, py_module.cpp:25-99) ------------------------- */
+/* Ascending indices of particles with at least one candidate sightline.  out_index must hold
+ * npart int32 (worst case); *count (HOST) receives the number written.  Synchronises `stream`. */
+FSB_API int fsb_near_lines(double box, const float *pos, const float *h, int64_t npart, const int32_t *axis,
+                   const double *cofm, int32_t nlos, int32_t *out_index, int64_t *count, void *stream);
+FSB_API int fsb_near_lines_host(double box, const float *pos, const float *h, int64_t npart, const int32_t *axis,
+                        const double *cofm, int32_t nlos, int32_t *out_index, int64_t *count);
+
+/* ---- Voronoi cells (replaces IndexTable::assign_cells, index_table.cpp:152-223) ------------ */
+/* cells[2*npairs] f32 in list order: (lo, hi) extent of each candidate's cell along its
+ * sightline, 3*box sentinel when it owns nothing.  Returns FSB_EVORONOI (after finishing all
+ * lines) where the reference would exit(1).  Synchronises `stream`. */
+FSB_API int fsb_assign_cells(const fsb_index *idx, double box, const double *cofm, const int32_t *axis,
+                     const float *pos, float *cells, void *stream);
+
+/* ---- roofline denominators ---------------------------------------------------------------- */
+/* Measured FMA throughput of the current device in TFLOP/s (2 flops per FMA), FP64 if fp64 != 0
+ * else FP32: 8 independent chains per thread, best of several launches.  Synchronous. */
+FSB_API int fsb_measure_fma_peak(int32_t fp64, double *tflops, void *stream);
+
+/* ---- Voigt profile, for tests ------------------------------------------------------------- */
+/* out[i] = Re w(x[i] + i y[i]) (singleabs.h:56-61) with the strategy `voigt` (FSB_VOIGT_*). */
+FSB_API int fsb_voigt_profile(const double *x, const double *y, double *out, int64_t n, int32_t voigt, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FSB200_H */

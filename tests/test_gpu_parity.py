@@ -1,0 +1,247 @@
+"""GPU parity tests: the sm_100a path (through the C ABI of libfsb200.so) against
+ (a) the committed golden fixtures produced by the unmodified reference, and
+ (b) the CPU oracle on fresh seeded inputs.
+
+Tolerances (BASELINE.json north_star / SURVEY section 8d): candidate lists, near_lines, dr^2 and
+Voronoi cell extents bit-exact; tau and column density <= 1e-10 relative on every non-zero pixel
+with an identical zero pattern.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(__file__))
+import cases  # noqa: E402
+from golden import make_golden as mg  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-10
+FIXTURES = [("case_random16.npz", mg.RANDOM16_CONFIGS), ("case_grid12.npz", mg.GRID12_CONFIGS),
+            ("case_edge.npz", mg.EDGE_CONFIGS)]
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    torch.cuda.set_device(0)
+    return torch
+
+
+@pytest.fixture(scope="module")
+def priv():
+    from fake_spectra_b200 import _spectra_priv
+    return _spectra_priv
+
+
+def load(golden_dir, name):
+    z = np.load(os.path.join(golden_dir, name))
+    d = {k: z[k] for k in z.files}
+    d["box"] = float(d["box"])
+    return d
+
+
+def dev(torch, d):
+    return {k: torch.from_numpy(np.ascontiguousarray(d[k])).cuda() for k in ("pos", "vel", "dens", "temp", "h", "cofm", "axis")}
+
+
+def interp(priv, compute_tau, p, d, **kw):
+    return priv._Particle_Interpolate(compute_tau, p["nbins"], p["kernel"], p["box"], p["velfac"], p["atime"],
+                                      p["lambda_cm"], p["gamma"], p["fosc"], p["amumass"], p["tautail"], d["pos"],
+                                      d["vel"], d["dens"], d["temp"], d["h"], d["axis"], d["cofm"], **kw)
+
+
+@pytest.mark.parametrize("name,configs", FIXTURES + [("case_voronoi8.npz", mg.VORONOI_CONFIGS)])
+def test_candidate_lists_golden(torch_cuda, priv, golden_dir, name, configs):
+    from fake_spectra_b200 import native
+    d = load(golden_dir, name)
+    t = dev(torch_cuda, d)
+    idx = native.CandidateIndex(d["box"], t["cofm"], t["axis"], t["pos"], t["h"])
+    off, part, dr2 = (x.cpu().numpy() for x in idx.export())
+    assert np.array_equal(off, d["offsets"])
+    assert np.array_equal(part, d["part"])
+    assert np.array_equal(dr2, d["dr2"])  # bit-exact float64
+    assert np.array_equal(priv._near_lines(d["box"], d["pos"], d["h"], d["axis"], d["cofm"]), d["near_lines"])
+    assert np.array_equal(native.near_lines(d["box"], t["pos"], t["h"], t["axis"], t["cofm"]).cpu().numpy(), d["near_lines"])
+
+
+@pytest.mark.parametrize("voigt", [0, 1])
+@pytest.mark.parametrize("name,configs", FIXTURES)
+def test_tau_colden_golden(priv, golden_dir, name, configs, voigt):
+    d = load(golden_dir, name)
+    for tag, kw in configs.items():
+        p = cases.params(d, **kw)
+        rel, same_zero = cases.rel_err(interp(priv, 1, p, d, voigt=voigt), d["tau_" + tag])
+        assert same_zero and rel < TOL, (name, tag, "tau", rel)
+        if voigt == 0:
+            rel, same_zero = cases.rel_err(interp(priv, 0, p, d), d["colden_" + tag])
+            assert same_zero and rel < TOL, (name, tag, "colden", rel)
+
+
+def test_voronoi_golden(torch_cuda, priv, golden_dir):
+    from fake_spectra_b200 import native
+    d = load(golden_dir, "case_voronoi8.npz")
+    t = dev(torch_cuda, d)
+    idx = native.CandidateIndex(d["box"], t["cofm"], t["axis"], t["pos"], t["h"])
+    cells = idx.assign_cells(t["cofm"], t["axis"], t["pos"]).cpu().numpy()
+    off = d["offsets"]
+    for line in range(d["cofm"].shape[0]):
+        got = cells[off[line]:off[line + 1]].ravel()
+        assert np.array_equal(got, d["cells_%d" % line]), line  # float32 bit-exact
+    p = cases.params(d, **mg.VORONOI_CONFIGS["voronoi_HI1215"])
+    rel, same_zero = cases.rel_err(interp(priv, 1, p, d), d["tau_voronoi_HI1215"])
+    assert same_zero and rel < TOL, rel
+    rel, same_zero = cases.rel_err(interp(priv, 0, p, d), d["colden_voronoi_HI1215"])
+    assert same_zero and rel < TOL, rel
+
+
+@pytest.mark.parametrize("voigt", [0, 1])
+def test_voigt_sweep_golden(torch_cuda, golden_dir, voigt):
+    from fake_spectra_b200 import native
+    z = np.load(os.path.join(golden_dir, "voigt_sweep.npz"))
+    x = torch_cuda.from_numpy(z["x"]).cuda()
+    y = torch_cuda.from_numpy(z["y"]).cuda()
+    got = native.voigt_profile(x, y, voigt=voigt).cpu().numpy()
+    rel, same_zero = cases.rel_err(got, z["h"])
+    assert same_zero and rel < 1e-12, rel
+
+
+@pytest.mark.parametrize("kernel,line,res", [(1, "HI1215", 1.0), (0, "HI1215", 1.0), (3, "CIV1548", 2.5),
+                                             (1, "MgII2796", 10.0), (1, "HI1025", 0.5)])
+def test_tau_colden_vs_oracle(priv, oracle, kernel, line, res):
+    """Fresh inputs, larger than the fixtures (24^3 particles, 96 sightlines on all three axes)."""
+    d = cases.random_case(nside=24, nlos=96, axis="cycle", seed=500 + kernel, los_seed=77)
+    p = cases.params(d, line=line, kernel=kernel, res=res)
+    want = oracle.compute_tau(**p, pos=d["pos"], vel=d["vel"], dens=d["dens"], temp=d["temp"], h=d["h"],
+                              axis=d["axis"], cofm=d["cofm"])
+    rel, same_zero = cases.rel_err(interp(priv, 1, p, d), want)
+    assert same_zero and rel < TOL, rel
+    want = oracle.compute_colden(**p, pos=d["pos"], dens=d["dens"], h=d["h"], axis=d["axis"], cofm=d["cofm"])
+    rel, same_zero = cases.rel_err(interp(priv, 0, p, d), want)
+    assert same_zero and rel < TOL, rel
+
+
+def test_cold_comb_and_dense_wings(priv, oracle):
+    """T = 1 K particles (7 separated spikes: the break rule must stop at the first dip) and very
+    dense particles whose damping wings march the full nbins/2."""
+    d = cases.random_case(nside=12, nlos=30, axis=1, seed=8)
+    d["temp"][::3] = 1.0
+    d["dens"][::7] *= 1e6
+    p = cases.params(d)
+    want = oracle.compute_tau(**p, pos=d["pos"], vel=d["vel"], dens=d["dens"], temp=d["temp"], h=d["h"],
+                              axis=d["axis"], cofm=d["cofm"])
+    rel, same_zero = cases.rel_err(interp(priv, 1, p, d), want)
+    assert same_zero and rel < TOL, rel
+
+
+def test_signed_weights_colden(priv, oracle):
+    d = cases.random_case(nside=12, nlos=30, axis=1, seed=8)
+    rng = np.random.default_rng(0)
+    d["dens"] = (d["dens"] * rng.choice([-1.0, 1.0], d["dens"].size)).astype(np.float32)
+    p = cases.params(d)
+    want = oracle.compute_colden(**p, pos=d["pos"], dens=d["dens"], h=d["h"], axis=d["axis"], cofm=d["cofm"])
+    got = interp(priv, 0, p, d)
+    assert np.max(np.abs(got - want)) <= 1e-12 * np.max(np.abs(want))
+
+
+def test_segmentation_and_determinism(torch_cuda):
+    """A sightline split over several work items gives the same spectrum as one item per line
+    (only the summation tree changes) and repeated runs are bit-identical."""
+    from fake_spectra_b200 import _lib, native
+    d = cases.random_case(nside=16, nlos=20, axis="cycle")
+    t = dev(torch_cuda, d)
+    idx = native.CandidateIndex(d["box"], t["cofm"], t["axis"], t["pos"], t["h"])
+    p = cases.params(d)
+    outs = {}
+    for seg in (1 << 30, 16, 40):
+        prm = _lib.make_params(**p, seg_pairs=seg)
+        a = idx.compute_tau(prm, t["pos"], t["vel"], t["dens"], t["temp"], t["h"]).cpu().numpy()
+        b = idx.compute_tau(prm, t["pos"], t["vel"], t["dens"], t["temp"], t["h"]).cpu().numpy()
+        assert np.array_equal(a, b), "run-to-run determinism, seg=%d" % seg
+        outs[seg] = a
+    for seg in (16, 40):
+        rel, same_zero = cases.rel_err(outs[seg], outs[1 << 30])
+        assert same_zero and rel < 1e-13
+    c0 = idx.compute_colden(_lib.make_params(**p, seg_pairs=1 << 30), t["pos"], t["dens"], t["h"]).cpu().numpy()
+    c1 = idx.compute_colden(_lib.make_params(**p, seg_pairs=8), t["pos"], t["dens"], t["h"]).cpu().numpy()
+    rel, same_zero = cases.rel_err(c1, c0)
+    assert same_zero and rel < 1e-13
+
+
+def test_particle_segments_accumulate(torch_cuda):
+    """Two calls on halves of the particle set accumulating into one array equal one call on all
+    particles (the host sums snapshot segments with +=, reference spectra.py:823)."""
+    from fake_spectra_b200 import _lib, native
+    d = cases.random_case(nside=14, nlos=24, axis="cycle", seed=21)
+    t = dev(torch_cuda, d)
+    prm = _lib.make_params(**cases.params(d))
+    full = native.particle_interpolate(1, prm, t["pos"], t["vel"], t["dens"], t["temp"], t["h"], t["axis"], t["cofm"])
+    n = d["pos"].shape[0] // 2
+    acc = None
+    for sl in (slice(0, n), slice(n, None)):
+        acc = native.particle_interpolate(1, prm, t["pos"][sl].contiguous(), t["vel"][sl].contiguous(),
+                                          t["dens"][sl].contiguous(), t["temp"][sl].contiguous(), t["h"][sl].contiguous(),
+                                          t["axis"], t["cofm"], out=acc)
+    rel, same_zero = cases.rel_err(acc.cpu().numpy(), full.cpu().numpy())
+    assert same_zero and rel < 1e-12
+
+
+def test_weight_columns_share_geometry(torch_cuda):
+    """K weight columns in one colden pass equal K separate passes (get_temp / get_velocity /
+    get_dens_weighted_density issue one call per weight in the reference, spectra.py:945-1024)."""
+    from fake_spectra_b200 import _lib, native
+    d = cases.random_case(nside=14, nlos=24, axis="cycle", seed=22)
+    t = dev(torch_cuda, d)
+    idx = native.CandidateIndex(d["box"], t["cofm"], t["axis"], t["pos"], t["h"])
+    prm = _lib.make_params(**cases.params(d))
+    w = torch_cuda.stack([t["dens"], t["dens"] * t["temp"], t["dens"] * t["vel"][:, 0], t["dens"] * t["vel"][:, 1],
+                          t["dens"] * t["vel"][:, 2]]).contiguous()
+    fused = idx.compute_colden(prm, t["pos"], w, t["h"]).cpu().numpy()
+    for k in range(w.shape[0]):
+        one = idx.compute_colden(prm, t["pos"], w[k].contiguous(), t["h"]).cpu().numpy()
+        assert np.array_equal(fused[k], one)
+
+
+def test_fused_lines(torch_cuda):
+    """Lya + Lyb in one call equal two calls."""
+    from fake_spectra_b200 import _lib, native
+    d = cases.random_case(nside=14, nlos=24, axis="cycle", seed=23)
+    t = dev(torch_cuda, d)
+    idx = native.CandidateIndex(d["box"], t["cofm"], t["axis"], t["pos"], t["h"])
+    pa = _lib.make_params(**cases.params(d, line="HI1215"))
+    pb = _lib.make_params(**cases.params(d, line="HI1025"))
+    both = idx.compute_tau([pa, pb], t["pos"], t["vel"], t["dens"], t["temp"], t["h"]).cpu().numpy()
+    for k, prm in enumerate((pa, pb)):
+        one = idx.compute_tau(prm, t["pos"], t["vel"], t["dens"], t["temp"], t["h"]).cpu().numpy()
+        rel, same_zero = cases.rel_err(both[k], one)
+        assert same_zero and rel < 1e-13
+
+
+def test_empty_inputs(priv):
+    d = cases.random_case(nside=8, nlos=5, axis=1)
+    p = cases.params(d)
+    e3, e1 = np.zeros((0, 3), np.float32), np.zeros(0, np.float32)
+    out = priv._Particle_Interpolate(1, p["nbins"], 1, p["box"], p["velfac"], p["atime"], p["lambda_cm"], p["gamma"],
+                                     p["fosc"], p["amumass"], p["tautail"], e3, e3, e1, e1, e1, d["axis"], d["cofm"])
+    assert out.shape == (5, p["nbins"]) and not out.any()
+    assert priv._near_lines(p["box"], e3, e1, d["axis"], d["cofm"]).size == 0
+    # a sightline nobody reaches stays exactly zero
+    far = d["cofm"].copy()
+    tiny_h = np.full_like(d["h"], 1e-3)
+    out = priv._Particle_Interpolate(0, p["nbins"], 1, p["box"], p["velfac"], p["atime"], p["lambda_cm"], p["gamma"],
+                                     p["fosc"], p["amumass"], p["tautail"], d["pos"], d["vel"], d["dens"], d["temp"],
+                                     tiny_h, d["axis"], far)
+    assert not out.any()
+
+
+def test_bad_axis_is_an_error_not_a_crash(priv):
+    from fake_spectra_b200._lib import FsbError
+    d = cases.random_case(nside=8, nlos=5, axis=1)
+    p = cases.params(d)
+    bad = d["axis"].copy()
+    bad[2] = 4
+    with pytest.raises(FsbError):
+        interp(priv, 1, p, dict(d, axis=bad))
