@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""Benchmark of the sightline-interpolation hot path (BASELINE.json metric: spectra/s and
+sightline-particle pairs/s for Ly-alpha-forest tau).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle/_ref)
+
+A "step" is one pass of the hot path over the whole workload: candidate-index build + optical
+depth of every fused line for every sightline.  Default workload = BASELINE.json configs[1]:
+GriddedSpectra 256x256 grid (65 536 x-axis sightlines) on a synthetic 2x256^3 snapshot (16.7 M gas
+particles, SURVEY App. F generator), cubic-spline SPH kernel, H I Ly-alpha + Ly-beta, 1 km/s pixels.
+
+One process per GPU.  Multi-GPU = sightline sharding with the particle set replicated in each
+GPU's HBM and NO data-path collective; weak scaling: every rank processes its
+own full 256x256 grid (rank r's grid is shifted by r/N of the grid spacing), so the whole-job
+value is the sum over ranks of sightlines / max-over-ranks time.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+LINES = {  # lambda (cm), Gamma (1/s), f_osc, amu: SURVEY App. F
+    "HI1215": (1215.6701e-8, 6.265e8, 0.4164, 1.00794),
+    "HI1025": (1025.7223e-8, 1.897e8, 0.07912, 1.00794),
+}
+WORKLOADS = {
+    # name: (nside, sightline spec, lines, kernel, pixel km/s)
+    "c2_grid256_lya_lyb": dict(nside=256, nspec=256, lines=("HI1215", "HI1025"), kernel=1, res=1.0),
+    "c1_rand1000_lya": dict(nside=64, numlos=1000, lines=("HI1215",), kernel=1, res=1.0),
+    "mini_grid64_lya_lyb": dict(nside=64, nspec=64, lines=("HI1215", "HI1025"), kernel=1, res=1.0),
+}
+FLOP_PER_VOIGT = 280.0  # algorithmic FP64 flop per Voigt evaluation
+TAUTAIL = 1e-7          # reference spectra.py:135
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2_grid256_lya_lyb", choices=sorted(WORKLOADS))
+    ap.add_argument("--voigt", default="fast", choices=["fast", "exact"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def build_workload(name, rank, world):
+    from fake_spectra_b200 import synthetic as syn
+    w = dict(WORKLOADS[name])
+    d = syn.boundary_arrays(w["nside"], seed=42, kernel=w["kernel"])
+    cos = syn.Cosmology()
+    box = d["box"]
+    if "nspec" in w:
+        cofm, axis = syn.grid_sightlines(box, w["nspec"], axis=1)
+        if world > 1:  # weak scaling: a distinct, shifted grid per rank
+            shift = (box / w["nspec"]) * rank / world
+            cofm = cofm.copy()
+            cofm[:, 1:] += shift
+    else:
+        cofm, axis = syn.random_sightlines(box, w["numlos"], seed=23 + rank, axis=1)
+    velfac = float(cos.velfac)
+    nbins = int(box * velfac / w["res"])
+    w.update(d)
+    w.update(cofm=np.ascontiguousarray(cofm), axis=np.ascontiguousarray(axis), velfac=velfac, atime=cos.atime,
+             nbins=nbins, nlos=cofm.shape[0], npart=d["pos"].shape[0], name=name)
+    return w
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower().startswith("active")})
+        power = [float(r[3]) for r in self.rows if len(r) >= 9 and r[3].replace(".", "").isdigit()]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm), "power_w_max": max(power) if power else None}
+
+
+def make_params(w, line, voigt):
+    from fake_spectra_b200 import _lib
+    lam, gam, fosc, amu = LINES[line]
+    return _lib.make_params(w["nbins"], w["kernel"], w["box"], w["velfac"], w["atime"], lam, gam, fosc, amu, TAUTAIL,
+                            voigt=_lib.VOIGT_EXACT if voigt == "exact" else _lib.VOIGT_FAST)
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from fake_spectra_b200 import _lib, native, _spectra_priv
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    w = build_workload(args.workload, rank, world)
+    nlines = len(w["lines"])
+    params = [make_params(w, ln, args.voigt) for ln in w["lines"]]
+    names = ("pos", "vel", "dens", "temp", "h", "cofm", "axis")
+    t = {k: torch.from_numpy(w[k]).to(dev) for k in names}
+    out = torch.zeros((nlines, w["nlos"], w["nbins"]), dtype=torch.float64, device=dev)
+    fp64_peak = native.measure_fma_peak(True)
+
+    tau_ms = []
+
+    def step(counters=None, time_tau=False):
+        out.zero_()
+        idx = native.CandidateIndex(w["box"], t["cofm"], t["axis"], t["pos"], t["h"])
+        if time_tau:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        idx.compute_tau(params, t["pos"], t["vel"], t["dens"], t["temp"], t["h"], out=out, counters=counters)
+        if time_tau:
+            e1.record()
+            tau_ms.append((e0, e1))
+        npairs = idx.npairs
+        idx.free()
+        return npairs
+
+    # untimed counter pass: deterministic work counts of one step
+    ctr = torch.zeros(4, dtype=torch.int64, device=dev)
+    npairs = step(counters=ctr)
+    torch.cuda.synchronize()
+    c = ctr.cpu().numpy()
+    n_voigt_step = int(c[2])
+    for _ in range(max(args.warmup - 1, 0)):
+        step()
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    launches0 = _lib.load().fsb_kernel_launches()
+    barrier()
+    torch.cuda.synchronize()
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step(time_tau=True)
+    ev1.record()
+    torch.cuda.synchronize()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = _lib.load().fsb_kernel_launches() - launches0
+    elapsed = max_over_ranks(ev0.elapsed_time(ev1) * 1e-3)
+    total_lines = sum_over_ranks(float(w["nlos"]))
+    total_pairs = sum_over_ranks(float(npairs))
+    ms_per_step = elapsed / args.steps * 1e3
+    value = total_lines * args.steps / elapsed
+    pairs_per_s = total_pairs * nlines * args.steps / elapsed
+    tau_launch_s = float(np.mean([a.elapsed_time(b) for a, b in tau_ms])) * 1e-3 / nlines  # per k_tau launch
+    achieved = FLOP_PER_VOIGT * (n_voigt_step / nlines) / tau_launch_s / 1e12
+    sanity = float(out[0].mean().item())
+
+    # ---- end to end through the reference-facing boundary: host buffers in, host buffer out ----
+    e2e = None
+    if not args.no_e2e:
+        pin = {k: torch.from_numpy(w[k]).pin_memory() for k in names}
+        hout = torch.empty((nlines, w["nlos"], w["nbins"]), dtype=torch.float64).pin_memory()
+        lam, gam, fosc, amu = LINES[w["lines"][0]]
+        extra = [LINES[ln][:3] for ln in w["lines"][1:]]
+        vg = _lib.VOIGT_EXACT if args.voigt == "exact" else _lib.VOIGT_FAST
+
+        def e2e_step():
+            return _spectra_priv._Particle_Interpolate(
+                1, w["nbins"], w["kernel"], w["box"], w["velfac"], w["atime"], lam, gam, fosc, amu, TAUTAIL,
+                pin["pos"].numpy(), pin["vel"].numpy(), pin["dens"].numpy(), pin["temp"].numpy(), pin["h"].numpy(),
+                pin["axis"].numpy(), pin["cofm"].numpy(), voigt=vg, out=hout.numpy(), extra_lines=extra)
+
+        e2e_step()  # warm-up (allocations, page faults of the pinned result)
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            res = e2e_step()
+        torch.cuda.synchronize()
+        e2e_elapsed = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        h2d = sum(int(pin[k].numel() * pin[k].element_size()) for k in names)
+        d2h = int(hout.numel() * hout.element_size())
+        e2e = {"value": total_lines * args.steps / e2e_elapsed, "unit": "spectra/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "ms_per_step": e2e_elapsed / args.steps * 1e3,
+               "call": "_spectra_priv._Particle_Interpolate(host buffers, extra_lines) -> fsb_particle_interpolate_multi_host",
+               "mean_tau_check": float(np.mean(res[0][: min(64, w["nlos"])]))}
+        del pin, hout
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_sample(w, steps=1)
+
+    if rank == 0:
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "tau_traffic.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get(args.workload)
+            except Exception:
+                traffic = None
+        line = {
+            "metric": "spectra_per_s", "value": value, "unit": "spectra/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "particles": int(w["npart"]), "sightlines_per_gpu": int(w["nlos"]),
+                       "pixels": int(w["nbins"]), "pixel_kms": w["res"], "lines": list(w["lines"]), "sph_kernel": "cubic",
+                       "voigt": args.voigt, "parallelism": "sightline-sharded x%d, particles replicated" % world,
+                       "l2": "inputs and outputs larger than L2 (particles %.2f GB, tau %.2f GB per GPU)" % (
+                           w["npart"] * 36 / 1e9, nlines * w["nlos"] * w["nbins"] * 8 / 1e9),
+                       "step": "index build + tau of all lines for every sightline, inputs resident in HBM"},
+            "pairs_per_s": pairs_per_s, "pairs_per_step": total_pairs, "voigt_evals_per_step": n_voigt_step * world,
+            "voigt_evals_per_s": n_voigt_step * world * args.steps / elapsed,
+            "roofline": {"bound": "fp64", "kernel": "k_tau", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+                         "frac": achieved / fp64_peak, "traffic": traffic,
+                         "note": "algorithmic %.0f FP64 flop per Voigt evaluation (SURVEY 8d) x %d evaluations per launch / "
+                                 "mean k_tau launch time %.4f s (CUDA events, timed region); peak = DFMA rate measured on "
+                                 "this device by fsb_measure_fma_peak (MEASURED_PEAKS.json has no FP64 entry)" % (
+                                     FLOP_PER_VOIGT, n_voigt_step // nlines, tau_launch_s),
+                         "tau_share_of_step": tau_launch_s * nlines / (elapsed / args.steps)},
+            "cpu_baseline": cpu, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "check_mean_tau": sanity,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_sample(w, steps=1, nsample=None):
+    """The reference's own CPU implementation (oracle/_ref when built, else the C restatement) on a
+    bounded sample of the workload: a regular subsample of the sightlines against the particles
+    that reach them (prefiltered, untimed, as the reference host does: spectra.py:556-568)."""
+    from oracle import Oracle, Reference
+    try:
+        impl, kind = Reference(), "reference"
+    except (FileNotFoundError, OSError):
+        impl, kind = Oracle(), "port"
+    cores = impl.threads()
+    if nsample is None:
+        # ~0.56 core-seconds per sightline at 256^3 (two lines); aim at 10-30 s of CPU work per step
+        nsample = int(min(w["nlos"], max(32, 24 * cores * 256 // w["nside"])))
+    sel = np.unique(np.linspace(0, w["nlos"] - 1, nsample).astype(np.int64))
+    cofm = np.ascontiguousarray(w["cofm"][sel])
+    axis = np.ascontiguousarray(w["axis"][sel])
+    near = Oracle().near_lines(w["box"], w["pos"], w["h"], axis, cofm) if kind == "port" else \
+        impl.near_lines(w["box"], w["pos"], w["h"], axis, cofm)
+    sub = {k: np.ascontiguousarray(w[k][near]) for k in ("pos", "vel", "dens", "temp", "h")}
+    best = None
+    for _ in range(steps):
+        t_step = 0.0
+        for ln in w["lines"]:
+            lam, gam, fosc, amu = LINES[ln]
+            t0 = time.perf_counter()
+            impl.compute_tau(w["nbins"], w["kernel"], w["box"], w["velfac"], w["atime"], lam, gam, fosc, amu, TAUTAIL,
+                             sub["pos"], sub["vel"], sub["dens"], sub["temp"], sub["h"], axis, cofm)
+            t_step += time.perf_counter() - t0
+        best = t_step if best is None else min(best, t_step)
+    return {"value": len(sel) / best, "unit": "spectra/s", "cores": cores, "kind": kind, "seconds_per_step": best,
+            "sample": "%d of %d sightlines (regular subsample), %d prefiltered particles, %d line(s) each; prefilter untimed"
+                      % (len(sel), w["nlos"], len(near), len(w["lines"]))}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w = build_workload(args.workload, 0, 1)
+    for _ in range(args.warmup):
+        cpu_sample(w, steps=1, nsample=8)  # warm caches / thread pool on a tiny sample
+    t0 = time.perf_counter()
+    runs = [cpu_sample(w, steps=1) for _ in range(args.steps)]
+    wall = time.perf_counter() - t0
+    sec = float(np.mean([r["seconds_per_step"] for r in runs]))
+    nsel = runs[0]["value"] * runs[0]["seconds_per_step"]
+    value = nsel / sec
+    cpu = dict(runs[0])
+    cpu["value"] = value
+    line = {"impl": "reference", "metric": "spectra_per_s", "value": value, "unit": "spectra/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "particles": int(w["npart"]), "pixels": int(w["nbins"]),
+                       "lines": list(w["lines"]), "sph_kernel": "cubic",
+                       "note": "reference C++ (OpenMP, all host threads) on a bounded sightline sample; wall %.1f s" % wall},
+            "cpu_baseline": cpu, "e2e": {"value": value, "unit": "spectra/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

@@ -36,6 +36,7 @@ SIGNATURES = {
     "fsb_abi_version": (C.c_int, []),
     "fsb_strerror": (C.c_char_p, [C.c_int]),
     "fsb_last_error": (C.c_char_p, []),
+    "fsb_kernel_launches": (C.c_uint64, []),
     "fsb_device_info": (C.c_int, [C.POINTER(C.c_int32)] * 4),
     "fsb_index_build": (C.c_int, [C.c_double, _P, _P, C.c_int32, _P, _P, C.c_int64, _P, C.POINTER(_P)]),
     "fsb_index_free": (C.c_int, [_P, _P]),
@@ -48,6 +49,8 @@ SIGNATURES = {
                                            C.c_int32, _P, _P]),
     "fsb_particle_interpolate_host": (C.c_int, [C.c_int32, C.POINTER(Params), _P, _P, _P, _P, _P, C.c_int64, _P, _P,
                                                 C.c_int32, _P]),
+    "fsb_particle_interpolate_multi_host": (C.c_int, [C.c_int32, C.POINTER(Params), C.c_int32, _P, _P, _P, _P, _P,
+                                                      C.c_int64, _P, _P, C.c_int32, _P]),
     "fsb_near_lines": (C.c_int, [C.c_double, _P, _P, C.c_int64, _P, _P, C.c_int32, _P, C.POINTER(C.c_int64), _P]),
     "fsb_near_lines_host": (C.c_int, [C.c_double, _P, _P, C.c_int64, _P, _P, C.c_int32, _P, C.POINTER(C.c_int64)]),
     "fsb_assign_cells": (C.c_int, [_P, C.c_double, _P, _P, _P, _P, _P]),

@@ -23,11 +23,16 @@ def _is_f32(a):
 
 
 def _Particle_Interpolate(compute_tau, nbins, kernel, box, velfac, atime, lambda_cm, gamma, fosc, amumass, tautail,
-                          pos, vel, dens, temp, h, axis, cofm, precision=None, voigt=None):
+                          pos, vel, dens, temp, h, axis, cofm, precision=None, voigt=None, out=None,
+                          extra_lines=()):
     """Optical depth (compute_tau != 0) or column density on every sightline.
 
     Arguments, order and units as py_module.cpp:115; returns a new float64 array [NumLos, nbins].
-    Raises TypeError / ValueError on the same conditions as py_module.cpp:122-151."""
+    Raises TypeError / ValueError on the same conditions as py_module.cpp:122-151.
+
+    Extensions (keyword only, absent from the reference): ``out`` = preallocated (e.g. pinned)
+    float64 result buffer; ``extra_lines`` = [(lambda_cm, gamma, fosc), ...] further lines of the
+    same ion computed from the same upload and candidate index, result [1+len, NumLos, nbins]."""
     for a in (pos, vel, dens, temp, h):
         if not _is_f32(a):
             raise TypeError("One of the data arrays does not have 32-bit float type")
@@ -48,17 +53,26 @@ def _Particle_Interpolate(compute_tau, nbins, kernel, box, velfac, atime, lambda
     p = _lib.make_params(nbins, kernel, box, velfac, atime, lambda_cm, gamma, fosc, amumass, tautail,
                          precision=DEFAULT_PRECISION if precision is None else precision,
                          voigt=DEFAULT_VOIGT if voigt is None else voigt)
-    out = np.empty((numlos, int(nbins)), dtype=np.float64)
+    prec = DEFAULT_PRECISION if precision is None else precision
+    vgt = DEFAULT_VOIGT if voigt is None else voigt
+    plist = [p] + [_lib.make_params(nbins, kernel, box, velfac, atime, lam, gam, fo, amumass, tautail, precision=prec,
+                                    voigt=vgt) for (lam, gam, fo) in extra_lines]
+    shape = (numlos, int(nbins)) if not extra_lines else (len(plist), numlos, int(nbins))
+    if out is None:
+        out = np.empty(shape, dtype=np.float64)
+    elif out.dtype != np.float64 or out.size != int(np.prod(shape)) or not out.flags.c_contiguous:
+        raise ValueError("out must be a C-contiguous float64 array of %s elements" % (shape,))
+    parr = (_lib.Params * len(plist))(*plist)
     lib = _lib.load()
     if compute_tau:
         vel, temp = np.ascontiguousarray(vel), np.ascontiguousarray(temp)
         pvel, ptemp = _ptr(vel), _ptr(temp)
     else:
         pvel = ptemp = None
-    rc = lib.fsb_particle_interpolate_host(1 if compute_tau else 0, C.byref(p), _ptr(pos), pvel, _ptr(dens), ptemp,
-                                           _ptr(h), npart, _ptr(axis), _ptr(cofm), numlos, _ptr(out))
+    rc = lib.fsb_particle_interpolate_multi_host(1 if compute_tau else 0, parr, len(plist), _ptr(pos), pvel, _ptr(dens),
+                                                 ptemp, _ptr(h), npart, _ptr(axis), _ptr(cofm), numlos, _ptr(out))
     _lib.check(rc, "_Particle_Interpolate")
-    return out
+    return out.reshape(shape)
 
 
 def _near_lines(box, pos, hh, axis, cofm):

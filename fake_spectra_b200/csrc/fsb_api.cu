@@ -2,6 +2,7 @@
 // one-shot and host-pointer entry points that mirror the reference's Python boundary
 // (py_module.cpp:25-233).
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstring>
@@ -11,6 +12,9 @@
 namespace fsb {
 
 static thread_local char g_err[512] = "";
+static std::atomic<unsigned long long> g_launches{0};
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 void set_error(const char *fmt, ...)
 {
@@ -78,6 +82,8 @@ using namespace fsb;
 extern "C" int fsb_abi_version(void) { return FSB_ABI_VERSION; }
 
 extern "C" const char *fsb_last_error(void) { return g_err; }
+
+extern "C" uint64_t fsb_kernel_launches(void) { return (uint64_t) g_launches.load(); }
 
 extern "C" const char *fsb_strerror(int code)
 {
@@ -188,25 +194,47 @@ extern "C" int fsb_particle_interpolate(int32_t compute_tau, const fsb_params *p
 }
 
 namespace {
+// Keep freed blocks in the stream-ordered pool across calls (otherwise every host-level call
+// pays for a fresh multi-GB allocation).
+int retain_pool_memory()
+{
+    static thread_local int done_for_device = -1;
+    int dev = 0;
+    FSB_CUDA_TRY(cudaGetDevice(&dev));
+    if (done_for_device == dev) return FSB_OK;
+    cudaMemPool_t pool;
+    FSB_CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, dev));
+    unsigned long long keep = ~0ull;
+    FSB_CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    done_for_device = dev;
+    return FSB_OK;
+}
+
 struct DevBuf {
     void *ptr = nullptr;
-    ~DevBuf() { if (ptr) cudaFree(ptr); }
+    cudaStream_t stream = nullptr;
+    ~DevBuf() { if (ptr) cudaFreeAsync(ptr, stream); }
     int upload(const void *host, size_t bytes, cudaStream_t s)
     {
+        stream = s;
         if (bytes == 0) bytes = 8, host = nullptr;
-        FSB_CUDA_TRY(cudaMalloc(&ptr, bytes));
+        FSB_CUDA_TRY(cudaMallocAsync(&ptr, bytes, s));
         if (host) FSB_CUDA_TRY(cudaMemcpyAsync(ptr, host, bytes, cudaMemcpyHostToDevice, s));
         return FSB_OK;
     }
 };
 }  // namespace
 
-extern "C" int fsb_particle_interpolate_host(int32_t compute_tau, const fsb_params *p, const float *pos, const float *vel,
-                                             const float *dens, const float *temp, const float *h, int64_t npart,
-                                             const int32_t *axis, const double *cofm, int32_t nlos, double *out)
+extern "C" int fsb_particle_interpolate_multi_host(int32_t compute_tau, const fsb_params *p, int32_t nlines,
+                                                   const float *pos, const float *vel, const float *dens,
+                                                   const float *temp, const float *h, int64_t npart, const int32_t *axis,
+                                                   const double *cofm, int32_t nlos, double *out)
 {
     FSB_REQUIRE(p != nullptr && out != nullptr, "params/out NULL");
-    FSB_REQUIRE(nlos >= 0 && npart >= 0 && p->nbins > 0, "bad sizes");
+    FSB_REQUIRE(nlines >= 1, "nlines must be >= 1");
+    FSB_REQUIRE(nlos >= 0 && npart >= 0 && p[0].nbins > 0, "bad sizes");
+    FSB_REQUIRE(compute_tau || nlines == 1, "several lines only make sense for tau");
+    FSB_TRY(retain_pool_memory());
     cudaStream_t s = nullptr;
     DevBuf dpos, dvel, ddens, dtemp, dh, daxis, dcofm, dout;
     const size_t np = (size_t) npart, nl = (size_t) nlos;
@@ -220,15 +248,36 @@ extern "C" int fsb_particle_interpolate_host(int32_t compute_tau, const fsb_para
     }
     FSB_TRY(daxis.upload(axis, sizeof(int32_t) * nl, s));
     FSB_TRY(dcofm.upload(cofm, sizeof(double) * 3 * nl, s));
-    const size_t out_bytes = sizeof(double) * nl * (size_t) p->nbins;
+    const size_t row_bytes = sizeof(double) * nl * (size_t) p[0].nbins;
+    const size_t out_bytes = row_bytes * (size_t) nlines;
     FSB_TRY(dout.upload(nullptr, out_bytes, s));
     FSB_CUDA_TRY(cudaMemsetAsync(dout.ptr, 0, std::max<size_t>(out_bytes, 8), s));
-    FSB_TRY(fsb_particle_interpolate(compute_tau, p, (const float *) dpos.ptr, (const float *) dvel.ptr, (const float *) ddens.ptr,
-                                     (const float *) dtemp.ptr, (const float *) dh.ptr, npart, (const int32_t *) daxis.ptr,
-                                     (const double *) dcofm.ptr, nlos, (double *) dout.ptr, s));
+    if (nlines == 1 || p[0].kernel == FSB_KERNEL_VORONOI) {
+        for (int32_t i = 0; i < nlines; ++i)
+            FSB_TRY(fsb_particle_interpolate(compute_tau, &p[i], (const float *) dpos.ptr, (const float *) dvel.ptr,
+                                             (const float *) ddens.ptr, (const float *) dtemp.ptr, (const float *) dh.ptr, npart,
+                                             (const int32_t *) daxis.ptr, (const double *) dcofm.ptr, nlos,
+                                             (double *) dout.ptr + (size_t) i * nl * (size_t) p[0].nbins, s));
+    } else {
+        fsb_index *idx = nullptr;
+        FSB_TRY(fsb_index_build(p[0].box, (const double *) dcofm.ptr, (const int32_t *) daxis.ptr, nlos, (const float *) dpos.ptr,
+                                (const float *) dh.ptr, npart, s, &idx));
+        const int rc = fsb_compute_tau_multi(idx, p, nlines, (const float *) dpos.ptr, (const float *) dvel.ptr,
+                                             (const float *) ddens.ptr, (const float *) dtemp.ptr, (const float *) dh.ptr,
+                                             (double *) dout.ptr, nullptr, s);
+        fsb_index_free(idx, s);
+        FSB_TRY(rc);
+    }
     if (out_bytes) FSB_CUDA_TRY(cudaMemcpyAsync(out, dout.ptr, out_bytes, cudaMemcpyDeviceToHost, s));
     FSB_CUDA_TRY(cudaStreamSynchronize(s));
     return FSB_OK;
+}
+
+extern "C" int fsb_particle_interpolate_host(int32_t compute_tau, const fsb_params *p, const float *pos, const float *vel,
+                                             const float *dens, const float *temp, const float *h, int64_t npart,
+                                             const int32_t *axis, const double *cofm, int32_t nlos, double *out)
+{
+    return fsb_particle_interpolate_multi_host(compute_tau, p, 1, pos, vel, dens, temp, h, npart, axis, cofm, nlos, out);
 }
 
 extern "C" int fsb_near_lines_host(double box, const float *pos, const float *h, int64_t npart, const int32_t *axis,

@@ -11,6 +11,7 @@ namespace fsb {
 
 // ---- error plumbing -------------------------------------------------------------------------
 void set_error(const char *fmt, ...);
+void count_launch();  // every kernel launch of this library is counted (fsb_kernel_launches)
 
 #define FSB_CUDA_TRY(expr)                                                                     \
     do {                                                                                       \

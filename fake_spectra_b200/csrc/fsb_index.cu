@@ -389,11 +389,11 @@ int build_line_table(double box, const double *cofm, const int32_t *axis, int32_
     FSB_CUDA_TRY(cudaMemsetAsync(cursor.ptr, 0, sizeof(int32_t) * (size_t) (total_cells + 1), stream));
     if (nlos > 0) {
         const int threads = 256, blocks = (nlos + threads - 1) / threads;
-        k_line_cells<<<blocks, threads, 0, stream>>>(cofm, axis, nlos, bt.T.grid[0], bt.T.grid[1], bt.T.grid[2],
+        count_launch(); k_line_cells<<<blocks, threads, 0, stream>>>(cofm, axis, nlos, bt.T.grid[0], bt.T.grid[1], bt.T.grid[2],
                                                      cell_of_line.as<int32_t>(), cell_count.as<int32_t>());
-        k_scan_single<int32_t, int32_t><<<1, 1024, 0, stream>>>(cell_count.as<int32_t>(), bt.cell_start.as<int32_t>(),
+        count_launch(); k_scan_single<int32_t, int32_t><<<1, 1024, 0, stream>>>(cell_count.as<int32_t>(), bt.cell_start.as<int32_t>(),
                                                                  total_cells, nullptr);
-        k_line_scatter<<<blocks, threads, 0, stream>>>(cofm, axis, nlos, cell_of_line.as<int32_t>(),
+        count_launch(); k_line_scatter<<<blocks, threads, 0, stream>>>(cofm, axis, nlos, cell_of_line.as<int32_t>(),
                                                        bt.cell_start.as<int32_t>(), cursor.as<int32_t>(),
                                                        bt.line_id.as<int32_t>(), bt.key.as<double>(), bt.proj2.as<double>());
         FSB_CUDA_TRY(cudaGetLastError());
@@ -436,10 +436,10 @@ static int index_build_impl(fsb_index *idx, double box, const double *cofm, cons
     const int threads = 256;
     const unsigned pblocks = (unsigned) ((npart + threads - 1) / threads);
     if (npart > 0 && nlos > 0) {
-        k_pairs<0><<<pblocks, threads, 0, stream>>>(bt.T, pos, h, npart, count.as<int32_t>(), nullptr, nullptr, nullptr);
+        count_launch(); k_pairs<0><<<pblocks, threads, 0, stream>>>(bt.T, pos, h, npart, count.as<int32_t>(), nullptr, nullptr, nullptr);
         FSB_CUDA_TRY(cudaGetLastError());
     }
-    k_scan_single<int32_t, int64_t><<<1, 1024, 0, stream>>>(count.as<int32_t>(), idx->offsets, nlos, max_list.as<int64_t>());
+    count_launch(); k_scan_single<int32_t, int64_t><<<1, 1024, 0, stream>>>(count.as<int32_t>(), idx->offsets, nlos, max_list.as<int64_t>());
     FSB_CUDA_TRY(cudaGetLastError());
     int64_t h_total = 0, h_max = 0;
     FSB_CUDA_TRY(cudaMemcpyAsync(&h_total, idx->offsets + nlos, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
@@ -454,14 +454,14 @@ static int index_build_impl(fsb_index *idx, double box, const double *cofm, cons
     if (idx->npairs == 0) return FSB_OK;
 
     FSB_CUDA_TRY(cudaMemsetAsync(count.ptr, 0, sizeof(int32_t) * (nl + 1), stream));
-    k_pairs<1><<<pblocks, threads, 0, stream>>>(bt.T, pos, h, npart, count.as<int32_t>(), idx->offsets, idx->particle, nullptr);
+    count_launch(); k_pairs<1><<<pblocks, threads, 0, stream>>>(bt.T, pos, h, npart, count.as<int32_t>(), idx->offsets, idx->particle, nullptr);
     FSB_CUDA_TRY(cudaGetLastError());
     // in-smem sort capacity: next power of two of the longest list, at most 32768 entries (128 KB)
     int cap = 32;
     while (cap < idx->max_list && cap < 32768) cap <<= 1;
     const size_t smem = sizeof(int32_t) * (size_t) cap;
     FSB_CUDA_TRY(cudaFuncSetAttribute(k_sort_lists, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-    k_sort_lists<<<nlos, 256, smem, stream>>>(idx->offsets, idx->particle, idx->dr2, pos, idx->cofm, idx->axis, box, cap);
+    count_launch(); k_sort_lists<<<nlos, 256, smem, stream>>>(idx->offsets, idx->particle, idx->dr2, pos, idx->cofm, idx->axis, box, cap);
     FSB_CUDA_TRY(cudaGetLastError());
     if (idx->max_list > cap) {
         std::vector<int64_t> h_off((size_t) nlos + 1);
@@ -476,9 +476,9 @@ static int index_build_impl(fsb_index *idx, double box, const double *cofm, cons
             FSB_TRY(pad.alloc(sizeof(int32_t) * (size_t) m, stream));
             FSB_CUDA_TRY(cudaMemsetAsync(pad.ptr, 0x7f, sizeof(int32_t) * (size_t) m, stream));  // 0x7f7f7f7f > any index
             FSB_CUDA_TRY(cudaMemcpyAsync(pad.ptr, idx->particle + h_off[l], sizeof(int32_t) * (size_t) n, cudaMemcpyDeviceToDevice, stream));
-            k_bitonic_global<<<1, 1024, 0, stream>>>(pad.as<int32_t>(), m);
+            count_launch(); k_bitonic_global<<<1, 1024, 0, stream>>>(pad.as<int32_t>(), m);
             FSB_CUDA_TRY(cudaMemcpyAsync(idx->particle + h_off[l], pad.ptr, sizeof(int32_t) * (size_t) n, cudaMemcpyDeviceToDevice, stream));
-            k_dr2_of_list<<<(unsigned) ((n + 255) / 256), 256, 0, stream>>>(idx->particle + h_off[l], idx->dr2 + h_off[l], n, pos,
+            count_launch(); k_dr2_of_list<<<(unsigned) ((n + 255) / 256), 256, 0, stream>>>(idx->particle + h_off[l], idx->dr2 + h_off[l], n, pos,
                                                                            idx->cofm, idx->axis, l, box);
             FSB_CUDA_TRY(cudaGetLastError());
         }
@@ -562,10 +562,10 @@ extern "C" int fsb_near_lines(double box, const float *pos, const float *h, int6
     FSB_TRY(flag.alloc((size_t) npart, stream));
     FSB_TRY(block_count.alloc(sizeof(int32_t) * (size_t) (nblocks + 1), stream));
     FSB_TRY(block_start.alloc(sizeof(int64_t) * (size_t) (nblocks + 1), stream));
-    k_pairs<2><<<(unsigned) ((npart + 255) / 256), 256, 0, stream>>>(bt.T, pos, h, npart, nullptr, nullptr, nullptr, flag.as<uint8_t>());
-    k_flag_block_counts<<<(unsigned) nblocks, threads, 0, stream>>>(flag.as<uint8_t>(), npart, block_count.as<int32_t>());
-    k_scan_single<int32_t, int64_t><<<1, 1024, 0, stream>>>(block_count.as<int32_t>(), block_start.as<int64_t>(), nblocks, nullptr);
-    k_flag_compact<<<(unsigned) nblocks, threads, 0, stream>>>(flag.as<uint8_t>(), npart, block_start.as<int64_t>(), out_index);
+    count_launch(); k_pairs<2><<<(unsigned) ((npart + 255) / 256), 256, 0, stream>>>(bt.T, pos, h, npart, nullptr, nullptr, nullptr, flag.as<uint8_t>());
+    count_launch(); k_flag_block_counts<<<(unsigned) nblocks, threads, 0, stream>>>(flag.as<uint8_t>(), npart, block_count.as<int32_t>());
+    count_launch(); k_scan_single<int32_t, int64_t><<<1, 1024, 0, stream>>>(block_count.as<int32_t>(), block_start.as<int64_t>(), nblocks, nullptr);
+    count_launch(); k_flag_compact<<<(unsigned) nblocks, threads, 0, stream>>>(flag.as<uint8_t>(), npart, block_start.as<int64_t>(), out_index);
     FSB_CUDA_TRY(cudaGetLastError());
     FSB_CUDA_TRY(cudaMemcpyAsync(count, block_start.as<int64_t>() + nblocks, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
     FSB_CUDA_TRY(cudaStreamSynchronize(stream));

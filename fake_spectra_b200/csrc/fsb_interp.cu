@@ -446,8 +446,8 @@ int plan_items(const fsb_index *idx, int seg_pairs_req, int nbins, int nrows_per
     const size_t nl = (size_t) std::max(idx->nlos, 1);
     FSB_TRY(plan.nitems.alloc(sizeof(int32_t) * (nl + 1), stream));
     FSB_TRY(plan.item_start.alloc(sizeof(int32_t) * (nl + 1), stream));
-    k_items_per_line<<<(idx->nlos + 255) / 256, 256, 0, stream>>>(idx->offsets, idx->nlos, seg, plan.nitems.as<int32_t>());
-    k_scan_single<int32_t, int32_t><<<1, 1024, 0, stream>>>(plan.nitems.as<int32_t>(), plan.item_start.as<int32_t>(), idx->nlos, nullptr);
+    count_launch(); k_items_per_line<<<(idx->nlos + 255) / 256, 256, 0, stream>>>(idx->offsets, idx->nlos, seg, plan.nitems.as<int32_t>());
+    count_launch(); k_scan_single<int32_t, int32_t><<<1, 1024, 0, stream>>>(plan.nitems.as<int32_t>(), plan.item_start.as<int32_t>(), idx->nlos, nullptr);
     FSB_CUDA_TRY(cudaGetLastError());
     plan.items.item_start = plan.item_start.as<int32_t>();
     const size_t bytes = sizeof(double) * (size_t) plan.n_items * (size_t) nbins * (size_t) nrows_per_item;
@@ -470,7 +470,7 @@ int launch_tau(const fsb_index *idx, const InterpConsts &c, const float *pos, co
     double *scratch = plan.scratch_rows.as<double>();
     unsigned long long *ctr = reinterpret_cast<unsigned long long *>(counters);
 #define FSB_LAUNCH_TAU(K)                                                                                          \
-    k_tau<K, FSB_VOIGT_EXACT><<<grid, 32, 0, stream>>>(c, plan.items, idx->offsets, idx->particle, idx->dr2, idx->axis, \
+    count_launch(); k_tau<K, FSB_VOIGT_EXACT><<<grid, 32, 0, stream>>>(c, plan.items, idx->offsets, idx->particle, idx->dr2, idx->axis, \
                                                         pos, vel, dens, temp, h, cells, out, scratch, ctr)
     switch (c.kernel) {
     case FSB_KERNEL_TOPHAT: FSB_LAUNCH_TAU(FSB_KERNEL_TOPHAT); break;
@@ -483,7 +483,7 @@ int launch_tau(const fsb_index *idx, const InterpConsts &c, const float *pos, co
     FSB_CUDA_TRY(cudaGetLastError());
     if (plan.segmented) {
         dim3 g(idx->nlos, (c.nbins + 255) / 256, 1);
-        k_reduce_rows<<<g, 256, 0, stream>>>(plan.items.item_start, scratch, 0, out, 0, c.nbins);
+        count_launch(); k_reduce_rows<<<g, 256, 0, stream>>>(plan.items.item_start, scratch, 0, out, 0, c.nbins);
         FSB_CUDA_TRY(cudaGetLastError());
     }
     return FSB_OK;
@@ -501,7 +501,7 @@ int launch_colden(const fsb_index *idx, const InterpConsts &c, const float *pos,
     const int64_t scratch_stride = plan.n_items * c.nbins;
     unsigned long long *ctr = reinterpret_cast<unsigned long long *>(counters);
 #define FSB_LAUNCH_COLDEN(K)                                                                                          \
-    k_colden<K><<<grid, 32, 0, stream>>>(c, plan.items, idx->offsets, idx->particle, idx->dr2, idx->axis, pos, dens,  \
+    count_launch(); k_colden<K><<<grid, 32, 0, stream>>>(c, plan.items, idx->offsets, idx->particle, idx->dr2, idx->axis, pos, dens,  \
                                          dens_stride, h, cells, out, out_stride, scratch, scratch_stride, ctr)
     switch (c.kernel) {
     case FSB_KERNEL_TOPHAT: FSB_LAUNCH_COLDEN(FSB_KERNEL_TOPHAT); break;
@@ -514,7 +514,7 @@ int launch_colden(const fsb_index *idx, const InterpConsts &c, const float *pos,
     FSB_CUDA_TRY(cudaGetLastError());
     if (plan.segmented) {
         dim3 g(idx->nlos, (c.nbins + 255) / 256, c.nlines);
-        k_reduce_rows<<<g, 256, 0, stream>>>(plan.items.item_start, scratch, scratch_stride, out, out_stride, c.nbins);
+        count_launch(); k_reduce_rows<<<g, 256, 0, stream>>>(plan.items.item_start, scratch, scratch_stride, out, out_stride, c.nbins);
         FSB_CUDA_TRY(cudaGetLastError());
     }
     return FSB_OK;
@@ -523,7 +523,7 @@ int launch_colden(const fsb_index *idx, const InterpConsts &c, const float *pos,
 int launch_voigt(const double *x, const double *y, double *out, int64_t n, int voigt, cudaStream_t stream)
 {
     if (n <= 0) return FSB_OK;
-    k_voigt_profile<<<(unsigned) ((n + 255) / 256), 256, 0, stream>>>(x, y, out, n, voigt);
+    count_launch(); k_voigt_profile<<<(unsigned) ((n + 255) / 256), 256, 0, stream>>>(x, y, out, n, voigt);
     FSB_CUDA_TRY(cudaGetLastError());
     return FSB_OK;
 }

@@ -37,7 +37,7 @@ int measure(double *tflops, double seconds_target, cudaStream_t stream)
     double best = 0;
     for (int rep = 0; rep < 6; ++rep) {
         FSB_CUDA_TRY(cudaEventRecord(e0, stream));
-        k_fma_peak<T><<<blocks, threads, 0, stream>>>(out.as<T>(), iters, (T) 1.0000001, (T) 1e-9);
+        count_launch(); k_fma_peak<T><<<blocks, threads, 0, stream>>>(out.as<T>(), iters, (T) 1.0000001, (T) 1e-9);
         FSB_CUDA_TRY(cudaEventRecord(e1, stream));
         FSB_CUDA_TRY(cudaEventSynchronize(e1));
         float ms = 0;

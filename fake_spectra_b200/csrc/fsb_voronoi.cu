@@ -171,9 +171,9 @@ extern "C" int fsb_assign_cells(const fsb_index *idx, double box, const double *
     for (int l0 = 0; l0 < idx->nlos; l0 += batch) {
         const int nl = std::min(batch, idx->nlos - l0);
         dim3 grid((npts + pts_per_block - 1) / pts_per_block, nl, 1);
-        k_owners<<<grid, kOwnThreads, 0, stream>>>(idx->offsets, idx->particle, idx->cofm, idx->axis, pos, box, npts, reso, l0,
+        count_launch(); k_owners<<<grid, kOwnThreads, 0, stream>>>(idx->offsets, idx->particle, idx->cofm, idx->axis, pos, box, npts, reso, l0,
                                                    owner.as<int32_t>());
-        k_extents<<<nl, 1024, 0, stream>>>(idx->offsets, box, npts, reso, l0, owner.as<int32_t>(), first.as<int32_t>(),
+        count_launch(); k_extents<<<nl, 1024, 0, stream>>>(idx->offsets, box, npts, reso, l0, owner.as<int32_t>(), first.as<int32_t>(),
                                            last.as<int32_t>(), runs.as<int32_t>(), cells, err.as<int32_t>());
         FSB_CUDA_TRY(cudaGetLastError());
     }

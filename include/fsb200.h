@@ -80,6 +80,8 @@ typedef struct fsb_counters {
 FSB_API int fsb_abi_version(void);
 FSB_API const char *fsb_strerror(int code);
 FSB_API const char *fsb_last_error(void);
+/* Number of CUDA kernels this library has launched in this process (all threads). */
+FSB_API uint64_t fsb_kernel_launches(void);
 /* Device properties the bench reports: SM count, clock (kHz), compute capability major/minor. */
 FSB_API int fsb_device_info(int32_t *sm_count, int32_t *clock_khz, int32_t *cc_major, int32_t *cc_minor);
 
@@ -133,6 +135,13 @@ FSB_API int fsb_particle_interpolate(int32_t compute_tau, const fsb_params *p, c
 FSB_API int fsb_particle_interpolate_host(int32_t compute_tau, const fsb_params *p, const float *pos, const float *vel,
                                   const float *dens, const float *temp, const float *h, int64_t npart,
                                   const int32_t *axis, const double *cofm, int32_t nlos, double *out);
+
+/* Several lines of one ion from one upload and one index (HOST pointers): out[nlines][nlos*nbins].
+ * What Spectra.get_tau does for Lya then Lyb as two boundary calls, in one. */
+FSB_API int fsb_particle_interpolate_multi_host(int32_t compute_tau, const fsb_params *p, int32_t nlines,
+                                        const float *pos, const float *vel, const float *dens, const float *temp,
+                                        const float *h, int64_t npart, const int32_t *axis, const double *cofm,
+                                        int32_t nlos, double *out);
 
 /* ---- particle filter (replaces Py_near_lines, py_module.cpp:25-99) ------------------------- */
 /* Ascending indices of particles with at least one candidate sightline.  out_index must hold
