@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libfsb200.so")
+LIB_PATH = os.environ.get("FSB200_LIB") or os.path.join(HERE, "libfsb200.so")  # FSB200_LIB: tuning variants
 
 FSB_OK = 0
 FSB_EINVAL, FSB_ECUDA, FSB_ENOMEM, FSB_EVORONOI, FSB_ENODEV = -1, -2, -3, -4, -5

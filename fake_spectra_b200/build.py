@@ -13,8 +13,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfsb200.so")
-SOURCES = ["fsb_api.cu", "fsb_index.cu", "fsb_interp.cu", "fsb_voronoi.cu", "fsb_microbench.cu"]
-HEADERS = ["fsb_common.cuh", "fsb_scan.cuh", "fsb_voigt.cuh"]
+SOURCES = ["fsb_api.cu", "fsb_index.cu", "fsb_items.cu", "fsb_tau.cu", "fsb_colden.cu", "fsb_voronoi.cu", "fsb_microbench.cu"]
+HEADERS = ["fsb_common.cuh", "fsb_scan.cuh", "fsb_voigt.cuh", "fsb_voigt_tables.h", "fsb_items.cuh"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--cudart", "static",
@@ -33,16 +33,23 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
+def build_variant(name, defines, verbose=False):
+    """Tuning aid: a second copy of the library with extra -D flags, selected at run time with
+    FSB200_LIB=<path> (see _lib.py).  Returns the path of libfsb200_<name>.so."""
+    return build(force=True, verbose=verbose, extra=["-D" + d for d in defines],
+                 lib=os.path.join(HERE, "libfsb200_%s.so" % name), objsub="build_" + name)
+
+
+def build(force=False, verbose=False, extra=(), lib=LIB, objsub="build"):
     if not force and not _stale():
         return LIB
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, objsub)
     os.makedirs(objdir, exist_ok=True)
     objs = []
     procs = []
     for src in SOURCES:
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [NVCC] + FLAGS + list(extra) + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     failed = False
@@ -54,8 +61,8 @@ def build(force=False, verbose=False):
     if failed:
         raise RuntimeError("nvcc failed")
     subprocess.run([NVCC, "-shared", "--cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a",
-                    "-o", LIB] + objs, check=True)
-    return LIB
+                    "-o", lib] + objs, check=True)
+    return lib
 
 
 if __name__ == "__main__":

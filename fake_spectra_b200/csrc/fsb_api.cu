@@ -24,9 +24,27 @@ void set_error(const char *fmt, ...)
     va_end(ap);
 }
 
+// Keep freed blocks in the stream-ordered pool across calls: with the default release threshold (0)
+// every synchronisation hands the multi-GB scratch and index arrays back to the driver and the
+// next call pays for fresh allocations.
+int retain_pool_memory()
+{
+    static thread_local int done_for_device = -1;
+    int dev = 0;
+    FSB_CUDA_TRY(cudaGetDevice(&dev));
+    if (done_for_device == dev) return FSB_OK;
+    cudaMemPool_t pool;
+    FSB_CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, dev));
+    unsigned long long keep = ~0ull;
+    FSB_CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    done_for_device = dev;
+    return FSB_OK;
+}
+
 int Scratch::alloc(size_t bytes, cudaStream_t s)
 {
     stream = s;
+    FSB_TRY(retain_pool_memory());
     if (bytes == 0) bytes = 8;
     cudaError_t e = cudaMallocAsync(&ptr, bytes, s);
     if (e != cudaSuccess) {
@@ -125,13 +143,19 @@ extern "C" int fsb_compute_tau_multi(const fsb_index *idx, const fsb_params *p, 
     FSB_REQUIRE(p[0].kernel != FSB_KERNEL_VORONOI, "Voronoi tau goes through fsb_particle_interpolate (needs fsb_assign_cells)");
     for (int32_t i = 0; i < nlines; ++i) {
         FSB_REQUIRE(p[i].nbins == p[0].nbins && p[i].kernel == p[0].kernel && p[i].box == p[0].box &&
-                    p[i].velfac == p[0].velfac && p[i].amumass == p[0].amumass && p[i].tautail == p[0].tautail,
-                    "fused lines must share nbins, kernel, box, velfac, amumass and tautail");
+                    p[i].velfac == p[0].velfac && p[i].amumass == p[0].amumass && p[i].tautail == p[0].tautail &&
+                    p[i].voigt == p[0].voigt && p[i].precision == p[0].precision,
+                    "fused lines must share nbins, kernel, box, velfac, amumass, tautail, voigt and precision");
+    }
+    // lines of one ion share every node position and Gaussian: the kernel takes them in groups
+    const int32_t group = tau_max_fused_lines();
+    for (int32_t i0 = 0; i0 < nlines; i0 += group) {
+        const int32_t n = std::min(group, nlines - i0);
         InterpConsts c;
-        FSB_TRY(make_consts(idx, &p[i], 1, c));
-        line_consts(p[i], c.line[0]);
-        FSB_TRY(launch_tau(idx, c, pos, vel, dens, temp, h, nullptr, tau + (size_t) i * (size_t) idx->nlos * (size_t) c.nbins,
-                           counters, p[i].precision, stream));
+        FSB_TRY(make_consts(idx, &p[i0], n, c));
+        for (int32_t k = 0; k < n; ++k) line_consts(p[i0 + k], c.line[k]);
+        FSB_TRY(launch_tau(idx, c, pos, vel, dens, temp, h, nullptr, tau + (size_t) i0 * (size_t) idx->nlos * (size_t) c.nbins,
+                           counters, p[i0].precision, stream));
     }
     return FSB_OK;
 }
@@ -194,22 +218,6 @@ extern "C" int fsb_particle_interpolate(int32_t compute_tau, const fsb_params *p
 }
 
 namespace {
-// Keep freed blocks in the stream-ordered pool across calls (otherwise every host-level call
-// pays for a fresh multi-GB allocation).
-int retain_pool_memory()
-{
-    static thread_local int done_for_device = -1;
-    int dev = 0;
-    FSB_CUDA_TRY(cudaGetDevice(&dev));
-    if (done_for_device == dev) return FSB_OK;
-    cudaMemPool_t pool;
-    FSB_CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, dev));
-    unsigned long long keep = ~0ull;
-    FSB_CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-    done_for_device = dev;
-    return FSB_OK;
-}
-
 struct DevBuf {
     void *ptr = nullptr;
     cudaStream_t stream = nullptr;

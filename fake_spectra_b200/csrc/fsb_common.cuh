@@ -12,6 +12,7 @@ namespace fsb {
 // ---- error plumbing -------------------------------------------------------------------------
 void set_error(const char *fmt, ...);
 void count_launch();  // every kernel launch of this library is counted (fsb_kernel_launches)
+int retain_pool_memory();  // raise the release threshold of the device's default memory pool (once per device)
 
 #define FSB_CUDA_TRY(expr)                                                                     \
     do {                                                                                       \
@@ -99,6 +100,7 @@ int launch_tau(const fsb_index *idx, const InterpConsts &c, const float *pos, co
                int precision, cudaStream_t stream);
 int launch_colden(const fsb_index *idx, const InterpConsts &c, const float *pos, const float *dens, int64_t dens_stride,
                   const float *h, const float *cells, double *out, fsb_counters *counters, cudaStream_t stream);
+int tau_max_fused_lines();
 int launch_voigt(const double *x, const double *y, double *out, int64_t n, int voigt, cudaStream_t stream);
 
 }  // namespace fsb

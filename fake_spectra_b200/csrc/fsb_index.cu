@@ -418,6 +418,7 @@ static int index_build_impl(fsb_index *idx, double box, const double *cofm, cons
                             const float *pos, const float *h, int64_t npart, cudaStream_t stream)
 {
     const size_t nl = (size_t) std::max(nlos, 1);
+    FSB_TRY(retain_pool_memory());
     FSB_CUDA_TRY(cudaMallocAsync(&idx->offsets, sizeof(int64_t) * (nl + 1), stream));
     FSB_CUDA_TRY(cudaMallocAsync(&idx->cofm, sizeof(double) * 3 * nl, stream));
     FSB_CUDA_TRY(cudaMallocAsync(&idx->axis, sizeof(int32_t) * nl, stream));

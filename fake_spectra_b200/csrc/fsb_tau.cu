@@ -1,0 +1,661 @@
+// Optical depth accumulation (replaces part_int.cpp:20-51 + absorption.cpp:212-279 +
+// singleabs.h:63-175 + the Re w(z) consumer of Faddeeva.cpp).
+//
+// Decomposition.  Persistent CTAs of kTauWarps warps pull work items (sightline, run of its
+// candidate list) from a global counter.  Per batch of kBatch particles one lane per particle
+// gathers the particle and derives every per-particle constant into a shared-memory slab
+// (field-major, so the later warp-uniform reads are broadcasts).  Then, particle by particle, the
+// 32 lanes of the warp march outward over its pixels (absorption.cpp:250-278): while both
+// directions are live each gets a half warp, afterwards all 32 lanes serve the remaining one; the
+// reference's "add, then stop once taulast < tautail" rule is a ballot + find-first-set.
+//
+// NL lines of one ion (Lya + Lyb ...) are fused in one pass: they share every node position, the
+// Gaussian and the Dawson-type table value; only the damping parameter y (hence the coefficient
+// sets Pe, A, BQ) and the amplitude differ.
+//
+// Per pixel the 7-node kernel x Voigt quadrature (singleabs.h:143-167) takes one of four
+// warp-uniform routes:
+//   NEAR   all nodes of all lanes at |x| < 16: branch-free, the 7 nodes interleaved for ILP;
+//          G(x) from the shared-memory table, Gaussians by a two-level recurrence (across the nodes
+//          of a pixel, and from one march step to the next: no exp() in steady state)
+//   FAR    all nodes at |x| >= 16: damping-wing series in 1/x^2, shared across the fused lines
+//   MIXED  the rare warp step that straddles |x| = 16, and pixels wider than btherm/2
+//          (sub-sampling rule of singleabs.h:110-125): generic per-node evaluation
+//   EXACT  FSB_VOIGT_EXACT or y outside (1e-30, 0.03]: restatement of the reference's Faddeeva::w
+#include "fsb_items.cuh"
+#include "fsb_voigt.cuh"
+
+namespace fsb {
+
+namespace {
+
+#ifndef FSB_TAU_MIN_BLOCKS
+#define FSB_TAU_MIN_BLOCKS 4  // resident CTAs per SM the register allocation must allow
+#endif
+#ifndef FSB_TAU_BATCH
+#define FSB_TAU_BATCH 16
+#endif
+
+#ifndef FSB_TAU_WARPS
+#define FSB_TAU_WARPS 4
+#endif
+constexpr int kTauWarps = FSB_TAU_WARPS;
+constexpr int kTauThreads = 32 * kTauWarps;
+constexpr int kBatch = FSB_TAU_BATCH;  // particles per slab refill (one lane each), <= 32
+constexpr int kMaxTauLines = 2;
+
+// ---- slab layout: [field][kBatch] doubles per warp --------------------------------------------------
+enum SharedField {
+    S_VEL = 0,   // velfac*pos + pvel                                  absorption.cpp:234
+    S_INVB,      // 1/btherm
+    S_HALFB,     // btherm/2: sub-sampling threshold                    singleabs.h:110
+    S_STEP,      // node spacing in units of btherm: (2 vhigh/8)/btherm
+    S_XOFF,      // -vhigh/btherm
+    S_Q,         // exp(-2 step^2): second-order ratio of the Gaussian recurrence across nodes
+    S_KW0,       // 7 kernel weights x deltav                           singleabs.h:152-163
+    S_XU2 = S_KW0 + 7,  // x^2 beyond which exp(-x^2) is negligible against the damping wing
+    S_XU,        // sqrt of it
+    S_ZMAX,      // floor(vel/bintov)
+    S_MODE,      // 0 skip, 1 fast, 2 exact
+    S_K16,       // exp(-2 D^2), D = 16 pixels in units of btherm: march-step recurrence, half warps
+    S_K32,       // same for D = 32 pixels
+    S_LU16,      // exp(+2 D16 step): ratio update of the inter-node factor, upward march
+    S_LU32,
+    S_LD16,      // exp(-2 D16 step): downward march
+    S_LD32,
+    S_RECMAX,    // largest pixel count per step (0, 16 or 32) for which the recurrence is safe
+    S_COUNT
+};
+enum LineField {
+    L_CD = 0,    // amp*dens/velfac
+    L_Y,         // aa = voigt_fac/btherm
+    L_PE0,       // Pe(s): 4 coefficients (exact mode: L_PE0 holds erfcx(aa))
+    L_A0 = L_PE0 + 4,
+    L_BQ0 = L_A0 + 4,   // sum_i kw_i B(s_i) as a quartic in xb: 5 coefficients
+    L_B0 = L_BQ0 + 5,   // B(s): 3 raw coefficients (generic route)
+    L_COUNT = L_B0 + 3
+};
+template <int NL> struct SlabSize { static constexpr int kDoubles = (S_COUNT + NL * L_COUNT) * kBatch; };
+
+#define SF(f) sl[(f) * kBatch]
+#define LF(l, f) sl[(S_COUNT + (l) * L_COUNT + (f)) * kBatch]
+
+// ---- node sums ------------------------------------------------------------------------------------
+// All return sum_i kw_i H(x_i, y_l) for x_i = xb + (i+1) step, per fused line l.
+
+// NEAR: every node at |x| < 16.  U0 = exp(-x_1^2), R = exp(-(2 x_1 + step) step), q = exp(-2 step^2)
+// (U0 = R = 0 when the Gaussian is negligible).  The table Horner runs node-interleaved (7
+// independent chains); x and s are recomputed where needed rather than kept live, and the Gaussians
+// are produced on the fly by the node recurrence.  Lanes with nodes beyond the table compute
+// finite garbage that the caller discards.
+template <int NL>
+__device__ __forceinline__ void node_sum_near(double xb, double step, const double *__restrict__ sl,
+                                              const double *__restrict__ tab, double U0, double R, unsigned lmask,
+                                              double (&tot)[NL])
+{
+    static_assert(FSB_GTAB_DEG == 7, "node_sum_near is written for a degree-7 table");
+    double t[7], g[7];
+    {
+        double2 c[7];
+        const double2 *base[7];
+        #pragma unroll
+        for (int i = 0; i < 7; ++i) {
+            int k;
+            g_index(fabs(fma((double) (i + 1), step, xb)), k, t[i]);
+            k = (int) min((unsigned) k, (unsigned) (FSB_GTAB_NINT - 1));
+            base[i] = reinterpret_cast<const double2 *>(tab + k * FSB_GTAB_STRIDE);
+        }
+        #pragma unroll
+        for (int i = 0; i < 7; ++i) c[i] = base[i][3];
+        #pragma unroll
+        for (int i = 0; i < 7; ++i) g[i] = fma(c[i].y, t[i], c[i].x);
+        #pragma unroll
+        for (int j = 2; j >= 0; --j) {
+            #pragma unroll
+            for (int i = 0; i < 7; ++i) c[i] = base[i][j];
+            #pragma unroll
+            for (int i = 0; i < 7; ++i) g[i] = fma(g[i], t[i], c[i].y);
+            #pragma unroll
+            for (int i = 0; i < 7; ++i) g[i] = fma(g[i], t[i], c[i].x);
+        }
+    }
+    // t[] is reused for s = x^2
+    #pragma unroll
+    for (int i = 0; i < 7; ++i) {
+        const double x = fma((double) (i + 1), step, xb);
+        t[i] = x * x;
+    }
+    const double q = SF(S_Q);
+    #pragma unroll
+    for (int l = 0; l < NL; ++l) {
+        if (NL > 1 && !((lmask >> l) & 1u)) {
+            tot[l] = 0;
+            continue;
+        }
+        const double a0 = LF(l, L_A0), a1 = LF(l, L_A0 + 1), a2 = LF(l, L_A0 + 2), a3 = LF(l, L_A0 + 3);
+        const double p0 = LF(l, L_PE0), p1 = LF(l, L_PE0 + 1), p2 = LF(l, L_PE0 + 2), p3 = LF(l, L_PE0 + 3);
+        double acc = fma(fma(fma(fma(LF(l, L_BQ0 + 4), xb, LF(l, L_BQ0 + 3)), xb, LF(l, L_BQ0 + 2)), xb, LF(l, L_BQ0 + 1)), xb,
+                         LF(l, L_BQ0));
+        double u = U0, r = R;
+        #pragma unroll
+        for (int i = 0; i < 7; ++i) {
+            const double A = fma(fma(fma(a3, t[i], a2), t[i], a1), t[i], a0);
+            const double Pe = fma(fma(fma(p3, t[i], p2), t[i], p1), t[i], p0);
+            acc = fma(fma(u, Pe, g[i] * A), SF(S_KW0 + i), acc);
+            u *= r;
+            r *= q;
+        }
+        tot[l] = acc;
+    }
+}
+
+// FAR: every node at |x| >= 16 (the Gaussian is < e^-256).  Lanes with nodes inside compute garbage
+// (possibly inf/NaN) that the caller discards.
+template <int NL>
+__device__ __forceinline__ void node_sum_far(double xb, double step, const double *__restrict__ sl, unsigned lmask,
+                                             double (&tot)[NL])
+{
+    const double isp = 0.56418958354775628694807945156;
+    double u[7], p1[7], p3[7], p5[7];
+    #pragma unroll
+    for (int i = 0; i < 7; ++i) {
+        const double x = fma((double) (i + 1), step, xb);
+        u[i] = 1.0 / (x * x);
+    }
+    #pragma unroll
+    for (int i = 0; i < 7; ++i) far_polys(u[i], p1[i], p3[i], p5[i]);
+    #pragma unroll
+    for (int l = 0; l < NL; ++l) {
+        if (NL > 1 && !((lmask >> l) & 1u)) {
+            tot[l] = 0;
+            continue;
+        }
+        const double y = LF(l, L_Y), y2 = y * y;
+        double acc = 0;
+        #pragma unroll
+        for (int i = 0; i < 7; ++i) {
+            const double v = y2 * u[i];
+            acc = fma(u[i] * fma(v, fma(v, p5[i], -p3[i]), p1[i]), SF(S_KW0 + i), acc);
+        }
+        tot[l] = isp * y * acc;
+    }
+}
+
+// Generic per-node evaluation at velocity offset vouter for ONE line (mixed near/far warp steps and
+// sub-sampled pixels).
+__device__ __noinline__ double node_sum_generic(double vouter, const double *__restrict__ sl, int l,
+                                                const double *__restrict__ tab)
+{
+    FastCoef fc;
+    #pragma unroll
+    for (int i = 0; i < 4; ++i) fc.pe[i] = LF(l, L_PE0 + i);
+    #pragma unroll
+    for (int i = 0; i < 4; ++i) fc.a[i] = LF(l, L_A0 + i);
+    #pragma unroll
+    for (int i = 0; i < 3; ++i) fc.b[i] = LF(l, L_B0 + i);
+    fc.xU2 = SF(S_XU2);
+    fc.y = LF(l, L_Y);
+    const double xb = fma(-vouter, SF(S_INVB), SF(S_XOFF)), step = SF(S_STEP);
+    double total = 0;
+    #pragma unroll 1
+    for (int i = 0; i < 7; ++i) total = fma(voigt_fast(fma((double) (i + 1), step, xb), fc, tab), SF(S_KW0 + i), total);
+    return total;
+}
+
+__device__ __noinline__ double node_sum_exact(double vouter, const double *__restrict__ sl, int l)
+{
+    const double xb = fma(-vouter, SF(S_INVB), SF(S_XOFF)), step = SF(S_STEP);
+    const double y = LF(l, L_Y), erfcx_y = LF(l, L_PE0);
+    double total = 0;
+    #pragma unroll 1
+    for (int i = 0; i < 7; ++i) total += voigt_exact(fma((double) (i + 1), step, xb), y, erfcx_y) * SF(S_KW0 + i);
+    return total;
+}
+
+// Pixel average tau_kern_outer (singleabs.h:104-126) for one line through the generic / exact
+// evaluators; returns the node sum (callers multiply by the amplitude) and the number of inner sums.
+template <bool EXACT>
+__device__ __noinline__ double pixel_sum_slow(double vlow, double vhigh_px, const double *__restrict__ sl, int l,
+                                              const double *__restrict__ tab, int &ninner)
+{
+    const double width = vhigh_px - vlow;
+    if (width < SF(S_HALFB)) {
+        ninner = 1;
+        const double vmid = (vhigh_px + vlow) / 2.;
+        return EXACT ? node_sum_exact(vmid, sl, l) : node_sum_generic(vmid, sl, l, tab);
+    }
+    const int npoints = (int) (2 * ceil(width / SF(S_HALFB) / 2) + 1.);
+    const double dv = width / (npoints - 1);
+    double total = 0;
+    for (int i = 0; i < npoints; ++i) {
+        const double v = (i == 0) ? vlow : ((i == npoints - 1) ? vhigh_px : i * dv + vlow);
+        const double wgt = (i == 0 || i == npoints - 1) ? 0.5 : 1.0;
+        total += wgt * (EXACT ? node_sum_exact(v, sl, l) : node_sum_generic(v, sl, l, tab));
+    }
+    ninner = npoints;
+    return total / (npoints - 1);
+}
+
+struct Tally {
+    unsigned pix = 0, inner = 0, iter = 0;
+    unsigned route[5] = {0, 0, 0, 0, 0};  // near+U, near, far, mixed, slow
+};
+
+// Outward pixel march of one particle (absorption.cpp:250-278) for NL fused lines.
+// live[l]: bit 0 = the upward run of line l is still going, bit 1 = the downward run.
+template <int NL, bool EXACT, bool COUNT>
+__device__ __forceinline__ void march(const double *__restrict__ sl, const double *__restrict__ tab, double *__restrict__ row0,
+                                      int64_t line_stride, int nbins, double bintov, double tautail, int lane, Tally &tally)
+{
+    const int half = nbins / 2;
+    const double vel = SF(S_VEL), inv_b = SF(S_INVB), step = SF(S_STEP), xoff = SF(S_XOFF);
+    const int zmax = (int) SF(S_ZMAX);
+    const int j0 = wrap_bin(zmax, nbins);
+    // pixel width >= btherm/2 anywhere?  (bintov is rounded differently per pixel by at most an ulp)
+    const bool any_sub = !(bintov * (1 + 1e-12) < SF(S_HALFB));
+    const int recmax = EXACT ? 0 : (int) SF(S_RECMAX);
+    const double xu = SF(S_XU);
+    const unsigned lt_mask = (1u << lane) - 1u;
+    unsigned live[NL];
+    #pragma unroll
+    for (int l = 0; l < NL; ++l) live[l] = half > 0 ? 3u : 0u;
+    int base_up = 0, base_dn = 0;
+    double U0 = 0, R = 0, rho = 0;  // Gaussian recurrence state of this lane
+    int rec_cfg = -1;               // lane->pixel mapping the state belongs to: 0 both, 1 up only, 2 down only
+    for (;;) {
+        unsigned any = 0;
+        #pragma unroll
+        for (int l = 0; l < NL; ++l) any |= live[l];
+        if (!any) break;
+        const bool both = any == 3u;
+        const int dir = both ? (lane >> 4) : (int) (any >> 1);
+        const int sub = both ? (lane & 15) : lane;
+        const int npx = both ? 16 : 32;
+        const int o = (dir ? base_dn : base_up) + sub;  // outward pixel index
+        const bool mine = o < half;
+        const int z = dir ? zmax - 1 - o : zmax + o;
+        int j = dir ? j0 - 1 - o : j0 + o;  // z mod nbins: |z - zmax| <= nbins/2
+        j += j < 0 ? nbins : (j >= nbins ? -nbins : 0);
+        // lanes of my direction below me, lanes of the upward / downward run
+        const unsigned grp_lt = both ? (lt_mask & (dir ? 0xffff0000u : 0x0000ffffu)) : lt_mask;
+        const unsigned up_lanes = both ? 0x0000ffffu : (dir ? 0u : kFull);
+        const unsigned dn_lanes = both ? 0xffff0000u : (dir ? kFull : 0u);
+        unsigned lmask = 0;  // lines with a live run among the directions of this step
+        #pragma unroll
+        for (int l = 0; l < NL; ++l) lmask |= (live[l] & (both ? 3u : (1u << dir))) ? (1u << l) : 0u;
+        // start the read of the output pixels now; they are consumed after the quadrature
+        double cur[NL];
+        #pragma unroll
+        for (int l = 0; l < NL; ++l) {
+            cur[l] = 0;
+            if (mine && ((live[l] >> dir) & 1u)) cur[l] = row0[l * line_stride + j];
+        }
+        const double vlow = __dsub_rn(__dmul_rn((double) z, bintov), vel);
+        const double vhigh_px = __dadd_rn(vlow, bintov);
+        double t[NL];
+        int ninner = 1;
+        if (EXACT || any_sub) {
+            rec_cfg = -1;
+            if (COUNT) ++tally.route[4];
+            #pragma unroll
+            for (int l = 0; l < NL; ++l) {
+                t[l] = 0;
+                if (mine && ((lmask >> l) & 1u)) t[l] = LF(l, L_CD) * pixel_sum_slow<EXACT>(vlow, vhigh_px, sl, l, tab, ninner);
+            }
+        } else {
+            const double vmid = (vhigh_px + vlow) / 2.;
+            const double xb = fma(-vmid, inv_b, xoff);
+            const double x1 = xb + step, x7 = fma(7.0, step, xb);  // x1 <= x7
+            // lane class: 0 every node inside |x| < 16, 1 every node outside, 2 straddling, 3 idle
+            const int lc = !mine ? 3 : ((x1 > -FSB_GTAB_XMAX && x7 < FSB_GTAB_XMAX) ? 0 : ((x1 >= FSB_GTAB_XMAX || x7 <= -FSB_GTAB_XMAX) ? 1 : 2));
+            const bool core = mine && !(x1 >= xu || x7 <= -xu);  // within reach of the Gaussian
+            const unsigned cls = __reduce_or_sync(kFull, (1u << lc) | (core ? 16u : 0u));
+            double tot[NL];
+            #pragma unroll
+            for (int l = 0; l < NL; ++l) tot[l] = 0;
+            const bool pure_near = !(cls & 6u);
+            if (cls & 1u) {
+                if (cls & 16u) {
+                    const int cfg = both ? 0 : 1 + dir;
+                    if (rec_cfg == cfg) {
+                        // one march step outward: x -> x + Delta, Delta = -+ npx pixels
+                        U0 *= rho;
+                        rho *= both ? SF(S_K16) : SF(S_K32);
+                        R *= both ? (dir ? SF(S_LD16) : SF(S_LU16)) : (dir ? SF(S_LD32) : SF(S_LU32));
+                    } else {
+                        U0 = exp(-x1 * x1);
+                        R = exp(-fma(2.0, x1, step) * step);
+                        if (npx <= recmax) {
+                            const double delta = (dir ? (double) npx : (double) -npx) * (bintov * inv_b);
+                            rho = exp(-fma(2.0, x1, delta) * delta);
+                        }
+                    }
+                    rec_cfg = (npx <= recmax && pure_near) ? cfg : -1;
+                    if (COUNT) ++tally.route[0];
+                } else {
+                    U0 = 0;
+                    R = 0;
+                    rec_cfg = -1;
+                    if (COUNT) ++tally.route[1];
+                }
+                node_sum_near<NL>(xb, step, sl, tab, U0, R, lmask, tot);
+            } else {
+                rec_cfg = -1;
+            }
+            if (cls & 2u) {
+                double tfar[NL];
+                node_sum_far<NL>(xb, step, sl, lmask, tfar);
+                #pragma unroll
+                for (int l = 0; l < NL; ++l) tot[l] = lc == 1 ? tfar[l] : tot[l];
+                if (COUNT) ++tally.route[2];
+            }
+            if (cls & 4u) {  // lanes whose own nodes straddle |x| = 16: node by node
+                if (lc == 2) {
+                    #pragma unroll
+                    for (int l = 0; l < NL; ++l)
+                        if ((lmask >> l) & 1u) tot[l] = node_sum_generic(vmid, sl, l, tab);
+                }
+                if (COUNT) ++tally.route[3];
+            }
+            #pragma unroll
+            for (int l = 0; l < NL; ++l) t[l] = LF(l, L_CD) * tot[l];
+        }
+        // add, then stop each run at its first pixel below tautail (absorption.cpp:260-263,274-277)
+        const bool up_done = base_up + npx >= half, dn_done = base_dn + npx >= half;
+        #pragma unroll
+        for (int l = 0; l < NL; ++l) {
+            const bool on = mine && ((live[l] >> dir) & 1u);
+            const unsigned stop = __ballot_sync(kFull, on && (t[l] < tautail));
+            if (on && !(stop & grp_lt)) {  // no lane of my run below me has stopped
+                row0[l * line_stride + j] = cur[l] + t[l];
+                if (COUNT) {
+                    ++tally.pix;
+                    tally.inner += ninner;
+                }
+            }
+            if ((stop & up_lanes) || (up_lanes && up_done)) live[l] &= ~1u;
+            if ((stop & dn_lanes) || (dn_lanes && dn_done)) live[l] &= ~2u;
+        }
+        base_up += up_lanes ? npx : 0;
+        base_dn += dn_lanes ? npx : 0;
+        if (COUNT) ++tally.iter;
+        __syncwarp();
+    }
+}
+
+template <int NL, bool COUNT>
+__device__ __noinline__ void march_exact(const double *__restrict__ sl, const double *__restrict__ tab, double *__restrict__ row0,
+                                         int64_t line_stride, int nbins, double bintov, double tautail, int lane, Tally &tally)
+{
+    march<NL, true, COUNT>(sl, tab, row0, line_stride, nbins, bintov, tautail, lane, tally);
+}
+
+// Per-particle constants, one particle per lane (absorption.cpp:218-246, singleabs.h:81-90).
+template <int KERNEL, int NL>
+__device__ __noinline__ void setup_particle(const InterpConsts &C, double *__restrict__ sl, int64_t k, int ax,
+                                               const int32_t *__restrict__ particle, const double *__restrict__ dr2s,
+                                               const float *__restrict__ pos, const float *__restrict__ vel,
+                                               const float *__restrict__ dens, const float *__restrict__ temp,
+                                               const float *__restrict__ hsml, const float *__restrict__ cells)
+{
+    const int64_t ip = particle[k];
+    const float ppos = pos[3 * ip + ax], pvel = vel[3 * ip + ax];
+    const float pdens = dens[ip], ptemp = temp[ip];
+    double dr2;
+    float smooth;
+    if (KERNEL == FSB_KERNEL_VORONOI) {
+        dr2 = (double) cells[2 * k];
+        smooth = cells[2 * k + 1];
+    } else {
+        dr2 = dr2s[k];
+        smooth = hsml[ip];
+    }
+    double pos1 = (double) ppos;
+    int mode = 1;
+    if (KERNEL == FSB_KERNEL_VORONOI) {
+        const double lim = 2 * C.vbox / C.velfac;
+        if (dr2 > lim || (double) smooth > lim) mode = 0;
+        pos1 = __dmul_rn(__dadd_rn(dr2, (double) smooth), 0.5);
+    } else {
+        if (__dsub_rn((double) __fmul_rn(smooth, smooth), dr2) <= 0) mode = 0;
+    }
+    const double btherm = C.bfac * sqrt((double) ptemp);
+    const double velp = __dadd_rn(__dmul_rn(C.velfac, pos1), (double) pvel);
+    double vdr2 = C.velfac * dr2;
+    if (KERNEL != FSB_KERNEL_VORONOI) vdr2 *= C.velfac;
+    const double vsmooth = C.velfac * (double) smooth;
+    const double inv_b = 1.0 / btherm;
+    double vhigh = (vsmooth * vsmooth > vdr2) ? sqrt(vsmooth * vsmooth - vdr2) : 0;
+    if (KERNEL == FSB_KERNEL_VORONOI) vhigh = (vdr2 > 0 && vsmooth > 0) ? (vsmooth - vdr2) / 2. : 0;
+    const double deltav = 2. * vhigh / kNGrid;
+    const double step = deltav * inv_b;
+    const bool force_exact = C.voigt == FSB_VOIGT_EXACT;
+    SF(S_VEL) = velp;
+    SF(S_INVB) = inv_b;
+    SF(S_HALFB) = btherm / 2.;
+    SF(S_STEP) = step;
+    SF(S_XOFF) = -vhigh * inv_b;
+    SF(S_Q) = exp(-2.0 * step * step);
+    double kw[7];
+    #pragma unroll
+    for (int i = 1; i < kNGrid; ++i) {
+        const double vv = i * deltav - vhigh;
+        kw[i - 1] = sph_kernel<KERNEL>(sqrt(vdr2 + vv * vv) / vsmooth) * deltav;
+        SF(S_KW0 + i - 1) = kw[i - 1];
+    }
+    // moments of the node weights about xb, in units of btherm: M_n = sum kw_i (i step)^n
+    double M[5] = {0, 0, 0, 0, 0};
+    #pragma unroll
+    for (int i = 0; i < 7; ++i) {
+        const double d = (i + 1) * step;
+        double p = kw[i];
+        #pragma unroll
+        for (int n = 0; n < 5; ++n) {
+            M[n] += p;
+            p *= d;
+        }
+    }
+    SF(S_ZMAX) = floor(velp / C.bintov);
+    // march-step recurrence factors: D = npx pixels in units of btherm
+    const double pix = C.bintov * inv_b;
+    const double D16 = 16.0 * pix, D32 = 32.0 * pix;
+    SF(S_K16) = exp(-2.0 * D16 * D16);
+    SF(S_K32) = exp(-2.0 * D32 * D32);
+    SF(S_LU16) = exp(2.0 * D16 * step);
+    SF(S_LU32) = exp(2.0 * D32 * step);
+    SF(S_LD16) = exp(-2.0 * D16 * step);
+    SF(S_LD32) = exp(-2.0 * D32 * step);
+    // every factor stays within e^+-500 while a lane is within reach of the Gaussian core
+    SF(S_RECMAX) = (step <= 1.0 && D32 <= 10.0) ? 32.0 : ((step <= 1.0 && D16 <= 10.0) ? 16.0 : 0.0);
+    double ymin = 1e300;
+    #pragma unroll
+    for (int l = 0; l < NL; ++l) {
+        const double aa = C.line[l].voigt_fac * inv_b;
+        const double amp = C.line[l].sigma_a / kSqrtPi * (kLight / 1e5 * inv_b);
+        if (mode && (force_exact || !fast_domain(aa))) mode = 2;
+        ymin = fmin(ymin, aa);
+        LF(l, L_CD) = amp * (double) pdens / C.velfac;
+        LF(l, L_Y) = aa;
+        FastCoef fc;
+        fast_coefs(aa, fc);
+        #pragma unroll
+        for (int i = 0; i < 4; ++i) LF(l, L_PE0 + i) = fc.pe[i];
+        #pragma unroll
+        for (int i = 0; i < 4; ++i) LF(l, L_A0 + i) = fc.a[i];
+        #pragma unroll
+        for (int i = 0; i < 3; ++i) LF(l, L_B0 + i) = fc.b[i];
+        // sum_i kw_i B((xb + d_i)^2), B(s) = b0 + b1 s + b2 s^2, as a quartic in xb
+        LF(l, L_BQ0) = fma(fc.b[2], M[4], fma(fc.b[1], M[2], fc.b[0] * M[0]));
+        LF(l, L_BQ0 + 1) = fma(4.0 * fc.b[2], M[3], 2.0 * fc.b[1] * M[1]);
+        LF(l, L_BQ0 + 2) = fma(6.0 * fc.b[2], M[2], fc.b[1] * M[0]);
+        LF(l, L_BQ0 + 3) = 4.0 * fc.b[2] * M[1];
+        LF(l, L_BQ0 + 4) = fc.b[2] * M[0];
+    }
+    if (mode == 2) {
+        #pragma unroll
+        for (int l = 0; l < NL; ++l) LF(l, L_PE0) = erfcx(C.line[l].voigt_fac * inv_b);
+    }
+    const double xu2 = ymin > 0 ? 37.0 - log(ymin) : 1e300;
+    SF(S_XU2) = xu2;
+    SF(S_XU) = sqrt(xu2);
+    SF(S_MODE) = (double) mode;
+}
+
+template <int KERNEL, int NL, bool COUNT>
+__global__ void __launch_bounds__(kTauThreads, FSB_TAU_MIN_BLOCKS)
+k_tau(InterpConsts C, Items items, int n_items, int *__restrict__ next_item, const int64_t *__restrict__ offsets,
+      const int32_t *__restrict__ particle, const double *__restrict__ dr2s, const int32_t *__restrict__ axis,
+      const float *__restrict__ pos, const float *__restrict__ vel, const float *__restrict__ dens,
+      const float *__restrict__ temp, const float *__restrict__ hsml, const float *__restrict__ cells,
+      double *__restrict__ out, double *__restrict__ scratch, int64_t scratch_stride,
+      unsigned long long *__restrict__ counters)
+{
+    extern __shared__ __align__(16) double smem[];
+    double *tab = smem;  // [FSB_GTAB_SIZE], 16-byte aligned
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *slab = smem + FSB_GTAB_SIZE + warp * SlabSize<NL>::kDoubles;
+    for (int i = threadIdx.x; i < FSB_GTAB_SIZE; i += kTauThreads) tab[i] = d_gtable[i];
+    __syncthreads();
+
+    const int nbins = C.nbins;
+    const int64_t out_stride = (int64_t) C.nlos * nbins;
+    Tally tally;
+    unsigned long long n_pairs = 0;
+
+    for (;;) {
+        int item = 0;
+        if (lane == 0) item = atomicAdd(next_item, 1);
+        item = __shfl_sync(kFull, item, 0);
+        if (item >= n_items) break;
+        int line;
+        int64_t kbeg, kend;
+        if (!locate_item(items, offsets, C.nlos, item, line, kbeg, kend)) continue;
+        double *row0 = items.item_start ? scratch + (int64_t) item * nbins : out + (int64_t) line * nbins;
+        const int64_t line_stride = items.item_start ? scratch_stride : out_stride;
+        const int ax = axis[line] - 1;
+        n_pairs += (unsigned long long) (kend - kbeg);
+
+        for (int64_t k0 = kbeg; k0 < kend; k0 += kBatch) {
+            const int nb = (int) min((int64_t) kBatch, kend - k0);
+            __syncwarp();
+            if (lane < nb) setup_particle<KERNEL, NL>(C, slab + lane, k0 + lane, ax, particle, dr2s, pos, vel, dens, temp, hsml, cells);
+            __syncwarp();
+            for (int b = 0; b < nb; ++b) {
+                const double *sl = slab + b;
+                const int mode = (int) SF(S_MODE);
+                if (mode == 0) continue;
+                if (mode == 2) march_exact<NL, COUNT>(sl, tab, row0, line_stride, nbins, C.bintov, C.tautail, lane, tally);
+                else march<NL, false, COUNT>(sl, tab, row0, line_stride, nbins, C.bintov, C.tautail, lane, tally);
+            }
+        }
+    }
+    if (COUNT) {
+        unsigned long long pix = tally.pix, vg = 7ull * tally.inner;
+        #pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            pix += __shfl_down_sync(kFull, pix, d);
+            vg += __shfl_down_sync(kFull, vg, d);
+        }
+        if (lane == 0) {
+            atomicAdd(&counters[0], n_pairs);
+            atomicAdd(&counters[1], pix);
+            atomicAdd(&counters[2], vg);
+            atomicAdd(&counters[3], 32ull * tally.iter * NL);
+            #pragma unroll
+            for (int r = 0; r < 5; ++r) atomicAdd(&counters[4 + r], (unsigned long long) tally.route[r]);
+        }
+    }
+}
+
+#undef SF
+#undef LF
+
+__global__ void k_voigt_profile(const double *__restrict__ x, const double *__restrict__ y, double *__restrict__ out,
+                                int64_t n, int voigt)
+{
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double yy = y[i];
+    if (voigt == FSB_VOIGT_FAST && fast_domain(yy)) {
+        FastCoef fc;
+        fast_coefs(yy, fc);
+        out[i] = voigt_fast(x[i], fc, d_gtable);
+    } else {
+        out[i] = voigt_exact(x[i], yy, erfcx(yy));
+    }
+}
+
+template <int KERNEL, int NL>
+int launch_tau_k(const fsb_index *idx, const InterpConsts &c, const ItemPlan &plan, int *next_item, const float *pos,
+                 const float *vel, const float *dens, const float *temp, const float *h, const float *cells, double *out,
+                 unsigned long long *ctr, cudaStream_t stream)
+{
+    int dev = 0, sms = 0, per_sm = 0;
+    FSB_CUDA_TRY(cudaGetDevice(&dev));
+    FSB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const size_t smem = sizeof(double) * (size_t) (FSB_GTAB_SIZE + kTauWarps * SlabSize<NL>::kDoubles);
+    const int n_items = (int) plan.n_items;
+    auto go = [&](auto kern) -> int {
+        FSB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        FSB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTauThreads, smem));
+        const int grid = std::max(1, std::min((n_items + kTauWarps - 1) / kTauWarps, sms * std::max(per_sm, 1)));
+        count_launch();
+        kern<<<grid, kTauThreads, smem, stream>>>(c, plan.items, n_items, next_item, idx->offsets, idx->particle, idx->dr2, idx->axis,
+                                                  pos, vel, dens, temp, h, cells, out, plan.scratch_rows.as<double>(),
+                                                  plan.n_items * (int64_t) c.nbins, ctr);
+        FSB_CUDA_TRY(cudaGetLastError());
+        return FSB_OK;
+    };
+    return ctr ? go(k_tau<KERNEL, NL, true>) : go(k_tau<KERNEL, NL, false>);
+}
+
+template <int NL>
+int launch_tau_nl(const fsb_index *idx, const InterpConsts &c, const ItemPlan &plan, int *next_item, const float *pos,
+                  const float *vel, const float *dens, const float *temp, const float *h, const float *cells, double *out,
+                  unsigned long long *ctr, cudaStream_t stream)
+{
+    switch (c.kernel) {
+    case FSB_KERNEL_TOPHAT: return launch_tau_k<FSB_KERNEL_TOPHAT, NL>(idx, c, plan, next_item, pos, vel, dens, temp, h, cells, out, ctr, stream);
+    case FSB_KERNEL_CUBIC: return launch_tau_k<FSB_KERNEL_CUBIC, NL>(idx, c, plan, next_item, pos, vel, dens, temp, h, cells, out, ctr, stream);
+    case FSB_KERNEL_VORONOI: return launch_tau_k<FSB_KERNEL_VORONOI, NL>(idx, c, plan, next_item, pos, vel, dens, temp, h, cells, out, ctr, stream);
+    case FSB_KERNEL_QUINTIC: return launch_tau_k<FSB_KERNEL_QUINTIC, NL>(idx, c, plan, next_item, pos, vel, dens, temp, h, cells, out, ctr, stream);
+    default: set_error("unknown kernel id %d", c.kernel); return FSB_EINVAL;
+    }
+}
+
+}  // namespace
+
+int tau_max_fused_lines() { return kMaxTauLines; }
+
+// c.nlines (1..kMaxTauLines) lines of one ion in one pass; out[l][nlos][nbins].
+int launch_tau(const fsb_index *idx, const InterpConsts &c, const float *pos, const float *vel, const float *dens,
+               const float *temp, const float *h, const float *cells, double *out, fsb_counters *counters, int precision,
+               cudaStream_t stream)
+{
+    (void) precision;
+    if (idx->nlos == 0 || idx->npairs == 0) return FSB_OK;
+    if (c.nlines < 1 || c.nlines > kMaxTauLines) {
+        set_error("launch_tau: %d fused lines (1..%d)", c.nlines, kMaxTauLines);
+        return FSB_EINVAL;
+    }
+    ItemPlan plan;
+    FSB_TRY(plan_items(idx, c.seg_pairs, c.nbins, c.nlines, stream, plan));
+    Scratch next_item;
+    FSB_TRY(next_item.alloc(sizeof(int), stream));
+    FSB_CUDA_TRY(cudaMemsetAsync(next_item.ptr, 0, sizeof(int), stream));
+    unsigned long long *ctr = reinterpret_cast<unsigned long long *>(counters);
+    if (c.nlines == 1) FSB_TRY(launch_tau_nl<1>(idx, c, plan, next_item.as<int>(), pos, vel, dens, temp, h, cells, out, ctr, stream));
+    else FSB_TRY(launch_tau_nl<2>(idx, c, plan, next_item.as<int>(), pos, vel, dens, temp, h, cells, out, ctr, stream));
+    FSB_TRY(reduce_items(plan, idx, c.nbins, c.nlines, out, stream));
+    return FSB_OK;
+}
+
+int launch_voigt(const double *x, const double *y, double *out, int64_t n, int voigt, cudaStream_t stream)
+{
+    if (n <= 0) return FSB_OK;
+    count_launch(); k_voigt_profile<<<(unsigned) ((n + 255) / 256), 256, 0, stream>>>(x, y, out, n, voigt);
+    FSB_CUDA_TRY(cudaGetLastError());
+    return FSB_OK;
+}
+
+}  // namespace fsb

@@ -5,9 +5,11 @@
 // voigt fast  : this library's own evaluation for the small damping parameters of real lines
 //               (0 <= y <= kFastYMax): expansion of w about the real axis to order y^7,
 //                   H(x,y) = U(x) Pe(s) + G(x) A(s) + B(s),   s = x^2,  U = exp(-s),
-//                   G(x) = 1 - 2 x Dawson(x)   (piecewise degree-10 polynomials, |x| < 16),
+//                   G(x) = 1 - 2 x Dawson(x)   (129 piecewise degree-7 polynomials, |x| < 16),
 //               with Pe, A, B polynomials in s whose coefficients depend on y only (per-particle
-//               constants), and the large-|z| asymptotic series of w beyond |x| >= 16.
+//               constants).  Beyond |x| >= 16 the Gaussian has vanished and the profile is the
+//               Taylor series in y of the damping wing, -y L' + y^3 L'''/6 - y^5 L^(5)/120 with
+//               L = Im w on the real axis expanded in u = 1/x^2 (polynomials P1, P3, P5 below).
 //               Agrees with voigt_exact to < 3e-13 relative on its domain (tests/test_gpu_parity).
 #pragma once
 
@@ -172,10 +174,9 @@ __device__ double voigt_exact(double xin, double y, double erfcx_y)
 
 constexpr double kFastYMax = 0.03;    // above: voigt_exact (error of the y^7 truncation < 3e-13 below)
 constexpr double kFastYMin = 1e-30;   // below (and > 0): voigt_exact (Gaussian cut-off would pass exp underflow)
-constexpr int kGTabStride = FSB_GTAB_NINT;
 
 // Global-memory master copy of the G(x) table; kernels stage it in shared memory.
-__device__ const double d_gtable[FSB_GTAB_SIZE] = FSB_GTAB_VALUES;
+__device__ __align__(16) const double d_gtable[FSB_GTAB_SIZE] = FSB_GTAB_VALUES;
 
 // y-dependent polynomial coefficients (derived with sympy from w' = -2zw + 2i/sqrt(pi)).
 struct FastCoef {
@@ -207,44 +208,64 @@ __device__ __forceinline__ void fast_coefs(double y, FastCoef &c)
     c.y = y;
 }
 
-// G(|x|) for |x| < 16.125 from the staged table (tab may be shared or global memory).
-__device__ __forceinline__ double g_table(double ax, const double *__restrict__ tab)
+// Table index and offset of |x| < 16: k = rint(8|x|), t = |x| - k/8.
+__device__ __forceinline__ void g_index(double ax, int &k, double &t)
 {
-    const double magic = 6755399441055744.0;  // 1.5 * 2^52: low mantissa bits = rint(4|x|)
-    const double m = fma(ax, 4.0, magic);
-    int k = __double2loint(m);
-    const double t = fma(m - magic, -0.25, ax);
-    k = k > FSB_GTAB_NINT - 1 ? FSB_GTAB_NINT - 1 : k;
-    const double *c = tab + k;
-    double g = c[FSB_GTAB_DEG * kGTabStride];
-    #pragma unroll
-    for (int j = FSB_GTAB_DEG - 1; j >= 0; --j) g = fma(g, t, c[j * kGTabStride]);
-    return g;
+    const double magic = 6755399441055744.0;  // 1.5 * 2^52: low mantissa bits = rint(8|x|)
+    const double m = fma(ax, FSB_GTAB_INV_DELTA, magic);
+    k = __double2loint(m);
+    t = fma(m - magic, -1.0 / FSB_GTAB_INV_DELTA, ax);
 }
 
-// |x| >= 16: Re[(i/sqrt(pi)) (1/z) S(1/z^2)], S = sum (2k-1)!!/2^k u^k to k = 8 (next term < 1e-14).
-__device__ __forceinline__ double voigt_far(double ax, double s, double y)
+// Degree-7 polynomial of interval k at offset t: four 16-byte loads (tab 16-byte aligned).
+__device__ __forceinline__ double g_eval(const double *__restrict__ tab, int k, double t)
+{
+    const double2 *c = reinterpret_cast<const double2 *>(tab + k * FSB_GTAB_STRIDE);
+    const double2 c67 = c[3], c45 = c[2], c23 = c[1], c01 = c[0];
+    double g = fma(c67.y, t, c67.x);
+    g = fma(g, t, c45.y);
+    g = fma(g, t, c45.x);
+    g = fma(g, t, c23.y);
+    g = fma(g, t, c23.x);
+    g = fma(g, t, c01.y);
+    return fma(g, t, c01.x);
+}
+
+// G(|x|) for |x| < 16 from the staged table (tab may be shared or global memory).
+__device__ __forceinline__ double g_table(double ax, const double *__restrict__ tab)
+{
+    int k;
+    double t;
+    g_index(ax, k, t);
+    k = k > FSB_GTAB_NINT - 1 ? FSB_GTAB_NINT - 1 : k;
+    return g_eval(tab, k, t);
+}
+
+// Damping wing for |x| >= 16, u = 1/x^2:  H = (y/sqrt(pi)) u [P1(u) - (y^2 u) P3(u) + (y^2 u)^2 P5(u)],
+// P1 = sum c_k (2k+1) u^k, P3 = sum c_k C(2k+3,3) u^k, P5 = sum c_k C(2k+5,5) u^k, c_k = (2k-1)!!/2^k.
+// Truncation error < 3e-14 relative for y <= 0.03 (scripts/voigt_design.py).
+__device__ __forceinline__ void far_polys(double u, double &p1, double &p3, double &p5)
+{
+    p1 = fma(fma(fma(fma(fma(fma(fma(15836.1328125, u, 2111.484375), u, 324.84375), u, 59.0625), u, 13.125), u, 3.75), u, 1.5), u, 1.0);
+    p3 = fma(fma(fma(fma(fma(8445.9375, u, 1082.8125), u, 157.5), u, 26.25), u, 5.0), u, 1.0);
+    p5 = fma(10.5, u, 1.0);
+}
+
+__device__ __forceinline__ double voigt_far(double s, double y)
 {
     const double isp = 0.56418958354775628694807945156;
-    const double inv = 1.0 / (s + y * y);
-    const double zr = ax * inv, zi = -y * inv;
-    const double ur = zr * zr - zi * zi, ui = 2 * zr * zi;
-    double sr = 7918.06640625, si = 0;
-    const double cs[8] = {1055.7421875, 162.421875, 29.53125, 6.5625, 1.875, 0.75, 0.5, 1.0};
-    #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const double nr = fma(sr, ur, fma(-si, ui, cs[k]));
-        si = fma(sr, ui, si * ur);
-        sr = nr;
-    }
-    return -isp * fma(zr, si, zi * sr);
+    const double u = 1.0 / s;
+    double p1, p3, p5;
+    far_polys(u, p1, p3, p5);
+    const double v = y * y * u;
+    return isp * y * u * fma(v, fma(v, p5, -p3), p1);
 }
 
 // One profile value with a known U = exp(-x^2) (or 0 where it is negligible).
 __device__ __forceinline__ double voigt_fast_with_u(double ax, double s, double U, const FastCoef &c,
                                                     const double *__restrict__ tab)
 {
-    if (ax >= FSB_GTAB_XMAX) return voigt_far(ax, s, c.y) + U;
+    if (ax >= FSB_GTAB_XMAX) return voigt_far(s, c.y);
     const double G = g_table(ax, tab);
     const double Pe = fma(fma(fma(c.pe[3], s, c.pe[2]), s, c.pe[1]), s, c.pe[0]);
     const double A = fma(fma(fma(c.a[3], s, c.a[2]), s, c.a[1]), s, c.a[0]);
@@ -260,6 +281,7 @@ __device__ __forceinline__ double voigt_fast(double x, const FastCoef &c, const 
     return voigt_fast_with_u(ax, s, U, c, tab);
 }
 
-__device__ __forceinline__ bool fast_domain(double y) { return y == 0.0 || (y >= kFastYMin && y <= kFastYMax); }
+// y == 0 (gamma = 0, spectra.py:669-672) takes the exact path, whose y == 0 branch is exp(-x^2).
+__device__ __forceinline__ bool fast_domain(double y) { return y >= kFastYMin && y <= kFastYMax; }
 
 }  // namespace fsb

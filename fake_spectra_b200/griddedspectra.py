@@ -1,6 +1,9 @@
 """Regular grids of sightlines (host-side mirror of the reference's griddedspectra.py)."""
 import numpy as np
 
+from . import abstractsnapshot as absn
+from . import spectra
+
 
 def grid_axes_and_cofm(box, nspec, axis):
     """Sightline directions and positions on an ``nspec x nspec`` grid perpendicular to ``axis``
@@ -20,3 +23,26 @@ def grid_axes_and_cofm(box, nspec, axis):
         raise ValueError('wrong axis number {}'.format(axis))
     dx = box / (1. * nspec)
     return grid_axes, dx * grid_id
+
+
+class GriddedSpectra(spectra.Spectra):
+    """Regular ``nspec x nspec`` grid of sightlines along ``axis`` (all three axes if ``axis < 0``);
+    constructor arguments as the reference's griddedspectra.py:12-56."""
+
+    def __init__(self, num, base, nspec=200, MPI=None, res=None, nbins=None, savefile="gridded_spectra.hdf5",
+                 reload_file=True, grid_axes=None, grid_cofm=None, axis=1, **kwargs):
+        if reload_file is False:
+            grid_cofm = None
+            grid_axes = None
+        else:
+            f = absn.AbstractSnapshotFactory(num, base)
+            self.box = f.get_header_attr("BoxSize")
+            del f
+            if grid_cofm is None:
+                grid_axes, grid_cofm = self.get_axes_and_cofm(nspec, axis)
+        spectra.Spectra.__init__(self, num, base, cofm=grid_cofm, axis=grid_axes, MPI=MPI, res=res, nbins=nbins,
+                                 savefile=savefile, reload_file=reload_file, **kwargs)
+
+    def get_axes_and_cofm(self, nspec, axis):
+        """Position of the skewers in the grid."""
+        return grid_axes_and_cofm(self.box, nspec, axis)

@@ -1,0 +1,112 @@
+"""Multi-GPU partitioning of the interpolation (one process per GPU, torch.distributed).
+
+Two modes:
+
+* ``"sightlines"`` (default): every rank holds the whole particle set and computes a contiguous
+  block of sightlines; blocks are disjoint rows of the result, so the data path needs NO
+  collective — one all-gather at the end hands every rank the full array (what the reference's
+  Allreduce leaves behind, spectra.py:828-830).
+* ``"particles"``: every rank holds a slice of the particles and computes ALL sightlines for it;
+  the partial [NumLos, nbins] arrays are summed with one all-reduce — the reference's MPI mode
+  (abstractsnapshot.py:195-207, spectra.py:825-831), but in float64 instead of its float32.
+
+The collectives run on whatever device the tensors live on: NCCL over NVLink for CUDA tensors, gloo
+for the CPU tests of this host logic.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def even_blocks(n, world):
+    """Edges [world+1] of contiguous blocks of near-equal size."""
+    return np.linspace(0, n, world + 1).astype(np.int64)
+
+
+def balanced_blocks(weights, world):
+    """Edges [world+1] of contiguous blocks with near-equal total weight (e.g. candidate pairs per
+    sightline): block r ends at the first index whose running weight reaches (r+1)/world of the total."""
+    w = np.asarray(weights, dtype=np.float64)
+    n = w.size
+    if n == 0 or w.sum() <= 0:
+        return even_blocks(n, world)
+    csum = np.cumsum(w)
+    targets = csum[-1] * np.arange(1, world) / world
+    inner = np.searchsorted(csum, targets, side="left") + 1
+    edges = np.concatenate([[0], np.minimum(inner, n), [n]]).astype(np.int64)
+    return np.maximum.accumulate(edges)
+
+
+class Sharder:
+    """Partition + recombination for one Spectra object.
+
+    group : a torch.distributed process group, or None for the default group when
+            torch.distributed is initialised (world of 1 otherwise).
+    mode  : "sightlines" or "particles".
+    """
+
+    def __init__(self, mode="sightlines", group=None):
+        if mode not in ("sightlines", "particles"):
+            raise ValueError("shard must be 'sightlines' or 'particles', not %r" % (mode,))
+        self.mode = mode
+        self.group = group
+        if dist.is_available() and dist.is_initialized():
+            self.rank = dist.get_rank(group)
+            self.size = dist.get_world_size(group)
+        else:
+            self.rank, self.size = 0, 1
+        self.edges = None
+
+    # -- partition -----------------------------------------------------------------------------------
+    def set_sightlines(self, numlos, weights=None):
+        """Fix the sightline blocks (only used in "sightlines" mode)."""
+        if weights is not None:
+            self.edges = balanced_blocks(weights, self.size)
+        else:
+            self.edges = even_blocks(numlos, self.size)
+        return self.edges
+
+    def my_sightlines(self, numlos):
+        """slice of the sightlines this rank computes."""
+        if self.mode != "sightlines" or self.size == 1:
+            return slice(0, numlos)
+        if self.edges is None or self.edges[-1] != numlos:
+            self.set_sightlines(numlos)
+        return slice(int(self.edges[self.rank]), int(self.edges[self.rank + 1]))
+
+    def my_particles(self, npart):
+        """slice of an (already filtered) particle list this rank interpolates."""
+        if self.mode != "particles" or self.size == 1:
+            return slice(0, npart)
+        e = even_blocks(npart, self.size)
+        return slice(int(e[self.rank]), int(e[self.rank + 1]))
+
+    # -- recombination -------------------------------------------------------------------------------
+    def combine(self, local, numlos):
+        """local: this rank's result (torch tensor, any device), [rows, ...] with rows = its
+        sightline block ("sightlines") or all sightlines ("particles").  Returns the full
+        [numlos, ...] tensor on every rank."""
+        if self.size == 1:
+            return local
+        if self.mode == "particles":
+            local = local.contiguous()
+            dist.all_reduce(local, op=dist.ReduceOp.SUM, group=self.group)
+            return local
+        if self.edges is None or self.edges[-1] != numlos:
+            self.set_sightlines(numlos)
+        tail = tuple(local.shape[1:])
+        full = torch.zeros((numlos,) + tail, dtype=local.dtype, device=local.device)
+        sizes = np.diff(self.edges)
+        if np.all(sizes == sizes[0]):
+            dist.all_gather_into_tensor(full, local.contiguous(), group=self.group)
+        else:
+            parts = [full[int(self.edges[r]):int(self.edges[r + 1])] for r in range(self.size)]
+            # all_gather wants equally shaped outputs: pad every block to the largest
+            big = int(sizes.max())
+            padded = torch.zeros((big,) + tail, dtype=local.dtype, device=local.device)
+            padded[:local.shape[0]] = local
+            recv = [torch.empty_like(padded) for _ in range(self.size)]
+            dist.all_gather(recv, padded, group=self.group)
+            for r, p in enumerate(parts):
+                p.copy_(recv[r][:p.shape[0]])
+        return full

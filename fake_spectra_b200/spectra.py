@@ -1,0 +1,685 @@
+"""Host driver of the sightline interpolation: the reference's ``Spectra`` API
+(spectra.py:51-1043: constructor, get_tau, get_col_density, get_density, get_temp, get_velocity,
+get_dens_weighted_density, compute_spectra, particles_near_lines, _do_interpolation_work) on top of
+the sm_100a kernels of libfsb200.so.
+
+Two routes lead to the same kernels:
+
+* drop-in route — ``_do_interpolation_work`` hands host arrays to
+  ``_spectra_priv._Particle_Interpolate`` exactly like the reference does (spectra.py:673);
+* resident route (default on a GPU) — per snapshot segment and ion the filtered particle arrays and
+  the candidate index stay in HBM (:class:`_SegmentEngine`), so that further lines of the ion, the
+  column density and the weighted fields reuse them; the reference rebuilds its index twice per call
+  (spectra.py:560-563 + part_int.cpp:22,55).
+
+With ``torch.distributed`` initialised (one process per GPU) the work is sharded by sightline or by
+particle (:mod:`fake_spectra_b200.sharding`).  There is no CPU fallback: without the CUDA library
+the native calls raise.
+"""
+import os.path as path
+
+import numpy as np
+
+from . import _spectra_priv
+from . import abstractsnapshot as absn
+from . import gas_properties
+from . import line_data
+from . import sharding
+from . import unitsystem
+
+_KERNELS = {"voronoi": 2, "tophat": 0, "quintic": 3, "cubic": 1, "sph": 1}
+_PRECISION = {"fp64": 0, "fp32": 1}
+_VOIGT = {"fast": 0, "exact": 1}
+
+
+class _SegmentEngine:
+    """Device-resident particles of one (segment, element, ion) plus their candidate index."""
+
+    def __init__(self, spec, pos, vel, elem_den, temp, hh):
+        import torch
+        from . import native
+        self.torch, self.native = torch, native
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.dev = dev
+        up = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev)  # noqa: E731
+        self.pos, self.vel, self.dens, self.temp, self.h = up(pos), up(vel), up(elem_den), up(temp), up(hh)
+        self.cofm = torch.from_numpy(np.ascontiguousarray(spec._my_cofm)).to(dev)
+        self.axis = torch.from_numpy(np.ascontiguousarray(spec._my_axis)).to(dev)
+        self.index = native.CandidateIndex(spec.box, self.cofm, self.axis, self.pos, self.h)
+        self.cells = None
+
+    def tau(self, params_list):
+        """float64 CUDA tensor [nlines, nlos_local, nbins]."""
+        if params_list[0].kernel == 2:
+            return self.torch.stack([self.native.particle_interpolate(1, p, self.pos, self.vel, self.dens, self.temp, self.h,
+                                                                      self.axis, self.cofm) for p in params_list])
+        return self.index.compute_tau(list(params_list), self.pos, self.vel, self.dens, self.temp, self.h)
+
+    def colden(self, params, weights=None):
+        """Column density of the ion density (weights None) or of K weight columns
+        [K, npart] float32 CUDA in one geometry pass: float64 [K, nlos_local, nbins]."""
+        dens = self.dens[None, :] if weights is None else weights
+        dens = dens.contiguous()
+        if params.kernel == 2:
+            return self.torch.stack([self.native.particle_interpolate(0, params, self.pos, None, d.contiguous(), None, self.h,
+                                                                      self.axis, self.cofm) for d in dens])
+        return self.index.compute_colden(params, self.pos, dens, self.h)
+
+
+class Spectra:
+    """Interpolates particle densities along sightlines and computes their absorption.
+
+    Positional and keyword arguments are those of the reference (spectra.py:85-87); ``base`` may be
+    an in-memory snapshot object (see :mod:`abstractsnapshot`).  Extensions, keyword only:
+
+    precision  "fp64" (parity mode, <= 1e-10 of the reference) or "fp32" (flux within 1e-5)
+    voigt      "fast" (this library's profile evaluation) or "exact" (restated Faddeeva::w)
+    shard      None, "sightlines" or "particles": partition over the ranks of torch.distributed
+    group      process group (default: the world group)
+    resident   keep particles + candidate index in HBM between calls (default: on when CUDA is there)
+    backend    object providing _Particle_Interpolate / _near_lines (default: the CUDA boundary
+               module; the CPU tests of the host logic pass a checker here)
+    """
+
+    def __init__(self, num, base, cofm, axis, MPI=None, nbins=None, res=1., cdir=None, savefile="spectra.hdf5",
+                 savedir=None, reload_file=False, spec_res=0, load_halo=False, units=None, sf_neutral=True,
+                 turn_off_selfshield=False, quiet=False, load_snapshot=True, gasprop=None, gasprop_args=None,
+                 kernel=None, use_external_Hz=None, precision="fp64", voigt="fast", shard=None, group=None,
+                 resident=None, backend=None):
+        _ = (load_halo, load_snapshot)
+        self.num = num
+        self.base = base
+        self.MPI = MPI
+        if MPI is not None:
+            self.comm = MPI.COMM_WORLD
+            self.rank = self.comm.Get_rank()
+            self.size = self.comm.Get_size()
+        else:
+            self.comm = None
+            self.rank = 0
+            self.size = 1
+        self.units = units if units is not None else unitsystem.UnitSystem()
+        # result caches, keyed like the reference's (spectra.py:109-117)
+        self.tau_obs, self.tau, self.sfr, self.vel_widths, self.absorber_width = {}, {}, {}, {}, {}
+        self.colden, self.velocity, self.temp, self.dens_weight_dens = {}, {}, {}, {}
+        self.part_ind = {}
+        self.cofm_final = False
+        self.num_important = {}
+        self.discarded = 0
+        self.npart = 0
+        self.turn_off_selfshield = turn_off_selfshield
+        self.spec_res = spec_res
+        self.cdir = cdir
+        self.minwidth = 500.
+        self.tautail = 1e-7  # spectra.py:135
+        self.precision = _PRECISION[precision]
+        self.voigt = _VOIGT[voigt]
+        self._backend = backend if backend is not None else _spectra_priv
+        self._sharder = sharding.Sharder(shard, group) if shard is not None else sharding.Sharder("sightlines", group)
+        if shard is None:
+            self._sharder.rank, self._sharder.size = 0, 1  # no partition unless asked for
+        self._engines = {}
+        try:
+            self.snapshot_set = absn.AbstractSnapshotFactory(num, base, comm=self.comm)
+            if kernel is None:
+                self.kernel_int = self.snapshot_set.get_kernel()
+            elif kernel in _KERNELS:
+                self.kernel_int = _KERNELS[kernel]
+            else:
+                raise ValueError("Unrecognised kernel %s" % (kernel,))
+        except IOError:
+            pass
+        if savedir is None and isinstance(base, str):
+            savedir = path.join(base, "snapdir_" + str(num).rjust(3, '0'))
+            if not path.exists(savedir):
+                savedir = path.join(base, "SPECTRA_" + str(num).rjust(3, '0'))
+        self.savefile = path.join(savedir, savefile) if savedir is not None else savefile
+
+        if reload_file:
+            if not quiet:
+                print("Reloading from snapshot (will save to: ", self.savefile, " )", flush=True)
+            if cofm is None or axis is None:
+                raise RuntimeError("None was passed for cofm or axis. If you are trying to load from a savefile, "
+                                   "use reload_file=False.")
+            if np.shape(cofm) == (3,):
+                cofm = np.array([cofm, ])
+            self.cofm = np.asarray(cofm).astype(np.float64)
+            if np.shape(axis) == ():
+                axis = np.array([axis])
+            self.axis = np.asarray(axis).astype(np.int32)
+            try:
+                self.npart = self.snapshot_set.get_npart()
+            except AttributeError as ae:
+                raise IOError("Unable to load snapshot ", num, base) from ae
+            self.box = self.snapshot_set.get_header_attr("BoxSize")
+            self.atime = self.snapshot_set.get_header_attr("Time")
+            self.red = 1 / self.atime - 1.
+            self.hubble = self.snapshot_set.get_header_attr("HubbleParam")
+            self.OmegaM = self.snapshot_set.get_header_attr("Omega0")
+            self.OmegaLambda = self.snapshot_set.get_header_attr("OmegaLambda")
+            self.omegab = self.snapshot_set.get_omega_baryon()
+            try:
+                self.units = self.snapshot_set.get_units()
+            except KeyError:
+                if not quiet:
+                    print('No units found. Using kpc/kms/10^10Msun by default')
+            self.Hz = use_external_Hz if use_external_Hz else None
+        else:
+            if not quiet:
+                print("Reading pre-computed spectra (from file", self.savefile, " )", flush=True)
+            self.load_savefile(self.savefile)
+
+        # conversion factors from internal units (spectra.py:210-232)
+        self.rscale = np.float32((self.units.UnitLength_in_cm * self.atime) / self.hubble)
+        if self.Hz is None:
+            self.Hz = 100.0 * self.hubble * np.sqrt(self.OmegaM / self.atime ** 3 + self.OmegaLambda)
+        self.velfac = self.rscale * self.Hz / 3.085678e24
+        self.vmax = self.box * self.velfac
+        self.NumLos = np.size(self.axis)
+        if reload_file:
+            if res is None:
+                if nbins is not None:
+                    self.nbins = nbins
+                    res = self.vmax / (1. * nbins)
+                else:
+                    raise ValueError('pixel width (res) not provided')
+            if nbins is None:
+                self.nbins = int(self.vmax / res)
+            else:
+                self.nbins = int(nbins)
+            self.dvbin = self.vmax / (1. * self.nbins)
+        else:
+            self.dvbin = self.vmax / (1. * self.nbins)
+            if res is not None:
+                assert np.isclose(self.dvbin, res, rtol=1e-2), 'pixel width error'
+            if use_external_Hz:
+                assert np.isclose(self.Hz, use_external_Hz, rtol=1e-4), 'Hz error'
+        self.species = ['H', 'He', 'C', 'N', 'O', 'Ne', 'Mg', 'Si', 'Fe', 'Z']
+        self.solar = {"H": 1, "He": 0.0851, "C": 2.69e-4, "N": 6.76e-5, "O": 4.9e-4, "Ne": 8.51e-5, "Mg": 3.98e-5,
+                      "Si": 3.24e-5, "Fe": 3.16e-5}
+        self.solarz = 0.0134 / 0.7381
+        self.lines = line_data.LineData()
+        if gasprop is None:
+            gasprop = gas_properties.GasProperties
+        try:
+            gprop_args = {"redshift": self.red, "absnap": self.snapshot_set, "hubble": self.hubble, "units": self.units,
+                          "sf_neutral": sf_neutral}
+            if gasprop_args is not None:
+                gprop_args.update(gasprop_args)
+            self.gasprop = gasprop(**gprop_args)
+        except AttributeError:
+            pass
+        if resident is None:
+            resident = backend is None and self._cuda_available()
+        self.resident = bool(resident)
+        self._set_my_sightlines()
+        if not quiet:
+            print(self.NumLos, " sightlines. resolution: ", self.dvbin, " z=", self.red)
+
+    # ---- partition -----------------------------------------------------------------------------------
+    @staticmethod
+    def _cuda_available():
+        try:
+            import torch
+            return torch.cuda.is_available()
+        except ImportError:
+            return False
+
+    def _set_my_sightlines(self):
+        sl = self._sharder.my_sightlines(self.NumLos)
+        self._my_slice = sl
+        self._my_cofm = np.ascontiguousarray(self.cofm[sl])
+        self._my_axis = np.ascontiguousarray(self.axis[sl])
+        self._engines = {}
+        self.part_ind = {}
+
+    def set_sightlines(self, cofm, axis):
+        """Replace the sightlines (drops cached particle lists, device state and results)."""
+        self.cofm = np.asarray(cofm).astype(np.float64)
+        self.axis = np.asarray(axis).astype(np.int32)
+        self.NumLos = np.size(self.axis)
+        for cache in (self.tau, self.colden, self.velocity, self.temp, self.dens_weight_dens, self.tau_obs):
+            cache.clear()
+        self._set_my_sightlines()
+
+    # ---- savefile (reference spectra.py:266-372,434-499) -----------------------------------------------
+    def load_savefile(self, savefile=None):
+        """The reference keeps results in an HDF5 file; h5py is not part of this environment and the
+        file format is outside the interpolation path."""
+        from . import savefile as sf
+        sf.load(self, savefile)
+
+    def save_file(self):
+        from . import savefile as sf
+        if self._sharder.rank == 0 and self.rank == 0:
+            sf.save(self, self.savefile)
+
+    def _really_load_array(self, key, array, array_name):
+        """Lazy loading of saved arrays: a one-element placeholder means 'on disc'."""
+        if np.size(array[key]) > 1:
+            return
+        from . import savefile as sf
+        array[key] = sf.load_array(self.savefile, array_name, key)
+
+    # ---- particle data (spectra.py:550-617,675-711) ----------------------------------------------------
+    def particles_near_lines(self, pos, hh, axis=None, cofm=None):
+        """Index list of the particles whose kernel reaches at least one sightline."""
+        if axis is None:
+            axis = self._my_axis
+        if cofm is None:
+            cofm = self._my_cofm
+        if np.size(axis) == 0:
+            return np.zeros(0, dtype=np.int32)
+        assert np.min(axis) > 0
+        assert np.max(axis) < 4
+        return self._backend._near_lines(self.box, pos, hh, np.ascontiguousarray(axis, dtype=np.int32),
+                                         np.ascontiguousarray(cofm, dtype=np.float64))
+
+    def get_mass_frac(self, elem, fn, ind):
+        """Mass fraction of an element for the particles ``ind`` of segment ``fn``."""
+        if elem == "Z":
+            mass_frac = self.snapshot_set.get_data(0, "Metallicity", segment=fn).astype(np.float32)
+        else:
+            nelem = self.species.index(elem)
+            try:
+                mass_frac = (self.snapshot_set.get_data(0, "GFM_Metals", segment=fn).astype(np.float32))[:, nelem]
+            except KeyError:
+                metal_abund = np.array([0.76, 0.24], dtype=np.float32)  # primordial
+                nvalues = self.snapshot_set.get_blocklen(0, "Density", segment=fn)
+                mass_frac = metal_abund[nelem] * np.ones(nvalues, dtype=np.float32)
+        mass_frac = mass_frac[ind]
+        mass_frac[np.where(mass_frac <= 0)] = 0
+        assert mass_frac.dtype == np.float32
+        return mass_frac
+
+    def _filter_particles(self, elem_den, pos, velocity, den):
+        _ = (pos, velocity, den)
+        return np.where(elem_den > 0)
+
+    def _get_elem_den(self, elem, ion, den, temp, ind, ind2):
+        """Ionisation fraction of a metal ion.  The reference looks it up in Cloudy tables
+        (convert_cloudy.py:167-200), an input of the hot path that is not rebuilt here; a snapshot or
+        subclass may provide ``ion_fraction(elem, ion, den, temp)``."""
+        _ = (ind, ind2)
+        fn = getattr(self.snapshot_set, "ion_fraction", None)
+        if fn is None:
+            raise NotImplementedError("ion fractions for %s %d need a table: give the snapshot an "
+                                      "ion_fraction(elem, ion, nH, temp) method or override _get_elem_den" % (elem, ion))
+        return np.float32(fn(elem, ion, den, temp))
+
+    def _read_particle_data(self, fn, elem, ion, get_tau):
+        """(pos, vel, elem_den, temp, hh, amumass) of the particles of segment ``fn`` near this
+        rank's sightlines, all float32; six times False when there are none."""
+        none = (False, False, False, False, False, False)
+        pos = self.snapshot_set.get_data(0, "Position", segment=fn).astype(np.float32)
+        hh = self.snapshot_set.get_smooth_length(0, segment=fn).astype(np.float32)
+        if self.cofm_final:
+            try:
+                ind = self.part_ind[fn]
+            except KeyError:
+                ind = self.particles_near_lines(pos, hh)
+                self.part_ind[fn] = ind
+        else:
+            ind = self.particles_near_lines(pos, hh)
+        if self._sharder.mode == "particles" and self._sharder.size > 1:
+            ind = ind[self._sharder.my_particles(np.size(ind))]
+        if np.size(ind) == 0:
+            return none
+        pos = pos[ind, :]
+        hh = hh[ind]
+        vel = np.zeros(1, dtype=np.float32)
+        temp = np.zeros(1, dtype=np.float32)
+        if get_tau:
+            vel = self.snapshot_set.get_peculiar_velocity(0, segment=fn).astype(np.float32)
+            vel = vel[ind, :]
+        den = self.gasprop.get_code_rhoH(0, segment=fn).astype(np.float32)
+        amumass = self.lines.get_mass(elem) if elem != "Z" else 1
+        den = den[ind]
+        if get_tau or (ion != -1 and elem != 'H'):
+            temp = self.gasprop.get_temp(0, segment=fn).astype(np.float32)
+            temp = temp[ind]
+            temp[np.where(temp <= 0)] = 1
+        elem_den = (den * self.rscale) * self.get_mass_frac(elem, fn, ind)
+        if elem == 'H' and ion == 1:
+            elem_den *= (self.gasprop.get_reproc_HI(0, segment=fn)[ind]).astype(np.float32)
+        elif ion != -1:
+            ind2 = self._filter_particles(elem_den, pos, vel, den)
+            if np.size(ind2) == 0:
+                return none
+            temp = temp[ind2]
+            pos = pos[ind2]
+            hh = hh[ind2]
+            if get_tau:
+                vel = vel[ind2]
+            elem_den = elem_den[ind2] * self._get_elem_den(elem, ion, den[ind2], temp, ind, ind2)
+        elem_den /= amumass
+        return (pos, vel, np.ascontiguousarray(elem_den, dtype=np.float32), temp, hh, amumass)
+
+    def find_all_particles(self):
+        """Positions and smoothing lengths of all particles near sightlines."""
+        pp = np.empty([0, 3])
+        hhh = np.array([])
+        for i in range(self.snapshot_set.get_n_segments()):
+            (pos, _, _, _, hh, amumass) = self._read_particle_data(i, "H", -1, False)
+            if amumass is not False:
+                pp = np.concatenate([pp, pos])
+                hhh = np.concatenate([hhh, hh])
+        return pp, hhh
+
+    # ---- the native boundary ---------------------------------------------------------------------------
+    def _line(self, elem, ion, ll):
+        if ion == -1:
+            for ii in range(8):
+                try:
+                    return self.lines[(elem, ii)][ll]
+                except KeyError:
+                    continue
+            raise KeyError((elem, ion, ll))
+        return self.lines[(elem, ion)][ll]
+
+    def _params(self, line, amumass):
+        from . import _lib
+        gamma_X = 0 if self.turn_off_selfshield else line.gamma_X
+        return _lib.make_params(self.nbins, self.kernel_int, self.box, self.velfac, self.atime, line.lambda_X * 1e-8, gamma_X,
+                                line.fosc_X, amumass, self.tautail, precision=self.precision, voigt=self.voigt)
+
+    def _do_interpolation_work(self, pos, vel, elem_den, temp, hh, amumass, line, get_tau):
+        """Run the interpolation on pre-determined host arrays (spectra.py:666-673): the drop-in
+        boundary call, on this rank's sightlines."""
+        gamma_X = 0 if self.turn_off_selfshield else line.gamma_X
+        kw = {}
+        if self._backend is _spectra_priv:
+            kw = dict(precision=self.precision, voigt=self.voigt)
+        if np.size(self._my_axis) == 0:
+            return np.zeros([0, self.nbins])
+        return self._backend._Particle_Interpolate(get_tau * 1, self.nbins, self.kernel_int, self.box, self.velfac, self.atime,
+                                                   line.lambda_X * 1e-8, gamma_X, line.fosc_X, amumass, self.tautail, pos,
+                                                   vel, elem_den, temp, hh, self._my_axis, self._my_cofm, **kw)
+
+    def _engine(self, fn, elem, ion):
+        """Device-resident particles + candidate index of a segment (None when it has no particles
+        near this rank's sightlines).  Cached once the sightlines are final."""
+        key = (fn, elem, ion)
+        if key in self._engines:
+            return self._engines[key]
+        (pos, vel, elem_den, temp, hh, amumass) = self._read_particle_data(fn, elem, ion, True)
+        eng = None
+        if amumass is not False and np.size(self._my_axis) > 0:
+            eng = _SegmentEngine(self, pos, vel, elem_den, temp, hh)
+            eng.amumass = amumass
+        if self.cofm_final:
+            self._engines[key] = eng
+        return eng
+
+    def _segments(self):
+        """Segments this call loops over (the Voronoi kernel needs all particles at once:
+        spectra.py:811-815)."""
+        if self.kernel_int == 2:
+            return [None] if self.snapshot_set.get_n_segments(part_type=0) > 1 else [0]
+        return list(range(self.snapshot_set.get_n_segments(part_type=0)))
+
+    def _interpolate_single_file(self, nsegment, elem, ion, ll, get_tau, load_all_data_first=False):
+        """Read arrays and interpolate one segment through the drop-in boundary (spectra.py:501-548)."""
+        seg = None if load_all_data_first else nsegment
+        (pos, vel, elem_den, temp, hh, amumass) = self._read_particle_data(seg, elem, ion, get_tau)
+        if amumass is False:
+            return np.zeros([np.shape(self._my_cofm)[0], self.nbins], dtype=np.float32)
+        line = self._line(elem, ion, ll) if get_tau else self.lines[("H", 1)][1215]
+        return self._do_interpolation_work(pos, vel, elem_den, temp, hh, amumass, line, get_tau)
+
+    def _combine(self, local):
+        """Recombine the ranks' pieces (torch tensor or numpy) into the full float64 numpy array."""
+        import torch
+        was_numpy = isinstance(local, np.ndarray)
+        t = torch.from_numpy(np.ascontiguousarray(local, dtype=np.float64)) if was_numpy else local
+        if self._sharder.size > 1:
+            if was_numpy and self._cuda_available() and self._backend is _spectra_priv:
+                t = t.cuda()
+            t = self._sharder.combine(t, self.NumLos)
+        return t.cpu().numpy() if t.is_cuda else t.numpy()
+
+    def compute_spectra(self, elem, ion, ll, get_tau):
+        """tau (get_tau) or column density of one species on every sightline: loop over the
+        snapshot's segments, accumulate, recombine the ranks (spectra.py:801-831)."""
+        return self.compute_spectra_lines(elem, ion, [ll], get_tau)[0]
+
+    def compute_spectra_lines(self, elem, ion, lls, get_tau):
+        """Several lines of one ion in one pass over the particles (they share the candidate index
+        and every per-particle quantity but the line constants): [len(lls), NumLos, nbins]."""
+        nlocal = np.shape(self._my_cofm)[0]
+        nl = len(lls) if get_tau else 1
+        if self.resident:
+            import torch
+            acc = torch.zeros((nl, nlocal, self.nbins), dtype=torch.float64, device="cuda")
+            for seg in self._segments():
+                eng = self._engine(seg, elem, ion)
+                if eng is None:
+                    continue
+                if get_tau:
+                    acc += eng.tau([self._params(self._line(elem, ion, ll), eng.amumass) for ll in lls])
+                else:
+                    acc += eng.colden(self._params(self.lines[("H", 1)][1215], eng.amumass))
+            local = acc.permute(1, 0, 2).contiguous()  # rows first for the gather
+        else:
+            arepo = self.kernel_int == 2
+            out = []
+            for ll in (lls if get_tau else [0]):
+                result = np.array(self._interpolate_single_file(0, elem, ion, ll, get_tau, load_all_data_first=arepo),
+                                  dtype=np.float64)
+                nseg = 1 if arepo else self.snapshot_set.get_n_segments(part_type=0)
+                for nn in range(1, nseg):
+                    result += self._interpolate_single_file(nn, elem, ion, ll, get_tau)
+                out.append(result)
+            local = np.stack(out, axis=1)
+        result = self._combine(local)  # [NumLos, nl, nbins]
+        result = np.ascontiguousarray(np.transpose(result, (1, 0, 2)))
+        if self.MPI is not None:
+            # the reference's MPI mode: ranks hold different particles, float32 sum (spectra.py:828-830)
+            result = np.ascontiguousarray(result, np.float32)
+            self.comm.Allreduce(self.MPI.IN_PLACE, result, op=self.MPI.SUM)
+        return result
+
+    # ---- public getters (spectra.py:862-893, 945-1043) -------------------------------------------------
+    def get_col_density(self, elem, ion, force_recompute=False):
+        """Column density in each pixel, [metal] ions cm^-2."""
+        try:
+            if force_recompute:
+                raise KeyError
+            self._really_load_array((elem, ion), self.colden, "colden")
+            return self.colden[(elem, ion)]
+        except KeyError:
+            colden = self.compute_spectra(elem, ion, 0, False)
+            self.colden[(elem, ion)] = colden
+            return colden
+
+    def get_density(self, elem, ion, force_recompute=False):
+        """Density in each pixel, [metal] ions cm^-3."""
+        colden = self.get_col_density(elem, ion, force_recompute)
+        phys = self.dvbin / self.velfac * self.rscale
+        return colden / phys
+
+    def get_tau(self, elem, ion, line, number=-1, force_recompute=False):
+        """Optical depth in each pixel for one line (``line`` = int(lambda in Angstrom))."""
+        try:
+            if force_recompute:
+                raise KeyError
+            self._really_load_array((elem, ion, line), self.tau, "tau")
+            tau = self.tau[(elem, ion, line)]
+        except KeyError:
+            tau = self.compute_spectra(elem, ion, line, True)
+            self.tau[(elem, ion, line)] = tau
+        if number >= 0:
+            tau = tau[number, :]
+        return tau
+
+    def get_tau_lines(self, elem, ion, lines, force_recompute=False):
+        """Optical depths of several lines of one ion from one pass (Lya + Lyb ...); fills the same
+        cache as get_tau.  Returns {line: tau}."""
+        todo = [ll for ll in lines if force_recompute or (elem, ion, ll) not in self.tau]
+        if todo:
+            taus = self.compute_spectra_lines(elem, ion, todo, True)
+            for ll, t in zip(todo, taus):
+                self.tau[(elem, ion, ll)] = t
+        return {ll: self.get_tau(elem, ion, ll) for ll in lines}
+
+    def _weighted_single_file(self, fn, elem, ion, make_weights):
+        """Column-density pass(es) with reweighted densities for one segment: [K, nlocal, nbins].
+        make_weights(pos, vel, elem_den, temp) -> list of float32 weight arrays."""
+        nlocal = np.shape(self._my_cofm)[0]
+        line = self.lines[("H", 1)][1215]
+        if self.resident:
+            import torch
+            eng = self._engine(fn, elem, ion)
+            if eng is None:
+                return None
+            w = make_weights(eng.pos, eng.vel, eng.dens, eng.temp, torch, fn)
+            return eng.colden(self._params(line, eng.amumass), torch.stack(w))
+        (pos, vel, elem_den, temp, hh, amumass) = self._read_particle_data(fn, elem, ion, True)
+        if amumass is False:
+            return None
+        w = make_weights(pos, vel, elem_den, temp, np, fn)
+        return np.stack([np.asarray(self._do_interpolation_work(pos, vel, np.ascontiguousarray(wi, dtype=np.float32), temp, hh,
+                                                                amumass, line, False), dtype=np.float64) for wi in w]
+                        ).reshape(len(w), nlocal, self.nbins)
+
+    def _get_mass_weight_quantity(self, make_weights, nweights, elem, ion):
+        """Sum the weighted passes over segments, recombine the ranks, divide by the density
+        (spectra.py:958-981).  Returns [K, NumLos, nbins]."""
+        nlocal = np.shape(self._my_cofm)[0]
+        acc = None
+        for seg in self._segments():
+            r = self._weighted_single_file(seg, elem, ion, make_weights)
+            if r is None:
+                continue
+            acc = r if acc is None else acc + r
+        if acc is None:
+            acc = np.zeros((nweights, nlocal, self.nbins))
+        if isinstance(acc, np.ndarray):
+            local = np.ascontiguousarray(np.transpose(acc, (1, 0, 2)))
+        else:
+            local = acc.permute(1, 0, 2).contiguous()
+        result = np.transpose(self._combine(local), (1, 0, 2))
+        den = np.array(self.get_density(elem, ion))
+        den[np.where(den == 0.)] = 1
+        return result / den[None, :, :]
+
+    def get_velocity(self, elem, ion):
+        """Column-density weighted velocity in each pixel, [NumLos, nbins, 3] km/s; the three
+        components share one geometry pass (the reference makes three calls, spectra.py:945-956)."""
+        try:
+            self._really_load_array((elem, ion), self.velocity, "velocity")
+            return self.velocity[(elem, ion)]
+        except KeyError:
+            phys = np.float32(self.dvbin / self.velfac * self.rscale)
+            sqa = np.float32(np.sqrt(self.atime))
+
+            def weights(pos, vel, elem_den, temp, xp, fn):
+                return [elem_den * (vel[:, ax] * sqa) / phys for ax in (0, 1, 2)]
+
+            vv = self._get_mass_weight_quantity(weights, 3, elem, ion)
+            velocity = np.ascontiguousarray(np.transpose(vv, (1, 2, 0)).astype(np.float32))
+            self.velocity[(elem, ion)] = velocity
+            return velocity
+
+    def get_temp(self, elem, ion):
+        """Density weighted temperature in each pixel."""
+        try:
+            self._really_load_array((elem, ion), self.temp, "temperature")
+            return self.temp[(elem, ion)]
+        except KeyError:
+            phys = np.float32(self.dvbin / self.velfac * self.rscale)
+
+            def weights(pos, vel, elem_den, temp, xp, fn):
+                return [elem_den * temp / phys]
+
+            temp = self._get_mass_weight_quantity(weights, 1, elem, ion)[0]
+            self.temp[(elem, ion)] = temp
+            return temp
+
+    def get_dens_weighted_density(self, elem, ion):
+        """(Ion) density weighted (species) density in each pixel (spectra.py:1015-1043)."""
+        try:
+            self._really_load_array((elem, ion), self.dens_weight_dens, "density_weight_density")
+            return self.dens_weight_dens[(elem, ion)]
+        except KeyError:
+            phys = np.float32(self.dvbin / self.velfac * self.rscale)
+            spec = self
+
+            def weights(pos, vel, elem_den, temp, xp, fn):
+                # density of all ionisation states of the element for the same particles
+                (_, _, species, _, _, amumass) = spec._read_particle_data(fn, elem, -1, True)
+                if amumass is False or species.shape[0] != elem_den.shape[0]:
+                    raise ValueError("get_dens_weighted_density needs the ion and species particle selections to "
+                                     "coincide (hydrogen, or ions without a zero-density filter)")
+                if xp is not np:
+                    species = xp.from_numpy(species).to(elem_den.device)
+                return [(elem_den / phys) * (species / spec.rscale)]
+
+            dwd = self._get_mass_weight_quantity(weights, 1, elem, ion)[0]
+            self.dens_weight_dens[(elem, ion)] = dwd
+            return dwd
+
+    def get_observer_tau(self, elem, ion, number=-1, force_recompute=False):
+        """Optical depth of the line of an ion whose maximum is closest to unity without being
+        saturated (spectra.py:895-943); all lines come from one pass over the particles."""
+        try:
+            if force_recompute:
+                raise KeyError
+            self._really_load_array((elem, ion), self.tau_obs, "tau_obs")
+            ntau = self.tau_obs[(elem, ion)]
+        except KeyError:
+            keys = list(self.lines[(elem, ion)].keys())
+            tau = self.compute_spectra_lines(elem, ion, keys, True)
+            from .spec_utils import res_corr
+            maxtaus = np.max(res_corr(tau, self.dvbin, self.spec_res), axis=-1)
+            ntau = np.empty([self.NumLos, self.nbins])
+            for ii in range(self.NumLos):
+                ind = np.where(np.logical_and(maxtaus[:, ii] < 3, maxtaus[:, ii] > 0.1))
+                if np.size(ind) > 0:
+                    line = np.where(maxtaus[:, ii] == np.max(maxtaus[ind, ii]))
+                else:
+                    ind2 = np.where(maxtaus[:, ii] > 0.1)
+                    if np.size(ind2) > 0:
+                        line = np.where(maxtaus[:, ii] == np.min(maxtaus[ind2, ii]))
+                    else:
+                        line = np.where(maxtaus[:, ii] == np.max(maxtaus[:, ii]))
+                ntau[ii, :] = tau[line[0][0], ii, :]
+            self.tau_obs[(elem, ion)] = ntau
+        if number >= 0:
+            ntau = ntau[number, :]
+        return ntau
+
+    def get_cofm(self, num=None):
+        """Find a bunch more sightlines: should be overridden by child classes"""
+        raise NotImplementedError
+
+    def filter_DLA(self, col_den, thresh=10 ** 20.3):
+        """Indices of sightlines whose summed column density exceeds ``thresh`` (or lies in a range)."""
+        cdsum = np.sum(col_den, axis=1)
+        if np.size(thresh) > 1:
+            return np.where(np.logical_and(cdsum > thresh[0], cdsum < thresh[1]))
+        return np.where(cdsum > thresh)
+
+    def replace_not_DLA(self, ndla, thresh=10 ** 20.3, elem="H", ion=1):
+        """Keep drawing sightlines until ``ndla`` of them exceed the column-density threshold
+        (spectra.py:713-755)."""
+        found = 0
+        wanted = ndla
+        cofm_DLA = np.empty_like(self.cofm)[:ndla, :]
+        col_den_DLA = np.empty((ndla, self.nbins))
+        self.set_sightlines(self.cofm, self.axis)
+        while True:
+            col_den = self.compute_spectra(elem, ion, 1215, False)
+            ind = self.filter_DLA(col_den, thresh)
+            top = np.min([wanted, found + np.size(ind)])
+            cofm_DLA[found:top] = self.cofm[ind][:top - found, :]
+            col_den_DLA[found:top] = col_den[ind][:top - found, :]
+            found += np.size(ind)
+            self.discarded += self.NumLos - np.size(ind)
+            print("Discarded: ", self.discarded)
+            if found >= wanted:
+                break
+            self.set_sightlines(self.get_cofm(), self.axis)
+        self.set_sightlines(cofm_DLA, np.ones(ndla) if np.size(self.axis) < ndla else self.axis[:ndla])
+        self.colden[(elem, ion)] = col_den_DLA
+        self.cofm_final = True

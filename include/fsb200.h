@@ -74,7 +74,14 @@ typedef struct fsb_counters {
     uint64_t pixels;    /* pixel contributions added                                              */
     uint64_t voigt;     /* Voigt profile evaluations (singleabs.h:157 calls)                      */
     uint64_t lanes;     /* lane-slots spent in the pixel march (pixels + discarded lanes)         */
+    uint64_t steps_near_u; /* warp march steps by route of the tau kernel: table + Gaussian        */
+    uint64_t steps_near;   /*   table only (Gaussian negligible)                                   */
+    uint64_t steps_far;    /*   damping-wing series, |x| >= 16                                     */
+    uint64_t steps_mixed;  /*   straddling |x| = 16 (generic evaluation)                           */
+    uint64_t steps_slow;   /*   exact Faddeeva or sub-sampled pixels                               */
+    uint64_t reserved;
 } fsb_counters;
+#define FSB_N_COUNTERS 10
 
 /* ---- library ------------------------------------------------------------------------------ */
 FSB_API int fsb_abi_version(void);

@@ -37,16 +37,19 @@ def run(nside, nlos, axis, voigt, reps=2):
     p = cases.params(d)
     prm = _lib.make_params(**p, voigt=voigt)
     t_idx, idx = timed(lambda: native.CandidateIndex(d["box"], t["cofm"], t["axis"], t["pos"], t["h"]), reps)
-    ctr = torch.zeros(4, dtype=torch.int64, device="cuda")
+    ctr = torch.zeros(10, dtype=torch.int64, device="cuda")
     out = torch.zeros((nlos, p["nbins"]), dtype=torch.float64, device="cuda")
     t_tau, _ = timed(lambda: idx.compute_tau(prm, t["pos"], t["vel"], t["dens"], t["temp"], t["h"], out=out), reps)
     idx.compute_tau(prm, t["pos"], t["vel"], t["dens"], t["temp"], t["h"], out=out, counters=ctr)
     t_col, _ = timed(lambda: idx.compute_colden(prm, t["pos"], t["dens"], t["h"]), reps)
+    prm_b = _lib.make_params(**cases.params(d, line="HI1025"), voigt=voigt)
+    out2 = torch.zeros((2, nlos, p["nbins"]), dtype=torch.float64, device="cuda")
+    t_tau2, _ = timed(lambda: idx.compute_tau([prm, prm_b], t["pos"], t["vel"], t["dens"], t["temp"], t["h"], out=out2), reps)
     c = ctr.cpu().numpy()
     res = dict(nside=nside, nlos=nlos, nbins=p["nbins"], voigt=voigt, npairs=idx.npairs, max_list=idx.max_list,
-               t_index=t_idx, t_tau=t_tau, t_colden=t_col, pairs_per_s=idx.npairs / t_tau, spectra_per_s=nlos / t_tau,
+               t_index=t_idx, t_tau=t_tau, t_tau_lya_lyb=t_tau2, t_colden=t_col, lib=os.path.basename(_lib.LIB_PATH), pairs_per_s=idx.npairs / t_tau, spectra_per_s=nlos / t_tau,
                n_voigt=int(c[2]), voigt_per_s=float(c[2]) / t_tau, pixels=int(c[1]), lane_eff=float(c[1]) / max(float(c[3]), 1),
-               tflops_280=280.0 * float(c[2]) / t_tau / 1e12)
+               routes=[int(v) for v in c[4:9]], check=float(out.mean().item()))
     print(json.dumps(res), flush=True)
     return res
 

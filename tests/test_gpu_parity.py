@@ -137,6 +137,38 @@ def test_cold_comb_and_dense_wings(priv, oracle):
     assert same_zero and rel < TOL, rel
 
 
+def test_wide_kernels_cold_gas(priv, oracle):
+    """Kernels much wider than the thermal width (300-3000 K gas, 0.25 km/s pixels): the seven
+    quadrature nodes of one pixel reach from the line core to beyond |x| = 16, and very dense
+    particles carry the march through the near / straddling / far routes of the tau kernel."""
+    d = cases.random_case(nside=12, nlos=30, axis="cycle", seed=9)
+    rng = np.random.default_rng(3)
+    d["temp"] = (300.0 * 10 ** rng.random(d["temp"].size)).astype(np.float32)
+    d["dens"][::5] *= 1e5
+    for line in ("HI1215", "CIV1548"):
+        p = cases.params(d, line=line, res=0.25)
+        want = oracle.compute_tau(**p, pos=d["pos"], vel=d["vel"], dens=d["dens"], temp=d["temp"], h=d["h"],
+                                  axis=d["axis"], cofm=d["cofm"])
+        rel, same_zero = cases.rel_err(interp(priv, 1, p, d), want)
+        assert same_zero and rel < TOL, (line, rel)
+
+
+def test_fused_lines_vs_oracle(torch_cuda, oracle):
+    """Lya + Lyb fused in one pass against the oracle's two separate passes."""
+    from fake_spectra_b200 import _lib, native
+    d = cases.random_case(nside=16, nlos=36, axis="cycle", seed=31)
+    d["dens"][::11] *= 1e4
+    t = dev(torch_cuda, d)
+    idx = native.CandidateIndex(d["box"], t["cofm"], t["axis"], t["pos"], t["h"])
+    plist = [cases.params(d, line=ln) for ln in ("HI1215", "HI1025")]
+    both = idx.compute_tau([_lib.make_params(**p) for p in plist], t["pos"], t["vel"], t["dens"], t["temp"], t["h"]).cpu().numpy()
+    for k, p in enumerate(plist):
+        want = oracle.compute_tau(**p, pos=d["pos"], vel=d["vel"], dens=d["dens"], temp=d["temp"], h=d["h"],
+                                  axis=d["axis"], cofm=d["cofm"])
+        rel, same_zero = cases.rel_err(both[k], want)
+        assert same_zero and rel < TOL, (k, rel)
+
+
 def test_signed_weights_colden(priv, oracle):
     d = cases.random_case(nside=12, nlos=30, axis=1, seed=8)
     rng = np.random.default_rng(0)

@@ -1,0 +1,188 @@
+"""Host classes (Spectra / RandSpectra / GriddedSpectra) on CPU: the reference's API contract
+ with the native boundary replaced by an oracle-backed checker, including the
+world_size-2 gloo runs of the sightline- and particle-sharded modes."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(__file__))
+import hostcases  # noqa: E402
+from fake_spectra_b200 import griddedspectra, randspectra, spectra  # noqa: E402
+
+
+@pytest.fixture()
+def backend(oracle):
+    return hostcases.OracleBackend(oracle)
+
+
+def make_rand(backend, nside=10, numlos=14, nsegments=1, **kw):
+    snap = hostcases.snapshot(nside, nsegments)
+    return randspectra.RandSpectra(0, snap, numlos=numlos, thresh=0., res=2.0, quiet=True, backend=backend, **kw)
+
+
+def test_constructor_contract(backend):
+    rs = make_rand(backend)
+    snap = rs.snapshot_set
+    assert rs.NumLos == 14 and rs.cofm.shape == (14, 3) and rs.cofm.dtype == np.float64
+    assert rs.axis.dtype == np.int32 and np.all(rs.axis == 1)
+    # randspectra.py:23-24,32-37: np.random.seed(seed); box * random_sample
+    np.random.seed(23)
+    assert np.array_equal(rs.cofm, snap.get_header_attr("BoxSize") * np.random.random_sample((14, 3)))
+    assert rs.rscale.dtype == np.float32
+    assert rs.nbins == int(rs.vmax / 2.0) and np.isclose(rs.dvbin, rs.vmax / rs.nbins)
+    assert rs.tautail == 1e-7 and rs.kernel_int == 1
+    assert np.isclose(rs.velfac, rs.rscale * rs.Hz / 3.085678e24)
+    with pytest.raises(ValueError):
+        spectra.Spectra(0, snap, rs.cofm, rs.axis, reload_file=True, quiet=True, kernel="bogus", backend=backend)
+    one = spectra.Spectra(0, snap, np.array([1., 2., 3.]), np.array(2), reload_file=True, quiet=True, backend=backend)
+    assert one.cofm.shape == (1, 3) and one.axis.shape == (1,) and one.NumLos == 1
+
+
+def test_get_tau_matches_a_direct_boundary_call(backend, oracle):
+    """get_tau == the boundary call on the arrays the reference's _read_particle_data would build
+    (spectra.py:550-617, restated here in numpy)."""
+    rs = make_rand(backend)
+    snap, gp = rs.snapshot_set, rs.gasprop
+    pos = snap.get_data(0, "Position", segment=0).astype(np.float32)
+    hh = snap.get_smooth_length(0, segment=0).astype(np.float32)
+    ind = oracle.near_lines(rs.box, pos, hh, rs.axis, rs.cofm)
+    vel = snap.get_peculiar_velocity(0, segment=0).astype(np.float32)[ind]
+    den = gp.get_code_rhoH(0, segment=0).astype(np.float32)[ind]
+    temp = gp.get_temp(0, segment=0).astype(np.float32)[ind]
+    temp[temp <= 0] = 1
+    mass_frac = snap.get_data(0, "GFM_Metals", segment=0).astype(np.float32)[:, 0][ind]
+    elem_den = (den * rs.rscale) * mass_frac
+    elem_den *= gp.get_reproc_HI(0, segment=0)[ind].astype(np.float32)
+    elem_den /= rs.lines.get_mass("H")
+    line = rs.lines[("H", 1)][1215]
+    want = oracle.compute_tau(rs.nbins, 1, rs.box, rs.velfac, rs.atime, line.lambda_X * 1e-8, line.gamma_X, line.fosc_X,
+                              rs.lines.get_mass("H"), 1e-7, pos[ind], vel, elem_den.astype(np.float32), temp, hh[ind],
+                              rs.axis, rs.cofm)
+    tau = rs.get_tau("H", 1, 1215)
+    assert tau.shape == (rs.NumLos, rs.nbins) and tau.dtype == np.float64
+    assert np.array_equal(tau, want)
+    assert rs.get_tau("H", 1, 1215) is tau                      # cached (spectra.py:883-890)
+    assert np.array_equal(rs.get_tau("H", 1, 1215, number=3), tau[3])
+    assert 0.01 < np.mean(tau) < 50
+
+
+def test_colden_density_and_weighted_fields(backend):
+    rs = make_rand(backend)
+    colden = rs.get_col_density("H", 1)
+    assert colden.shape == (rs.NumLos, rs.nbins) and np.all(colden >= 0) and colden.max() > 0
+    phys = rs.dvbin / rs.velfac * rs.rscale
+    assert np.allclose(rs.get_density("H", 1), colden / phys)
+    temp = rs.get_temp("H", 1)
+    sel = colden > 0
+    assert temp.shape == colden.shape
+    assert np.all(temp[sel] > 1e2) and np.all(temp[sel] < 1e7)  # a density-weighted mean of particle temperatures
+    vel = rs.get_velocity("H", 1)
+    assert vel.shape == (rs.NumLos, rs.nbins, 3) and vel.dtype == np.float32
+    assert np.all(np.abs(vel) < 2000)
+    dwd = rs.get_dens_weighted_density("H", 1)
+    assert dwd.shape == colden.shape and np.all(dwd[sel] > 0)
+    # turn_off_selfshield: Gamma = 0 at the boundary (spectra.py:669-672)
+    g0 = make_rand(backend, turn_off_selfshield=True)
+    assert not np.array_equal(g0.get_tau("H", 1, 1215), rs.get_tau("H", 1, 1215))
+
+
+def test_segments_accumulate(backend):
+    """A snapshot split in three segments gives the single-segment result (spectra.py:818-823)."""
+    a = make_rand(backend, nsegments=1).get_tau("H", 1, 1215)
+    b = make_rand(backend, nsegments=3).get_tau("H", 1, 1215)
+    assert np.allclose(a, b, rtol=1e-12, atol=0)
+    assert np.array_equal(a == 0, b == 0)
+
+
+def test_fused_lines_fill_the_cache(backend):
+    rs = make_rand(backend)
+    both = rs.get_tau_lines("H", 1, [1215, 1025])
+    assert set(both) == {1215, 1025}
+    assert np.array_equal(both[1215], make_rand(backend).get_tau("H", 1, 1215))
+    assert rs.get_tau("H", 1, 1025) is both[1025]
+    assert both[1025].max() < both[1215].max()
+
+
+def test_gridded_spectra_layout(backend):
+    snap = hostcases.snapshot(8)
+    gs = griddedspectra.GriddedSpectra(0, snap, nspec=4, res=5.0, axis=-1, quiet=True, backend=backend)
+    box = snap.get_header_attr("BoxSize")
+    assert gs.NumLos == 48 and list(gs.axis[:16]) == [1] * 16 and list(gs.axis[16:32]) == [2] * 16
+    # reference griddedspectra.py:68-81: [0,nn,mm], [nn,0,mm], [nn,mm,0] times box/nspec
+    assert np.array_equal(gs.cofm[5], box / 4 * np.array([0, 1, 1]))
+    assert np.array_equal(gs.cofm[16 + 6], box / 4 * np.array([1, 0, 2]))
+    assert np.array_equal(gs.cofm[32 + 7], box / 4 * np.array([1, 3, 0]))
+    tau = gs.get_tau("H", 1, 1215)
+    assert tau.shape == (48, gs.nbins) and tau.max() > 0
+    with pytest.raises(ValueError):
+        griddedspectra.GriddedSpectra(0, snap, nspec=4, res=None, nbins=None, quiet=True, backend=backend)
+    g2 = griddedspectra.GriddedSpectra(0, snap, nspec=2, res=None, nbins=64, quiet=True, backend=backend)
+    assert g2.nbins == 64 and np.isclose(g2.dvbin, g2.vmax / 64)
+
+
+def test_savefile_roundtrip(backend, tmp_path):
+    rs = make_rand(backend, savefile="spectra.npz", savedir=str(tmp_path))
+    tau = rs.get_tau("H", 1, 1215)
+    col = rs.get_col_density("H", 1)
+    rs.save_file()
+    snap = rs.snapshot_set
+    back = spectra.Spectra(0, snap, None, None, savefile="spectra.npz", savedir=str(tmp_path), res=None, quiet=True,
+                           backend=backend)
+    assert back.nbins == rs.nbins and np.array_equal(back.cofm, rs.cofm) and np.isclose(back.velfac, rs.velfac)
+    assert np.array_equal(back.get_tau("H", 1, 1215), tau)
+    assert np.array_equal(back.get_col_density("H", 1), col)
+    with pytest.raises(IOError):
+        spectra.Spectra(0, snap, None, None, savefile="missing.npz", savedir=str(tmp_path), quiet=True, backend=backend)
+
+
+def test_balanced_blocks():
+    from fake_spectra_b200 import sharding
+    w = np.array([1, 1, 1, 1, 10, 1, 1, 1, 1, 10])
+    e = sharding.balanced_blocks(w, 2)
+    assert e[0] == 0 and e[-1] == 10 and abs(w[:e[1]].sum() - w[e[1]:].sum()) <= 10
+    assert list(sharding.even_blocks(10, 4)) == [0, 2, 5, 7, 10]
+    assert list(sharding.balanced_blocks(np.zeros(6), 3)) == [0, 2, 4, 6]
+    e = sharding.balanced_blocks(np.ones(7), 8)
+    assert e[0] == 0 and e[-1] == 7 and np.all(np.diff(e) >= 0)
+
+
+def _worker(rank, world, port, mode, out_dir):
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.dirname(__file__))
+    import hostcases as hc
+    from oracle import Oracle
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    orc = Oracle()
+    orc.set_threads(2)
+    be = hc.OracleBackend(orc)
+    snap = hc.snapshot(10, 2)
+    rs = randspectra.RandSpectra(0, snap, numlos=13, thresh=0., res=2.0, quiet=True, backend=be, shard=mode)
+    tau = rs.get_tau("H", 1, 1215)
+    vel = rs.get_velocity("H", 1)
+    np.savez(os.path.join(out_dir, "r%d.npz" % rank), tau=tau, vel=vel, lines=[c[2] for c in be.calls], parts=[c[1] for c in be.calls])
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("mode", ["sightlines", "particles"])
+def test_two_rank_sharding_gloo(backend, tmp_path, mode):
+    """world_size 2 over gloo: both ranks end with the full arrays, equal to the unsharded run
+    (bitwise for sightline sharding; to summation order for particle sharding)."""
+    import torch.multiprocessing as mp
+    port = 29500 + (os.getpid() % 2000) + (7 if mode == "particles" else 0)
+    mp.spawn(_worker, args=(2, port, mode, str(tmp_path)), nprocs=2, join=True)
+    ref = make_rand(backend, numlos=13, nsegments=2)
+    tau, vel = ref.get_tau("H", 1, 1215), ref.get_velocity("H", 1)
+    outs = [np.load(os.path.join(str(tmp_path), "r%d.npz" % r)) for r in range(2)]
+    for o in outs:
+        if mode == "sightlines":
+            assert np.array_equal(o["tau"], tau) and np.array_equal(o["vel"], vel)
+            assert set(o["lines"]) <= {6, 7}          # each rank only interpolated its block of the 13 sightlines
+        else:
+            assert np.allclose(o["tau"], tau, rtol=1e-12, atol=0) and np.array_equal(o["tau"] == 0, tau == 0)
+            assert np.allclose(o["vel"], vel, rtol=1e-5, atol=1e-4)
+            assert set(o["lines"]) == {13}            # every rank did all sightlines for its particles
+    assert np.array_equal(outs[0]["tau"], outs[1]["tau"])
