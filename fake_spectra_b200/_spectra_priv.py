@@ -24,7 +24,7 @@ def _is_f32(a):
 
 def _Particle_Interpolate(compute_tau, nbins, kernel, box, velfac, atime, lambda_cm, gamma, fosc, amumass, tautail,
                           pos, vel, dens, temp, h, axis, cofm, precision=None, voigt=None, out=None,
-                          extra_lines=()):
+                          extra_lines=(), extra_weights=()):
     """Optical depth (compute_tau != 0) or column density on every sightline.
 
     Arguments, order and units as py_module.cpp:115; returns a new float64 array [NumLos, nbins].
@@ -32,7 +32,9 @@ def _Particle_Interpolate(compute_tau, nbins, kernel, box, velfac, atime, lambda
 
     Extensions (keyword only, absent from the reference): ``out`` = preallocated (e.g. pinned)
     float64 result buffer; ``extra_lines`` = [(lambda_cm, gamma, fosc), ...] further lines of the
-    same ion computed from the same upload and candidate index, result [1+len, NumLos, nbins]."""
+    same ion computed from the same upload and candidate index, result [1+len, NumLos, nbins];
+    ``extra_weights`` (column density only) = further float32 density-like arrays interpolated in
+    the same geometry pass, result [1+len, NumLos, nbins]."""
     for a in (pos, vel, dens, temp, h):
         if not _is_f32(a):
             raise TypeError("One of the data arrays does not have 32-bit float type")
@@ -42,12 +44,19 @@ def _Particle_Interpolate(compute_tau, nbins, kernel, box, velfac, atime, lambda
         raise TypeError("Axis must be a 32-bit integer")
     numlos = cofm.shape[0]
     npart = pos.shape[0]
-    if npart != dens.shape[0] or npart != h.shape[0]:
+    if npart != dens.shape[-1] or npart != h.shape[0]:
         raise ValueError(" Dens, pos and h must have the same length")
     if cofm.ndim != 2 or numlos != axis.shape[0] or cofm.shape[1] != 3:
         raise ValueError("cofm must have dimensions (np.size(axis),3) ")
     if compute_tau and (vel.shape[0] != npart or temp.shape[0] != npart):
         raise ValueError(" Vel and temp must have the same length as pos when computing tau")
+    if extra_weights:
+        if compute_tau or extra_lines:
+            raise ValueError("extra_weights only apply to column density")
+        for w in extra_weights:
+            if not _is_f32(w) or w.shape[0] != npart:
+                raise TypeError("weight columns must be float32 arrays as long as pos")
+        dens = np.stack([dens] + list(extra_weights))
     pos, dens, h = (np.ascontiguousarray(a) for a in (pos, dens, h))
     cofm, axis = np.ascontiguousarray(cofm), np.ascontiguousarray(axis)
     p = _lib.make_params(nbins, kernel, box, velfac, atime, lambda_cm, gamma, fosc, amumass, tautail,
@@ -57,7 +66,8 @@ def _Particle_Interpolate(compute_tau, nbins, kernel, box, velfac, atime, lambda
     vgt = DEFAULT_VOIGT if voigt is None else voigt
     plist = [p] + [_lib.make_params(nbins, kernel, box, velfac, atime, lam, gam, fo, amumass, tautail, precision=prec,
                                     voigt=vgt) for (lam, gam, fo) in extra_lines]
-    shape = (numlos, int(nbins)) if not extra_lines else (len(plist), numlos, int(nbins))
+    ncols = len(plist) if compute_tau or not extra_weights else 1 + len(extra_weights)
+    shape = (numlos, int(nbins)) if ncols == 1 else (ncols, numlos, int(nbins))
     if out is None:
         out = np.empty(shape, dtype=np.float64)
     elif out.dtype != np.float64 or out.size != int(np.prod(shape)) or not out.flags.c_contiguous:
@@ -69,7 +79,7 @@ def _Particle_Interpolate(compute_tau, nbins, kernel, box, velfac, atime, lambda
         pvel, ptemp = _ptr(vel), _ptr(temp)
     else:
         pvel = ptemp = None
-    rc = lib.fsb_particle_interpolate_multi_host(1 if compute_tau else 0, parr, len(plist), _ptr(pos), pvel, _ptr(dens),
+    rc = lib.fsb_particle_interpolate_multi_host(1 if compute_tau else 0, parr, ncols, _ptr(pos), pvel, _ptr(dens),
                                                  ptemp, _ptr(h), npart, _ptr(axis), _ptr(cofm), numlos, _ptr(out))
     _lib.check(rc, "_Particle_Interpolate")
     return out.reshape(shape)

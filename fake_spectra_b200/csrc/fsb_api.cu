@@ -241,13 +241,13 @@ extern "C" int fsb_particle_interpolate_multi_host(int32_t compute_tau, const fs
     FSB_REQUIRE(p != nullptr && out != nullptr, "params/out NULL");
     FSB_REQUIRE(nlines >= 1, "nlines must be >= 1");
     FSB_REQUIRE(nlos >= 0 && npart >= 0 && p[0].nbins > 0, "bad sizes");
-    FSB_REQUIRE(compute_tau || nlines == 1, "several lines only make sense for tau");
     FSB_TRY(retain_pool_memory());
     cudaStream_t s = nullptr;
     DevBuf dpos, dvel, ddens, dtemp, dh, daxis, dcofm, dout;
     const size_t np = (size_t) npart, nl = (size_t) nlos;
     FSB_TRY(dpos.upload(pos, sizeof(float) * 3 * np, s));
-    FSB_TRY(ddens.upload(dens, sizeof(float) * np, s));
+    // column density: nlines counts weight columns, dens is [nlines][npart]
+    FSB_TRY(ddens.upload(dens, sizeof(float) * np * (compute_tau ? 1 : (size_t) nlines), s));
     FSB_TRY(dh.upload(h, sizeof(float) * np, s));
     if (compute_tau) {
         FSB_REQUIRE(npart == 0 || (vel && temp), "vel/temp NULL with compute_tau");
@@ -262,17 +262,21 @@ extern "C" int fsb_particle_interpolate_multi_host(int32_t compute_tau, const fs
     FSB_CUDA_TRY(cudaMemsetAsync(dout.ptr, 0, std::max<size_t>(out_bytes, 8), s));
     if (nlines == 1 || p[0].kernel == FSB_KERNEL_VORONOI) {
         for (int32_t i = 0; i < nlines; ++i)
-            FSB_TRY(fsb_particle_interpolate(compute_tau, &p[i], (const float *) dpos.ptr, (const float *) dvel.ptr,
-                                             (const float *) ddens.ptr, (const float *) dtemp.ptr, (const float *) dh.ptr, npart,
+            FSB_TRY(fsb_particle_interpolate(compute_tau, &p[compute_tau ? i : 0], (const float *) dpos.ptr, (const float *) dvel.ptr,
+                                             (const float *) ddens.ptr + (compute_tau ? 0 : (size_t) i * np),
+                                             (const float *) dtemp.ptr, (const float *) dh.ptr, npart,
                                              (const int32_t *) daxis.ptr, (const double *) dcofm.ptr, nlos,
                                              (double *) dout.ptr + (size_t) i * nl * (size_t) p[0].nbins, s));
     } else {
         fsb_index *idx = nullptr;
         FSB_TRY(fsb_index_build(p[0].box, (const double *) dcofm.ptr, (const int32_t *) daxis.ptr, nlos, (const float *) dpos.ptr,
                                 (const float *) dh.ptr, npart, s, &idx));
-        const int rc = fsb_compute_tau_multi(idx, p, nlines, (const float *) dpos.ptr, (const float *) dvel.ptr,
-                                             (const float *) ddens.ptr, (const float *) dtemp.ptr, (const float *) dh.ptr,
-                                             (double *) dout.ptr, nullptr, s);
+        const int rc = compute_tau
+                           ? fsb_compute_tau_multi(idx, p, nlines, (const float *) dpos.ptr, (const float *) dvel.ptr,
+                                                   (const float *) ddens.ptr, (const float *) dtemp.ptr,
+                                                   (const float *) dh.ptr, (double *) dout.ptr, nullptr, s)
+                           : fsb_compute_colden(idx, p, (const float *) dpos.ptr, (const float *) ddens.ptr, nlines,
+                                                (const float *) dh.ptr, (double *) dout.ptr, nullptr, s);
         fsb_index_free(idx, s);
         FSB_TRY(rc);
     }

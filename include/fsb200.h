@@ -144,7 +144,9 @@ FSB_API int fsb_particle_interpolate_host(int32_t compute_tau, const fsb_params 
                                   const int32_t *axis, const double *cofm, int32_t nlos, double *out);
 
 /* Several lines of one ion from one upload and one index (HOST pointers): out[nlines][nlos*nbins].
- * What Spectra.get_tau does for Lya then Lyb as two boundary calls, in one. */
+ * What Spectra.get_tau does for Lya then Lyb as two boundary calls, in one.  With compute_tau == 0,
+ * nlines counts density-like weight columns instead: dens[nlines][npart], p[0] is used
+ * (the three passes of Spectra.get_velocity, spectra.py:945-956, in one). */
 FSB_API int fsb_particle_interpolate_multi_host(int32_t compute_tau, const fsb_params *p, int32_t nlines,
                                         const float *pos, const float *vel, const float *dens, const float *temp,
                                         const float *h, int64_t npart, const int32_t *axis, const double *cofm,

@@ -237,6 +237,18 @@ def test_weight_columns_share_geometry(torch_cuda):
         assert np.array_equal(fused[k], one)
 
 
+def test_host_boundary_weight_columns(priv):
+    """extra_weights at the host boundary: K column-density passes from one upload and one index."""
+    d = cases.random_case(nside=12, nlos=18, axis="cycle", seed=24)
+    p = cases.params(d)
+    w1 = (d["dens"] * d["temp"]).astype(np.float32)
+    w2 = (d["dens"] * d["vel"][:, 1]).astype(np.float32)
+    fused = interp(priv, 0, p, d, extra_weights=[w1, w2])
+    assert fused.shape == (3, 18, p["nbins"])
+    for k, w in enumerate((d["dens"], w1, w2)):
+        assert np.array_equal(fused[k], interp(priv, 0, p, dict(d, dens=w)))
+
+
 def test_fused_lines(torch_cuda):
     """Lya + Lyb in one call equal two calls."""
     from fake_spectra_b200 import _lib, native
