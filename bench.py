@@ -37,6 +37,11 @@ WORKLOADS = {
     "c2_grid256_lya_lyb": dict(nside=256, nspec=256, lines=("HI1215", "HI1025"), kernel=1, res=1.0),
     "c1_rand1000_lya": dict(nside=64, numlos=1000, lines=("HI1215",), kernel=1, res=1.0),
     "mini_grid64_lya_lyb": dict(nside=64, nspec=64, lines=("HI1215", "HI1025"), kernel=1, res=1.0),
+    # BASELINE.json configs[3] in miniature: Arepo-like top-hat kernel, particles sharded over the ranks
+    # (nside^3 cells PER RANK of one common box), every rank computes all sightlines for its cells and the
+    # FP64 tau arrays are summed with one NCCL all-reduce per step (the reference's MPI mode, spectra.py:825-831)
+    "c4_tophat_pshard": dict(nside=256, numlos=16384, lines=("HI1215",), kernel=0, res=1.0, shard="particles"),
+    "mini_tophat_pshard": dict(nside=64, numlos=2048, lines=("HI1215",), kernel=0, res=1.0, shard="particles"),
 }
 # Algorithmic FP64 work of THIS library's profile evaluation, per Voigt evaluation
 # (one quadrature node of one pixel of one line), FMA = 2 flop: NEAR route with Gaussian = 41 flop for the
@@ -66,10 +71,20 @@ def parse():
 def build_workload(name, rank, world):
     from fake_spectra_b200 import synthetic as syn
     w = dict(WORKLOADS[name])
-    d = syn.boundary_arrays(w["nside"], seed=42, kernel=w["kernel"])
-    cos = syn.Cosmology()
-    box = d["box"]
-    if "nspec" in w:
+    w.setdefault("shard", "sightlines")
+    if w["shard"] == "particles":
+        # rank r holds nside^3 cells (seed 42 + r) of a box sized for world * nside^3 cells; same sightlines everywhere
+        box = syn.MEAN_SPACING * w["nside"] * world ** (1.0 / 3.0)
+        d = syn.boundary_arrays(w["nside"], seed=42 + rank, kernel=w["kernel"], box=box)
+        cos = syn.Cosmology()
+        cofm, axis = syn.random_sightlines(box, w["numlos"], seed=23, axis=1)
+    else:
+        d = syn.boundary_arrays(w["nside"], seed=42, kernel=w["kernel"])
+        cos = syn.Cosmology()
+        box = d["box"]
+    if w["shard"] == "particles":
+        pass
+    elif "nspec" in w:
         cofm, axis = syn.grid_sightlines(box, w["nspec"], axis=1)
         if world > 1:  # weak scaling: a distinct, shifted grid per rank
             shift = (box / w["nspec"]) * rank / world
@@ -173,17 +188,27 @@ def run_b200(args):
     fp64_peak = native.measure_fma_peak(True)
 
     tau_ms = []
+    pshard = w["shard"] == "particles"
+
+    idx_ms = []
 
     def step(counters=None, time_tau=False):
         out.zero_()
+        if time_tau:
+            i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            i0.record()
         idx = native.CandidateIndex(w["box"], t["cofm"], t["axis"], t["pos"], t["h"])
         if time_tau:
+            i1.record()
+            idx_ms.append((i0, i1))
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
         idx.compute_tau(params, t["pos"], t["vel"], t["dens"], t["temp"], t["h"], out=out, counters=counters)
         if time_tau:
             e1.record()
             tau_ms.append((e0, e1))
+        if pshard and world > 1:
+            dist.all_reduce(out, op=dist.ReduceOp.SUM)  # FP64 [lines, nlos, nbins] over NCCL / NVLink
         npairs = idx.npairs
         idx.free()
         return npairs
@@ -225,7 +250,8 @@ def run_b200(args):
     clocks = sampler.stop() if rank == 0 else None
     launches = _lib.load().fsb_kernel_launches() - launches0
     elapsed = max_over_ranks(ev0.elapsed_time(ev1) * 1e-3)
-    total_lines = sum_over_ranks(float(w["nlos"]))
+    # sightline sharding: every rank has its own sightlines; particle sharding: all ranks share them
+    total_lines = float(w["nlos"]) if pshard else sum_over_ranks(float(w["nlos"]))
     total_pairs = sum_over_ranks(float(npairs))
     ms_per_step = elapsed / args.steps * 1e3
     value = total_lines * args.steps / elapsed
@@ -235,6 +261,15 @@ def run_b200(args):
     tau_launch_s = float(np.mean([a.elapsed_time(b) for a, b in tau_ms])) * 1e-3 / n_tau_launches
     achieved = algo_flop_step / n_tau_launches / tau_launch_s / 1e12
     sanity = float(out[0].mean().item())
+    # candidate-index build (K1): HBM-bound by design; algorithmic bytes = 16 B per particle read (pos + h, one
+    # axis group here) + 12 B per pair written (int32 particle + f64 dr2), SURVEY 8(d)
+    index_s = float(np.mean([a.elapsed_time(b) for a, b in idx_ms])) * 1e-3
+    index_bytes = 16.0 * w["npart"] * len(set(int(a) for a in np.unique(w["axis"]))) + 12.0 * npairs
+    try:
+        hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+        hbm_src = "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
 
     # ---- end to end through the reference-facing boundary: host buffers in, host buffer out ----
     e2e = None
@@ -245,11 +280,27 @@ def run_b200(args):
         extra = [LINES[ln][:3] for ln in w["lines"][1:]]
         vg = _lib.VOIGT_EXACT if args.voigt == "exact" else _lib.VOIGT_FAST
 
-        def e2e_step():
+        def e2e_step_host():
             return _spectra_priv._Particle_Interpolate(
                 1, w["nbins"], w["kernel"], w["box"], w["velfac"], w["atime"], lam, gam, fosc, amu, TAUTAIL,
                 pin["pos"].numpy(), pin["vel"].numpy(), pin["dens"].numpy(), pin["temp"].numpy(), pin["h"].numpy(),
                 pin["axis"].numpy(), pin["cofm"].numpy(), voigt=vg, out=hout.numpy(), extra_lines=extra)
+
+        def e2e_step_pshard():
+            # particle-sharded: upload this rank's particles, interpolate all sightlines, sum over ranks
+            # on the device (NCCL), read the result back
+            dv = {k: pin[k].to(dev, non_blocking=True) for k in names}
+            o = torch.zeros((nlines, w["nlos"], w["nbins"]), dtype=torch.float64, device=dev)
+            idx = native.CandidateIndex(w["box"], dv["cofm"], dv["axis"], dv["pos"], dv["h"])
+            idx.compute_tau(params, dv["pos"], dv["vel"], dv["dens"], dv["temp"], dv["h"], out=o)
+            idx.free()
+            if world > 1:
+                dist.all_reduce(o, op=dist.ReduceOp.SUM)
+            hout.copy_(o, non_blocking=True)
+            torch.cuda.synchronize()
+            return hout.numpy()
+
+        e2e_step = e2e_step_pshard if pshard else e2e_step_host
 
         e2e_step()  # warm-up (allocations, page faults of the pinned result)
         barrier()
@@ -264,7 +315,8 @@ def run_b200(args):
         d2h = int(hout.numel() * hout.element_size())
         e2e = {"value": total_lines * args.steps / e2e_elapsed, "unit": "spectra/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_elapsed / args.steps * 1e3,
-               "call": "_spectra_priv._Particle_Interpolate(host buffers, extra_lines) -> fsb_particle_interpolate_multi_host",
+               "call": ("pinned host -> device, native.CandidateIndex + compute_tau, NCCL all-reduce, device -> pinned host" if pshard else
+                        "_spectra_priv._Particle_Interpolate(host buffers, extra_lines) -> fsb_particle_interpolate_multi_host"),
                "mean_tau_check": float(np.mean(res[0][: min(64, w["nlos"])]))}
         del pin, hout
 
@@ -285,8 +337,10 @@ def run_b200(args):
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload, "particles": int(w["npart"]), "sightlines_per_gpu": int(w["nlos"]),
-                       "pixels": int(w["nbins"]), "pixel_kms": w["res"], "lines": list(w["lines"]), "sph_kernel": "cubic",
-                       "voigt": args.voigt, "parallelism": "sightline-sharded x%d, particles replicated" % world,
+                       "pixels": int(w["nbins"]), "pixel_kms": w["res"], "lines": list(w["lines"]), "sph_kernel": {0: "tophat", 1: "cubic", 2: "voronoi", 3: "quintic"}[w["kernel"]],
+                       "voigt": args.voigt,
+                       "parallelism": ("particle-sharded x%d (%d cells per rank), NCCL all-reduce of the FP64 tau array each step"
+                                       % (world, w["npart"])) if pshard else "sightline-sharded x%d, particles replicated" % world,
                        "l2": "inputs and outputs larger than L2 (particles %.2f GB, tau %.2f GB per GPU)" % (
                            w["npart"] * 36 / 1e9, nlines * w["nlos"] * w["nbins"] * 8 / 1e9),
                        "step": "index build + tau of all lines for every sightline, inputs resident in HBM"},
@@ -302,6 +356,10 @@ def run_b200(args):
                          "reference_equivalent_tflops": FLOP_PER_VOIGT_REFERENCE * n_voigt_step / n_tau_launches / tau_launch_s / 1e12,
                          "march_steps_by_route": dict(zip(["near_gauss", "near", "far", "straddle", "slow"], [int(v) for v in routes])),
                          "tau_share_of_step": tau_launch_s * n_tau_launches / (elapsed / args.steps)},
+            "index_build": {"bound": "hbm", "ms": index_s * 1e3, "algorithmic_bytes": index_bytes,
+                            "achieved": index_bytes / index_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                            "frac": index_bytes / index_s / 1e9 / hbm_peak, "peak_source": hbm_src,
+                            "share_of_step": index_s / (elapsed / args.steps)},
             "cpu_baseline": cpu, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "check_mean_tau": sanity,
         }
@@ -363,7 +421,7 @@ def run_reference(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload, "particles": int(w["npart"]), "pixels": int(w["nbins"]),
-                       "lines": list(w["lines"]), "sph_kernel": "cubic",
+                       "lines": list(w["lines"]), "sph_kernel": {0: "tophat", 1: "cubic", 2: "voronoi", 3: "quintic"}[w["kernel"]],
                        "note": "reference C++ (OpenMP, all host threads) on a bounded sightline sample; wall %.1f s" % wall},
             "cpu_baseline": cpu, "e2e": {"value": value, "unit": "spectra/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))

@@ -64,6 +64,8 @@ enum SharedField {
     S_LD16,      // exp(-2 D16 step): downward march
     S_LD32,
     S_RECMAX,    // largest pixel count per step (0, 16 or 32) for which the recurrence is safe
+    S_XB0,       // xb of the centre of pixel zmax: -vhigh/b - ((zmax + 1/2) bintov - vel)/b
+    S_PIX,       // pixel width in units of btherm
     S_COUNT
 };
 enum LineField {
@@ -84,14 +86,14 @@ template <int NL> struct SlabSize { static constexpr int kDoubles = (S_COUNT + N
 // All return sum_i kw_i H(x_i, y_l) for x_i = xb + (i+1) step, per fused line l.
 
 // NEAR: every node at |x| < 16.  U0 = exp(-x_1^2), R = exp(-(2 x_1 + step) step), q = exp(-2 step^2)
-// (U0 = R = 0 when the Gaussian is negligible).  The table Horner runs node-interleaved (7
+// (gauss = false when the Gaussian is negligible for the whole warp step).  The table Horner runs node-interleaved (7
 // independent chains); x and s are recomputed where needed rather than kept live, and the Gaussians
 // are produced on the fly by the node recurrence.  Lanes with nodes beyond the table compute
 // finite garbage that the caller discards.
 template <int NL>
 __device__ __forceinline__ void node_sum_near(double xb, double step, const double *__restrict__ sl,
-                                              const double *__restrict__ tab, double U0, double R, unsigned lmask,
-                                              double (&tot)[NL])
+                                              const double *__restrict__ tab, double U0, double R, bool gauss,
+                                              unsigned lmask, double (&tot)[NL])
 {
     static_assert(FSB_GTAB_DEG == 7, "node_sum_near is written for a degree-7 table");
     double t[7], g[7];
@@ -133,17 +135,25 @@ __device__ __forceinline__ void node_sum_near(double xb, double step, const doub
             continue;
         }
         const double a0 = LF(l, L_A0), a1 = LF(l, L_A0 + 1), a2 = LF(l, L_A0 + 2), a3 = LF(l, L_A0 + 3);
-        const double p0 = LF(l, L_PE0), p1 = LF(l, L_PE0 + 1), p2 = LF(l, L_PE0 + 2), p3 = LF(l, L_PE0 + 3);
         double acc = fma(fma(fma(fma(LF(l, L_BQ0 + 4), xb, LF(l, L_BQ0 + 3)), xb, LF(l, L_BQ0 + 2)), xb, LF(l, L_BQ0 + 1)), xb,
                          LF(l, L_BQ0));
-        double u = U0, r = R;
-        #pragma unroll
-        for (int i = 0; i < 7; ++i) {
-            const double A = fma(fma(fma(a3, t[i], a2), t[i], a1), t[i], a0);
-            const double Pe = fma(fma(fma(p3, t[i], p2), t[i], p1), t[i], p0);
-            acc = fma(fma(u, Pe, g[i] * A), SF(S_KW0 + i), acc);
-            u *= r;
-            r *= q;
+        if (gauss) {
+            const double p0 = LF(l, L_PE0), p1 = LF(l, L_PE0 + 1), p2 = LF(l, L_PE0 + 2), p3 = LF(l, L_PE0 + 3);
+            double u = U0, r = R;
+            #pragma unroll
+            for (int i = 0; i < 7; ++i) {
+                const double A = fma(fma(fma(a3, t[i], a2), t[i], a1), t[i], a0);
+                const double Pe = fma(fma(fma(p3, t[i], p2), t[i], p1), t[i], p0);
+                acc = fma(fma(u, Pe, g[i] * A), SF(S_KW0 + i), acc);
+                u *= r;
+                r *= q;
+            }
+        } else {  // the Gaussian is negligible for every lane of this step
+            #pragma unroll
+            for (int i = 0; i < 7; ++i) {
+                const double A = fma(fma(fma(a3, t[i], a2), t[i], a1), t[i], a0);
+                acc = fma(g[i] * A, SF(S_KW0 + i), acc);
+            }
         }
         tot[l] = acc;
     }
@@ -248,7 +258,7 @@ __device__ __forceinline__ void march(const double *__restrict__ sl, const doubl
                                       int64_t line_stride, int nbins, double bintov, double tautail, int lane, Tally &tally)
 {
     const int half = nbins / 2;
-    const double vel = SF(S_VEL), inv_b = SF(S_INVB), step = SF(S_STEP), xoff = SF(S_XOFF);
+    const double vel = SF(S_VEL), step = SF(S_STEP), xb0 = SF(S_XB0), pix = SF(S_PIX);
     const int zmax = (int) SF(S_ZMAX);
     const int j0 = wrap_bin(zmax, nbins);
     // pixel width >= btherm/2 anywhere?  (bintov is rounded differently per pixel by at most an ulp)
@@ -290,11 +300,11 @@ __device__ __forceinline__ void march(const double *__restrict__ sl, const doubl
             cur[l] = 0;
             if (mine && ((live[l] >> dir) & 1u)) cur[l] = row0[l * line_stride + j];
         }
-        const double vlow = __dsub_rn(__dmul_rn((double) z, bintov), vel);
-        const double vhigh_px = __dadd_rn(vlow, bintov);
         double t[NL];
         int ninner = 1;
         if (EXACT || any_sub) {
+            const double vlow = __dsub_rn(__dmul_rn((double) z, bintov), vel);
+            const double vhigh_px = __dadd_rn(vlow, bintov);
             rec_cfg = -1;
             if (COUNT) ++tally.route[4];
             #pragma unroll
@@ -303,13 +313,30 @@ __device__ __forceinline__ void march(const double *__restrict__ sl, const doubl
                 if (mine && ((lmask >> l) & 1u)) t[l] = LF(l, L_CD) * pixel_sum_slow<EXACT>(vlow, vhigh_px, sl, l, tab, ninner);
             }
         } else {
-            const double vmid = (vhigh_px + vlow) / 2.;
-            const double xb = fma(-vmid, inv_b, xoff);
+            // node 0 of pixel z in units of btherm: affine in the pixel offset from zmax (the reference's
+            // (vlow + vhigh)/2 differs from this by rounding only, < 1e-13 in x)
+            const double xb = fma((double) (z - zmax), -pix, xb0);
             const double x1 = xb + step, x7 = fma(7.0, step, xb);  // x1 <= x7
-            // lane class: 0 every node inside |x| < 16, 1 every node outside, 2 straddling, 3 idle
-            const int lc = !mine ? 3 : ((x1 > -FSB_GTAB_XMAX && x7 < FSB_GTAB_XMAX) ? 0 : ((x1 >= FSB_GTAB_XMAX || x7 <= -FSB_GTAB_XMAX) ? 1 : 2));
+            // The table covers |x| < 24 and the wing series |x| >= 16: a pixel may take the table route
+            // if all its nodes are inside 24, the series route if all are outside 16.  Lane class:
+            // 0 table, 1 series, 2 neither (nodes on both sides of the overlap), 3 idle.
+            const bool near_ok = x1 > -FSB_GTAB_XMAX && x7 < FSB_GTAB_XMAX;
+            const bool far_ok = x1 >= kFarXMin || x7 <= -kFarXMin;
             const bool core = mine && !(x1 >= xu || x7 <= -xu);  // within reach of the Gaussian
-            const unsigned cls = __reduce_or_sync(kFull, (1u << lc) | (core ? 16u : 0u));
+            const unsigned m = __reduce_or_sync(kFull, ((mine && !near_ok) ? 1u : 0u) | ((mine && !far_ok) ? 2u : 0u) | (core ? 4u : 0u));
+            int lc;
+            unsigned cls;
+            if (!(m & 1u)) {  // every lane can use the table
+                lc = 0;
+                cls = 1u;
+            } else if (!(m & 2u)) {  // every lane can use the series
+                lc = 1;
+                cls = 2u;
+            } else {
+                lc = !mine ? 3 : (far_ok ? 1 : (near_ok ? 0 : 2));
+                cls = __reduce_or_sync(kFull, 1u << lc);
+            }
+            if (m & 4u) cls |= 16u;
             double tot[NL];
             #pragma unroll
             for (int l = 0; l < NL; ++l) tot[l] = 0;
@@ -326,7 +353,7 @@ __device__ __forceinline__ void march(const double *__restrict__ sl, const doubl
                         U0 = exp(-x1 * x1);
                         R = exp(-fma(2.0, x1, step) * step);
                         if (npx <= recmax) {
-                            const double delta = (dir ? (double) npx : (double) -npx) * (bintov * inv_b);
+                            const double delta = (dir ? (double) npx : (double) -npx) * pix;
                             rho = exp(-fma(2.0, x1, delta) * delta);
                         }
                     }
@@ -338,7 +365,7 @@ __device__ __forceinline__ void march(const double *__restrict__ sl, const doubl
                     rec_cfg = -1;
                     if (COUNT) ++tally.route[1];
                 }
-                node_sum_near<NL>(xb, step, sl, tab, U0, R, lmask, tot);
+                node_sum_near<NL>(xb, step, sl, tab, U0, R, (cls & 16u) != 0, lmask, tot);
             } else {
                 rec_cfg = -1;
             }
@@ -353,7 +380,7 @@ __device__ __forceinline__ void march(const double *__restrict__ sl, const doubl
                 if (lc == 2) {
                     #pragma unroll
                     for (int l = 0; l < NL; ++l)
-                        if ((lmask >> l) & 1u) tot[l] = node_sum_generic(vmid, sl, l, tab);
+                        if ((lmask >> l) & 1u) tot[l] = node_sum_generic((SF(S_XOFF) - xb) / SF(S_INVB), sl, l, tab);
                 }
                 if (COUNT) ++tally.route[3];
             }
@@ -455,7 +482,10 @@ __device__ __noinline__ void setup_particle(const InterpConsts &C, double *__res
             p *= d;
         }
     }
-    SF(S_ZMAX) = floor(velp / C.bintov);
+    const double zmaxd = floor(velp / C.bintov);
+    SF(S_ZMAX) = zmaxd;
+    SF(S_XB0) = fma(-(fma(zmaxd + 0.5, C.bintov, -velp)), inv_b, -vhigh * inv_b);
+    SF(S_PIX) = C.bintov * inv_b;
     // march-step recurrence factors: D = npx pixels in units of btherm
     const double pix = C.bintov * inv_b;
     const double D16 = 16.0 * pix, D32 = 32.0 * pix;

@@ -5,7 +5,7 @@
 // voigt fast  : this library's own evaluation for the small damping parameters of real lines
 //               (0 <= y <= kFastYMax): expansion of w about the real axis to order y^7,
 //                   H(x,y) = U(x) Pe(s) + G(x) A(s) + B(s),   s = x^2,  U = exp(-s),
-//                   G(x) = 1 - 2 x Dawson(x)   (129 piecewise degree-7 polynomials, |x| < 16),
+//                   G(x) = 1 - 2 x Dawson(x)   (193 piecewise degree-7 polynomials, |x| < 24),
 //               with Pe, A, B polynomials in s whose coefficients depend on y only (per-particle
 //               constants).  Beyond |x| >= 16 the Gaussian has vanished and the profile is the
 //               Taylor series in y of the damping wing, -y L' + y^3 L'''/6 - y^5 L^(5)/120 with
@@ -172,6 +172,7 @@ __device__ double voigt_exact(double xin, double y, double erfcx_y)
 
 // ---- fast path -----------------------------------------------------------------------------
 
+constexpr double kFarXMin = 16.0;     // the damping-wing series is used from here on; the table reaches FSB_GTAB_XMAX = 24
 constexpr double kFastYMax = 0.03;    // above: voigt_exact (error of the y^7 truncation < 3e-13 below)
 constexpr double kFastYMin = 1e-30;   // below (and > 0): voigt_exact (Gaussian cut-off would pass exp underflow)
 
@@ -265,7 +266,7 @@ __device__ __forceinline__ double voigt_far(double s, double y)
 __device__ __forceinline__ double voigt_fast_with_u(double ax, double s, double U, const FastCoef &c,
                                                     const double *__restrict__ tab)
 {
-    if (ax >= FSB_GTAB_XMAX) return voigt_far(s, c.y);
+    if (ax >= kFarXMin) return voigt_far(s, c.y);
     const double G = g_table(ax, tab);
     const double Pe = fma(fma(fma(c.pe[3], s, c.pe[2]), s, c.pe[1]), s, c.pe[0]);
     const double A = fma(fma(fma(c.a[3], s, c.a[2]), s, c.a[1]), s, c.a[0]);

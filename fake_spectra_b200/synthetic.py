@@ -41,11 +41,13 @@ class Cosmology:
         return self.rscale * self.Hz / MPC_IN_CM
 
 
-def _fields(nside, seed):
-    """Primitive per-particle fields: positions, overdensity, temperature, 3 velocity components."""
+def _fields(nside, seed, box=None):
+    """Primitive per-particle fields: positions, overdensity, temperature, 3 velocity components.
+    ``box`` overrides the default side (mean spacing x nside): a shard of a larger box."""
     npart = int(nside) ** 3
     rng = np.random.default_rng(seed)
-    box = MEAN_SPACING * nside
+    if box is None:
+        box = MEAN_SPACING * nside
     pos = (rng.random((npart, 3), dtype=np.float64) * box).astype(np.float32)
     # positions must stay inside [0, box): float32 rounding can land exactly on box
     np.minimum(pos, np.nextafter(np.float32(box), np.float32(0)), out=pos)
@@ -57,7 +59,7 @@ def _fields(nside, seed):
     return box, pos, delta, temp, vel
 
 
-def boundary_arrays(nside, seed=42, kernel=1, metal_scale=1.0):
+def boundary_arrays(nside, seed=42, kernel=1, metal_scale=1.0, box=None):
     """Arrays as they cross the native boundary.
 
     Returns a dict with ``box`` (kpc/h), ``pos`` f32[N,3], ``vel`` f32[N,3] (physical km/s, already
@@ -65,7 +67,7 @@ def boundary_arrays(nside, seed=42, kernel=1, metal_scale=1.0):
     spectra.py:593-615), ``temp`` f32[N] (K), ``h`` f32[N] (kernel support radius, kpc/h).
     ``kernel`` 0 mimics Arepo (h = Volume^(1/3), abstractsnapshot.py:268), otherwise SPH.
     """
-    box, pos, delta, temp, vel = _fields(nside, seed)
+    box, pos, delta, temp, vel = _fields(nside, seed, box)
     hh = MEAN_SPACING * delta ** (-1.0 / 3.0)
     if kernel in (0, 2):
         hh = hh  # cell "radius" = Volume^(1/3) = spacing * delta^(-1/3): same scaling

@@ -1,0 +1,101 @@
+"""Parity at BASELINE.json's sizes.
+
+* configs[0] (2x64^3 particles, 1000 random x-axis sightlines, H I Lya tau + column density) in full
+  against the CPU oracle: 1e-10 relative, identical zero pattern, identical candidate lists.
+* configs[1] (GriddedSpectra 256x256 on 2x256^3, Lya + Lyb): the oracle cannot run 65 536 sightlines in
+  test time, so the full-size GPU run is checked through rows: every sightline is independent and
+  the kernel is deterministic, hence (a) the rows of a regular 192-sightline subsample of the full run
+  must equal, bit for bit, a GPU run on just those sightlines, and (b) that small run is checked
+  against the oracle at 1e-10.  Plus a checksum property: two calls accumulating halves of the
+  particle set reproduce the full run to 1e-12.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(__file__))
+import cases  # noqa: E402
+from fake_spectra_b200 import synthetic as syn  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def _dev(torch, d):
+    return {k: torch.from_numpy(np.ascontiguousarray(d[k])).cuda() for k in ("pos", "vel", "dens", "temp", "h", "cofm", "axis")}
+
+
+def test_config0_full_vs_oracle(oracle):
+    import torch
+    from fake_spectra_b200 import _lib, native
+    d = syn.boundary_arrays(64, seed=42)
+    d["cofm"], d["axis"] = syn.random_sightlines(d["box"], 1000, seed=23, axis=1)
+    p = cases.params(d)
+    assert p["nbins"] == 1115
+    t = _dev(torch, d)
+    idx = native.CandidateIndex(d["box"], t["cofm"], t["axis"], t["pos"], t["h"])
+    off, part, dr2 = (x.cpu().numpy() for x in idx.export())
+    o_off, o_part, o_dr2 = oracle.near_particles(d["cofm"], d["axis"], d["box"], d["pos"], d["h"])
+    assert np.array_equal(off, o_off) and np.array_equal(part, o_part) and np.array_equal(dr2, o_dr2)
+    prm = _lib.make_params(**p)
+    tau = idx.compute_tau(prm, t["pos"], t["vel"], t["dens"], t["temp"], t["h"]).cpu().numpy()
+    col = idx.compute_colden(prm, t["pos"], t["dens"], t["h"]).cpu().numpy()
+    near = oracle.near_lines(d["box"], d["pos"], d["h"], d["axis"], d["cofm"])
+    sub = {k: np.ascontiguousarray(d[k][near]) for k in ("pos", "vel", "dens", "temp", "h")}
+    want = oracle.compute_tau(**p, pos=sub["pos"], vel=sub["vel"], dens=sub["dens"], temp=sub["temp"], h=sub["h"],
+                              axis=d["axis"], cofm=d["cofm"])
+    rel, same_zero = cases.rel_err(tau, want)
+    assert same_zero and rel < TOL, rel
+    want = oracle.compute_colden(**p, pos=sub["pos"], dens=sub["dens"], h=sub["h"], axis=d["axis"], cofm=d["cofm"])
+    rel, same_zero = cases.rel_err(col, want)
+    assert same_zero and rel < TOL, rel
+    assert 0.3 < tau.mean() < 0.7  # a realistic forest (mean tau 0.47)
+
+
+def test_config1_full_size_rows(oracle):
+    import torch
+    from fake_spectra_b200 import _lib, native
+    d = syn.boundary_arrays(256, seed=42)
+    cofm, axis = syn.grid_sightlines(d["box"], 256, axis=1)
+    d["cofm"], d["axis"] = cofm, axis
+    pa, pb = cases.params(d, line="HI1215"), cases.params(d, line="HI1025")
+    assert cofm.shape[0] == 65536 and pa["nbins"] == 4460
+    t = _dev(torch, d)
+    idx = native.CandidateIndex(d["box"], t["cofm"], t["axis"], t["pos"], t["h"])
+    prms = [_lib.make_params(**pa), _lib.make_params(**pb)]
+    full = idx.compute_tau(prms, t["pos"], t["vel"], t["dens"], t["temp"], t["h"])          # [2, 65536, 4460] in HBM
+    sel = np.linspace(0, 65535, 192).astype(np.int64)
+    rows = full[:, torch.from_numpy(sel).cuda()].cpu().numpy()
+    # property: halves of the particle set accumulate to the full result
+    n = d["pos"].shape[0] // 2
+    acc = torch.zeros_like(full[0])
+    for sl in (slice(0, n), slice(n, None)):
+        native.particle_interpolate(1, prms[0], t["pos"][sl].contiguous(), t["vel"][sl].contiguous(), t["dens"][sl].contiguous(),
+                                    t["temp"][sl].contiguous(), t["h"][sl].contiguous(), t["axis"], t["cofm"], out=acc)
+    diff = (acc - full[0]).abs().max().item() / full[0].abs().max().item()
+    assert diff < 1e-12, diff
+    assert bool(((acc == 0) == (full[0] == 0)).all().item())
+    del full, acc
+    idx.free()
+    # (a) the same sightlines alone: bit-identical rows
+    sc = torch.from_numpy(np.ascontiguousarray(cofm[sel])).cuda()
+    sa = torch.from_numpy(np.ascontiguousarray(axis[sel])).cuda()
+    small = native.CandidateIndex(d["box"], sc, sa, t["pos"], t["h"])
+    # one work item per sightline, as in the full run (few sightlines would otherwise be split over
+    # several warps, which only changes the summation tree)
+    whole = [_lib.make_params(**pa, seg_pairs=1 << 30), _lib.make_params(**pb, seg_pairs=1 << 30)]
+    got = small.compute_tau(whole, t["pos"], t["vel"], t["dens"], t["temp"], t["h"]).cpu().numpy()
+    assert np.array_equal(got, rows)
+    split = small.compute_tau(prms, t["pos"], t["vel"], t["dens"], t["temp"], t["h"]).cpu().numpy()
+    rel, same_zero = cases.rel_err(split, rows)
+    assert same_zero and rel < 1e-13, rel
+    # (b) against the oracle
+    near = oracle.near_lines(d["box"], d["pos"], d["h"], axis[sel], cofm[sel])
+    sub = {k: np.ascontiguousarray(d[k][near]) for k in ("pos", "vel", "dens", "temp", "h")}
+    for k, p in enumerate((pa, pb)):
+        want = oracle.compute_tau(**p, pos=sub["pos"], vel=sub["vel"], dens=sub["dens"], temp=sub["temp"], h=sub["h"],
+                                  axis=axis[sel], cofm=cofm[sel])
+        rel, same_zero = cases.rel_err(got[k], want)
+        assert same_zero and rel < TOL, (k, rel)
