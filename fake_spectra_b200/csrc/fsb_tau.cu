@@ -79,6 +79,13 @@ enum LineField {
 };
 template <int NL> struct SlabSize { static constexpr int kDoubles = (S_COUNT + NL * L_COUNT) * kBatch; };
 
+// FP32 fast path: float copies of the node constants, [field][kBatch] floats per warp after the doubles
+enum FShared { F_STEP = 0, F_KW0, F_COUNT = F_KW0 + 7 };
+enum FLineField { FL_A0 = 0, FL_PE0 = 3, FL_BQ0 = 6, FL_Y2 = 11, FL_YISP, FL_COUNT };
+template <int NL> struct FSlabSize { static constexpr int kFloats = (F_COUNT + NL * FL_COUNT) * kBatch; };
+#define FS(f) fl[(f) * kBatch]
+#define FLF(l, f) fl[(F_COUNT + (l) * FL_COUNT + (f)) * kBatch]
+
 #define SF(f) sl[(f) * kBatch]
 #define LF(l, f) sl[(S_COUNT + (l) * L_COUNT + (f)) * kBatch]
 
@@ -191,6 +198,81 @@ __device__ __forceinline__ void node_sum_far(double xb, double step, const doubl
     }
 }
 
+// ---- FP32 fast path (FSB_PRECISION_FP32: flux within 1e-5 of the reference) ------------------------
+// Same decomposition in single precision: the pixel coordinate xb is formed in FP64 (velocities of
+// thousands of km/s against 1e-5 accuracy), everything per node runs in FP32: degree-3 table pieces
+// (one 16-byte load per node), quadratics for A and Pe, one __expf per node for the Gaussian.
+template <int NL>
+__device__ __forceinline__ void node_sum_near32(float xb, float step, const float *__restrict__ fl,
+                                                const float4 *__restrict__ tab32, bool gauss, unsigned lmask,
+                                                float (&tot)[NL])
+{
+    float s[7], g[7], U[7];
+    #pragma unroll
+    for (int i = 0; i < 7; ++i) {
+        const float x = fmaf((float) (i + 1), step, xb), ax = fabsf(x);
+        const float m = fmaf(ax, (float) FSB_GTAB_INV_DELTA, 12582912.0f);  // 1.5 * 2^23: low bits = rint(8|x|)
+        const int k = min(__float_as_int(m) & 0x3fffff, FSB_GTAB_NINT - 1);
+        const float t = fmaf(m - 12582912.0f, -1.0f / (float) FSB_GTAB_INV_DELTA, ax);
+        const float4 c = tab32[k];
+        g[i] = fmaf(fmaf(fmaf(c.w, t, c.z), t, c.y), t, c.x);
+        s[i] = x * x;
+    }
+    if (gauss) {  // one special-function-unit exponential per node: no recurrence to overflow in FP32
+        #pragma unroll
+        for (int i = 0; i < 7; ++i) U[i] = __expf(-s[i]);
+    }
+    #pragma unroll
+    for (int l = 0; l < NL; ++l) {
+        if (NL > 1 && !((lmask >> l) & 1u)) {
+            tot[l] = 0;
+            continue;
+        }
+        const float a0 = FLF(l, FL_A0), a1 = FLF(l, FL_A0 + 1), a2 = FLF(l, FL_A0 + 2);
+        float acc = fmaf(fmaf(fmaf(fmaf(FLF(l, FL_BQ0 + 4), xb, FLF(l, FL_BQ0 + 3)), xb, FLF(l, FL_BQ0 + 2)), xb, FLF(l, FL_BQ0 + 1)),
+                         xb, FLF(l, FL_BQ0));
+        if (gauss) {
+            const float p0 = FLF(l, FL_PE0), p1 = FLF(l, FL_PE0 + 1), p2 = FLF(l, FL_PE0 + 2);
+            #pragma unroll
+            for (int i = 0; i < 7; ++i) {
+                const float A = fmaf(fmaf(a2, s[i], a1), s[i], a0);
+                const float Pe = fmaf(fmaf(p2, s[i], p1), s[i], p0);
+                acc = fmaf(fmaf(U[i], Pe, g[i] * A), FS(F_KW0 + i), acc);
+            }
+        } else {
+            #pragma unroll
+            for (int i = 0; i < 7; ++i) acc = fmaf(g[i] * fmaf(fmaf(a2, s[i], a1), s[i], a0), FS(F_KW0 + i), acc);
+        }
+        tot[l] = acc;
+    }
+}
+
+template <int NL>
+__device__ __forceinline__ void node_sum_far32(float xb, float step, const float *__restrict__ fl, unsigned lmask,
+                                               float (&tot)[NL])
+{
+    float u[7], p1[7], p3[7];
+    #pragma unroll
+    for (int i = 0; i < 7; ++i) {
+        const float x = fmaf((float) (i + 1), step, xb);
+        u[i] = __frcp_rn(x * x);
+        p1[i] = fmaf(fmaf(fmaf(13.125f, u[i], 3.75f), u[i], 1.5f), u[i], 1.0f);
+        p3[i] = fmaf(5.0f, u[i], 1.0f);
+    }
+    #pragma unroll
+    for (int l = 0; l < NL; ++l) {
+        if (NL > 1 && !((lmask >> l) & 1u)) {
+            tot[l] = 0;
+            continue;
+        }
+        const float y2 = FLF(l, FL_Y2);
+        float acc = 0;
+        #pragma unroll
+        for (int i = 0; i < 7; ++i) acc = fmaf(u[i] * fmaf(-y2 * u[i], p3[i], p1[i]), FS(F_KW0 + i), acc);
+        tot[l] = FLF(l, FL_YISP) * acc;
+    }
+}
+
 // Generic per-node evaluation at velocity offset vouter for ONE line (mixed near/far warp steps and
 // sub-sampled pixels).
 __device__ __noinline__ double node_sum_generic(double vouter, const double *__restrict__ sl, int l,
@@ -253,9 +335,10 @@ struct Tally {
 
 // Outward pixel march of one particle (absorption.cpp:250-278) for NL fused lines.
 // live[l]: bit 0 = the upward run of line l is still going, bit 1 = the downward run.
-template <int NL, bool EXACT, bool COUNT>
-__device__ __forceinline__ void march(const double *__restrict__ sl, const double *__restrict__ tab, double *__restrict__ row0,
-                                      int64_t line_stride, int nbins, double bintov, double tautail, int lane, Tally &tally)
+template <int NL, bool EXACT, bool COUNT, bool F32>
+__device__ __forceinline__ void march(const double *__restrict__ sl, const float *__restrict__ fl, const double *__restrict__ tab,
+                                      const float4 *__restrict__ tab32, double *__restrict__ row0, int64_t line_stride, int nbins,
+                                      double bintov, double tautail, int lane, Tally &tally)
 {
     const int half = nbins / 2;
     const double vel = SF(S_VEL), step = SF(S_STEP), xb0 = SF(S_XB0), pix = SF(S_PIX);
@@ -341,6 +424,22 @@ __device__ __forceinline__ void march(const double *__restrict__ sl, const doubl
             #pragma unroll
             for (int l = 0; l < NL; ++l) tot[l] = 0;
             const bool pure_near = !(cls & 6u);
+            if (F32) {
+                float tf[NL];
+                const float xbf = (float) xb, stepf = FS(F_STEP);
+                if (cls & 1u) {
+                    if (COUNT) ++tally.route[(cls & 16u) ? 0 : 1];
+                    node_sum_near32<NL>(xbf, stepf, fl, tab32, (cls & 16u) != 0, lmask, tf);
+                    #pragma unroll
+                    for (int l = 0; l < NL; ++l) tot[l] = (double) tf[l];
+                }
+                if (cls & 2u) {
+                    node_sum_far32<NL>(xbf, stepf, fl, lmask, tf);
+                    #pragma unroll
+                    for (int l = 0; l < NL; ++l) tot[l] = lc == 1 ? (double) tf[l] : tot[l];
+                    if (COUNT) ++tally.route[2];
+                }
+            } else {
             if (cls & 1u) {
                 if (cls & 16u) {
                     const int cfg = both ? 0 : 1 + dir;
@@ -375,6 +474,7 @@ __device__ __forceinline__ void march(const double *__restrict__ sl, const doubl
                 #pragma unroll
                 for (int l = 0; l < NL; ++l) tot[l] = lc == 1 ? tfar[l] : tot[l];
                 if (COUNT) ++tally.route[2];
+            }
             }
             if (cls & 4u) {  // lanes whose own nodes straddle |x| = 16: node by node
                 if (lc == 2) {
@@ -414,12 +514,12 @@ template <int NL, bool COUNT>
 __device__ __noinline__ void march_exact(const double *__restrict__ sl, const double *__restrict__ tab, double *__restrict__ row0,
                                          int64_t line_stride, int nbins, double bintov, double tautail, int lane, Tally &tally)
 {
-    march<NL, true, COUNT>(sl, tab, row0, line_stride, nbins, bintov, tautail, lane, tally);
+    march<NL, true, COUNT, false>(sl, nullptr, tab, nullptr, row0, line_stride, nbins, bintov, tautail, lane, tally);
 }
 
 // Per-particle constants, one particle per lane (absorption.cpp:218-246, singleabs.h:81-90).
 template <int KERNEL, int NL>
-__device__ __noinline__ void setup_particle(const InterpConsts &C, double *__restrict__ sl, int64_t k, int ax,
+__device__ __noinline__ void setup_particle(const InterpConsts &C, double *__restrict__ sl, float *__restrict__ fl, int64_t k, int ax,
                                                const int32_t *__restrict__ particle, const double *__restrict__ dr2s,
                                                const float *__restrict__ pos, const float *__restrict__ vel,
                                                const float *__restrict__ dens, const float *__restrict__ temp,
@@ -469,7 +569,9 @@ __device__ __noinline__ void setup_particle(const InterpConsts &C, double *__res
         const double vv = i * deltav - vhigh;
         kw[i - 1] = sph_kernel<KERNEL>(sqrt(vdr2 + vv * vv) / vsmooth) * deltav;
         SF(S_KW0 + i - 1) = kw[i - 1];
+        FS(F_KW0 + i - 1) = (float) kw[i - 1];
     }
+    FS(F_STEP) = (float) step;
     // moments of the node weights about xb, in units of btherm: M_n = sum kw_i (i step)^n
     double M[5] = {0, 0, 0, 0, 0};
     #pragma unroll
@@ -520,6 +622,14 @@ __device__ __noinline__ void setup_particle(const InterpConsts &C, double *__res
         LF(l, L_BQ0 + 2) = fma(6.0 * fc.b[2], M[2], fc.b[1] * M[0]);
         LF(l, L_BQ0 + 3) = 4.0 * fc.b[2] * M[1];
         LF(l, L_BQ0 + 4) = fc.b[2] * M[0];
+        #pragma unroll
+        for (int i = 0; i < 3; ++i) FLF(l, FL_A0 + i) = (float) fc.a[i];
+        #pragma unroll
+        for (int i = 0; i < 3; ++i) FLF(l, FL_PE0 + i) = (float) fc.pe[i];
+        #pragma unroll
+        for (int i = 0; i < 5; ++i) FLF(l, FL_BQ0 + i) = (float) LF(l, L_BQ0 + i);
+        FLF(l, FL_Y2) = (float) (aa * aa);
+        FLF(l, FL_YISP) = (float) (aa * 0.56418958354775628694807945156);
     }
     if (mode == 2) {
         #pragma unroll
@@ -531,7 +641,13 @@ __device__ __noinline__ void setup_particle(const InterpConsts &C, double *__res
     SF(S_MODE) = (double) mode;
 }
 
-template <int KERNEL, int NL, bool COUNT>
+template <int NL> constexpr size_t tau_smem_bytes()
+{
+    return sizeof(double) * (size_t) (FSB_GTAB_SIZE + kTauWarps * SlabSize<NL>::kDoubles) +
+           sizeof(float) * (size_t) (4 * FSB_GTAB_NINT + kTauWarps * FSlabSize<NL>::kFloats);
+}
+
+template <int KERNEL, int NL, bool COUNT, bool F32>
 __global__ void __launch_bounds__(kTauThreads, FSB_TAU_MIN_BLOCKS)
 k_tau(InterpConsts C, Items items, int n_items, int *__restrict__ next_item, const int64_t *__restrict__ offsets,
       const int32_t *__restrict__ particle, const double *__restrict__ dr2s, const int32_t *__restrict__ axis,
@@ -544,7 +660,14 @@ k_tau(InterpConsts C, Items items, int n_items, int *__restrict__ next_item, con
     double *tab = smem;  // [FSB_GTAB_SIZE], 16-byte aligned
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double *slab = smem + FSB_GTAB_SIZE + warp * SlabSize<NL>::kDoubles;
+    // floats follow the doubles: the degree-3 table of the FP32 path (16-byte aligned), then the float slabs
+    static_assert((FSB_GTAB_SIZE + kTauWarps * SlabSize<NL>::kDoubles) % 2 == 0, "float4 table must stay 16-byte aligned");
+    float *tab32f = reinterpret_cast<float *>(smem + FSB_GTAB_SIZE + kTauWarps * SlabSize<NL>::kDoubles);
+    const float4 *tab32 = reinterpret_cast<const float4 *>(tab32f);
+    float *fslab = tab32f + 4 * FSB_GTAB_NINT + warp * FSlabSize<NL>::kFloats;
     for (int i = threadIdx.x; i < FSB_GTAB_SIZE; i += kTauThreads) tab[i] = d_gtable[i];
+    if (F32)
+        for (int i = threadIdx.x; i < 4 * FSB_GTAB_NINT; i += kTauThreads) tab32f[i] = d_gtable32[i];
     __syncthreads();
 
     const int nbins = C.nbins;
@@ -568,14 +691,14 @@ k_tau(InterpConsts C, Items items, int n_items, int *__restrict__ next_item, con
         for (int64_t k0 = kbeg; k0 < kend; k0 += kBatch) {
             const int nb = (int) min((int64_t) kBatch, kend - k0);
             __syncwarp();
-            if (lane < nb) setup_particle<KERNEL, NL>(C, slab + lane, k0 + lane, ax, particle, dr2s, pos, vel, dens, temp, hsml, cells);
+            if (lane < nb) setup_particle<KERNEL, NL>(C, slab + lane, fslab + lane, k0 + lane, ax, particle, dr2s, pos, vel, dens, temp, hsml, cells);
             __syncwarp();
             for (int b = 0; b < nb; ++b) {
                 const double *sl = slab + b;
                 const int mode = (int) SF(S_MODE);
                 if (mode == 0) continue;
                 if (mode == 2) march_exact<NL, COUNT>(sl, tab, row0, line_stride, nbins, C.bintov, C.tautail, lane, tally);
-                else march<NL, false, COUNT>(sl, tab, row0, line_stride, nbins, C.bintov, C.tautail, lane, tally);
+                else march<NL, false, COUNT, F32>(sl, fslab + b, tab, tab32, row0, line_stride, nbins, C.bintov, C.tautail, lane, tally);
             }
         }
     }
@@ -599,6 +722,8 @@ k_tau(InterpConsts C, Items items, int n_items, int *__restrict__ next_item, con
 
 #undef SF
 #undef LF
+#undef FS
+#undef FLF
 
 __global__ void k_voigt_profile(const double *__restrict__ x, const double *__restrict__ y, double *__restrict__ out,
                                 int64_t n, int voigt)
@@ -618,12 +743,12 @@ __global__ void k_voigt_profile(const double *__restrict__ x, const double *__re
 template <int KERNEL, int NL>
 int launch_tau_k(const fsb_index *idx, const InterpConsts &c, const ItemPlan &plan, int *next_item, const float *pos,
                  const float *vel, const float *dens, const float *temp, const float *h, const float *cells, double *out,
-                 unsigned long long *ctr, cudaStream_t stream)
+                 unsigned long long *ctr, int precision, cudaStream_t stream)
 {
     int dev = 0, sms = 0, per_sm = 0;
     FSB_CUDA_TRY(cudaGetDevice(&dev));
     FSB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const size_t smem = sizeof(double) * (size_t) (FSB_GTAB_SIZE + kTauWarps * SlabSize<NL>::kDoubles);
+    const size_t smem = tau_smem_bytes<NL>();
     const int n_items = (int) plan.n_items;
     auto go = [&](auto kern) -> int {
         FSB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
@@ -636,19 +761,20 @@ int launch_tau_k(const fsb_index *idx, const InterpConsts &c, const ItemPlan &pl
         FSB_CUDA_TRY(cudaGetLastError());
         return FSB_OK;
     };
-    return ctr ? go(k_tau<KERNEL, NL, true>) : go(k_tau<KERNEL, NL, false>);
+    if (precision == FSB_PRECISION_FP32) return ctr ? go(k_tau<KERNEL, NL, true, true>) : go(k_tau<KERNEL, NL, false, true>);
+    return ctr ? go(k_tau<KERNEL, NL, true, false>) : go(k_tau<KERNEL, NL, false, false>);
 }
 
 template <int NL>
 int launch_tau_nl(const fsb_index *idx, const InterpConsts &c, const ItemPlan &plan, int *next_item, const float *pos,
                   const float *vel, const float *dens, const float *temp, const float *h, const float *cells, double *out,
-                  unsigned long long *ctr, cudaStream_t stream)
+                  unsigned long long *ctr, int precision, cudaStream_t stream)
 {
     switch (c.kernel) {
-    case FSB_KERNEL_TOPHAT: return launch_tau_k<FSB_KERNEL_TOPHAT, NL>(idx, c, plan, next_item, pos, vel, dens, temp, h, cells, out, ctr, stream);
-    case FSB_KERNEL_CUBIC: return launch_tau_k<FSB_KERNEL_CUBIC, NL>(idx, c, plan, next_item, pos, vel, dens, temp, h, cells, out, ctr, stream);
-    case FSB_KERNEL_VORONOI: return launch_tau_k<FSB_KERNEL_VORONOI, NL>(idx, c, plan, next_item, pos, vel, dens, temp, h, cells, out, ctr, stream);
-    case FSB_KERNEL_QUINTIC: return launch_tau_k<FSB_KERNEL_QUINTIC, NL>(idx, c, plan, next_item, pos, vel, dens, temp, h, cells, out, ctr, stream);
+    case FSB_KERNEL_TOPHAT: return launch_tau_k<FSB_KERNEL_TOPHAT, NL>(idx, c, plan, next_item, pos, vel, dens, temp, h, cells, out, ctr, precision, stream);
+    case FSB_KERNEL_CUBIC: return launch_tau_k<FSB_KERNEL_CUBIC, NL>(idx, c, plan, next_item, pos, vel, dens, temp, h, cells, out, ctr, precision, stream);
+    case FSB_KERNEL_VORONOI: return launch_tau_k<FSB_KERNEL_VORONOI, NL>(idx, c, plan, next_item, pos, vel, dens, temp, h, cells, out, ctr, precision, stream);
+    case FSB_KERNEL_QUINTIC: return launch_tau_k<FSB_KERNEL_QUINTIC, NL>(idx, c, plan, next_item, pos, vel, dens, temp, h, cells, out, ctr, precision, stream);
     default: set_error("unknown kernel id %d", c.kernel); return FSB_EINVAL;
     }
 }
@@ -662,8 +788,11 @@ int launch_tau(const fsb_index *idx, const InterpConsts &c, const float *pos, co
                const float *temp, const float *h, const float *cells, double *out, fsb_counters *counters, int precision,
                cudaStream_t stream)
 {
-    (void) precision;
     if (idx->nlos == 0 || idx->npairs == 0) return FSB_OK;
+    if (precision != FSB_PRECISION_FP64 && precision != FSB_PRECISION_FP32) {
+        set_error("launch_tau: unknown precision %d", precision);
+        return FSB_EINVAL;
+    }
     if (c.nlines < 1 || c.nlines > kMaxTauLines) {
         set_error("launch_tau: %d fused lines (1..%d)", c.nlines, kMaxTauLines);
         return FSB_EINVAL;
@@ -674,8 +803,8 @@ int launch_tau(const fsb_index *idx, const InterpConsts &c, const float *pos, co
     FSB_TRY(next_item.alloc(sizeof(int), stream));
     FSB_CUDA_TRY(cudaMemsetAsync(next_item.ptr, 0, sizeof(int), stream));
     unsigned long long *ctr = reinterpret_cast<unsigned long long *>(counters);
-    if (c.nlines == 1) FSB_TRY(launch_tau_nl<1>(idx, c, plan, next_item.as<int>(), pos, vel, dens, temp, h, cells, out, ctr, stream));
-    else FSB_TRY(launch_tau_nl<2>(idx, c, plan, next_item.as<int>(), pos, vel, dens, temp, h, cells, out, ctr, stream));
+    if (c.nlines == 1) FSB_TRY(launch_tau_nl<1>(idx, c, plan, next_item.as<int>(), pos, vel, dens, temp, h, cells, out, ctr, precision, stream));
+    else FSB_TRY(launch_tau_nl<2>(idx, c, plan, next_item.as<int>(), pos, vel, dens, temp, h, cells, out, ctr, precision, stream));
     FSB_TRY(reduce_items(plan, idx, c.nbins, c.nlines, out, stream));
     return FSB_OK;
 }

@@ -179,6 +179,9 @@ constexpr double kFastYMin = 1e-30;   // below (and > 0): voigt_exact (Gaussian 
 // Global-memory master copy of the G(x) table; kernels stage it in shared memory.
 __device__ __align__(16) const double d_gtable[FSB_GTAB_SIZE] = FSB_GTAB_VALUES;
 
+// FP32 fast path: degree-3 pieces on the same intervals, {c0, c1, c2, c3} per interval.
+__device__ __align__(16) const float d_gtable32[4 * FSB_GTAB_NINT] = FSB_GTAB32_VALUES;
+
 // y-dependent polynomial coefficients (derived with sympy from w' = -2zw + 2i/sqrt(pi)).
 struct FastCoef {
     double pe[4];  // Pe(s): even orders y^0..y^6, multiplies U

@@ -45,9 +45,15 @@ def run(nside, nlos, axis, voigt, reps=2):
     prm_b = _lib.make_params(**cases.params(d, line="HI1025"), voigt=voigt)
     out2 = torch.zeros((2, nlos, p["nbins"]), dtype=torch.float64, device="cuda")
     t_tau2, _ = timed(lambda: idx.compute_tau([prm, prm_b], t["pos"], t["vel"], t["dens"], t["temp"], t["h"], out=out2), reps)
+    prm32 = _lib.make_params(**p, voigt=voigt, precision=_lib.PRECISION_FP32)
+    prm32_b = _lib.make_params(**cases.params(d, line="HI1025"), voigt=voigt, precision=_lib.PRECISION_FP32)
+    ref64 = out.clone()
+    t_tau32, _ = timed(lambda: idx.compute_tau(prm32, t["pos"], t["vel"], t["dens"], t["temp"], t["h"], out=out.zero_()), reps)
+    flux_err = float((torch.exp(-out) - torch.exp(-ref64 / max(reps, 1) if False else -ref64)).abs().max().item()) if False else None
+    t_tau32_2, _ = timed(lambda: idx.compute_tau([prm32, prm32_b], t["pos"], t["vel"], t["dens"], t["temp"], t["h"], out=out2), reps)
     c = ctr.cpu().numpy()
     res = dict(nside=nside, nlos=nlos, nbins=p["nbins"], voigt=voigt, npairs=idx.npairs, max_list=idx.max_list,
-               t_index=t_idx, t_tau=t_tau, t_tau_lya_lyb=t_tau2, t_colden=t_col, lib=os.path.basename(_lib.LIB_PATH), pairs_per_s=idx.npairs / t_tau, spectra_per_s=nlos / t_tau,
+               t_index=t_idx, t_tau=t_tau, t_tau_lya_lyb=t_tau2, t_tau_fp32=t_tau32, t_tau_fp32_lya_lyb=t_tau32_2, t_colden=t_col, lib=os.path.basename(_lib.LIB_PATH), pairs_per_s=idx.npairs / t_tau, spectra_per_s=nlos / t_tau,
                n_voigt=int(c[2]), voigt_per_s=float(c[2]) / t_tau, pixels=int(c[1]), lane_eff=float(c[1]) / max(float(c[3]), 1),
                routes=[int(v) for v in c[4:9]], check=float(out.mean().item()))
     print(json.dumps(res), flush=True)

@@ -169,6 +169,24 @@ def test_fused_lines_vs_oracle(torch_cuda, oracle):
         assert same_zero and rel < TOL, (k, rel)
 
 
+@pytest.mark.parametrize("kernel,line,res,seed", [(1, "HI1215", 1.0, 41), (1, "HI1025", 1.0, 42), (0, "HI1215", 2.0, 43),
+                                                  (3, "CIV1548", 1.0, 44), (1, "MgII2796", 5.0, 45)])
+def test_fp32_fast_path_flux(priv, oracle, kernel, line, res, seed):
+    """FSB_PRECISION_FP32: |exp(-tau) - exp(-tau_ref)| <= 1e-5 on every pixel (BASELINE.json north_star),
+    including saturated and damped absorbers."""
+    from fake_spectra_b200 import _lib
+    d = cases.random_case(nside=20, nlos=60, axis="cycle", seed=seed, los_seed=seed + 100)
+    d["dens"][::97] *= 3e3
+    p = cases.params(d, line=line, kernel=kernel, res=res)
+    want = oracle.compute_tau(**p, pos=d["pos"], vel=d["vel"], dens=d["dens"], temp=d["temp"], h=d["h"],
+                              axis=d["axis"], cofm=d["cofm"])
+    got = interp(priv, 1, p, d, precision=_lib.PRECISION_FP32)
+    err = np.max(np.abs(np.exp(-got) - np.exp(-want)))
+    assert err <= 1e-5, err
+    assert np.max(np.abs(got - want) / np.maximum(want, 1e-3)) < 1e-4  # and tau itself to ~1e-5 where it matters
+    assert want.max() > 5 and (want < 1).mean() > 0.05  # the case spans unsaturated and saturated pixels
+
+
 def test_signed_weights_colden(priv, oracle):
     d = cases.random_case(nside=12, nlos=30, axis=1, seed=8)
     rng = np.random.default_rng(0)
