@@ -54,18 +54,17 @@ enum SharedField {
     S_Q,         // exp(-2 step^2): second-order ratio of the Gaussian recurrence across nodes
     S_KW0,       // 7 kernel weights x deltav                           singleabs.h:152-163
     S_XU2 = S_KW0 + 7,  // x^2 beyond which exp(-x^2) is negligible against the damping wing
-    S_XU,        // sqrt of it
     S_ZMAX,      // floor(vel/bintov)
     S_MODE,      // 0 skip, 1 fast, 2 exact
-    S_K16,       // exp(-2 D^2), D = 16 pixels in units of btherm: march-step recurrence, half warps
-    S_K32,       // same for D = 32 pixels
-    S_LU16,      // exp(+2 D16 step): ratio update of the inter-node factor, upward march
-    S_LU32,
-    S_LD16,      // exp(-2 D16 step): downward march
-    S_LD32,
-    S_RECMAX,    // largest pixel count per step (0, 16 or 32) for which the recurrence is safe
+    S_K16,       // exp(-2 D^2), D = 16 pixels in units of btherm: march-step recurrence of the Gaussian
+    S_LU16,      // exp(+2 D step): ratio update of the inter-node factor, upward march
+    S_LD16,      // exp(-2 D step): downward march
+    S_RECOK,     // 1 when the march-step recurrence is safe (all factors within e^+-500)
     S_XB0,       // xb of the centre of pixel zmax: -vhigh/b - ((zmax + 1/2) bintov - vel)/b
     S_PIX,       // pixel width in units of btherm
+    S_THR_N,     // int2 {up, down}: outward pixels o < N have all nodes inside the table (|x| < 24)
+    S_THR_F,     // int2: outward pixels o >= F have all nodes on the wing series (|x| >= 16)
+    S_THR_G,     // int2: outward pixels o >= G are out of reach of the Gaussian
     S_COUNT
 };
 enum LineField {
@@ -333,192 +332,245 @@ struct Tally {
     unsigned route[5] = {0, 0, 0, 0, 0};  // near+U, near, far, mixed, slow
 };
 
-// Outward pixel march of one particle (absorption.cpp:250-278) for NL fused lines.
+// ---- outward pixel march of one particle (absorption.cpp:250-278) for NL fused lines --------------
+// Lane layout, fixed for the whole march: lanes 0-15 serve the upward run (z = zmax + o), lanes 16-31
+// the downward run (z = zmax - 1 - o), o = base + (lane & 15); both runs advance 16 pixels per step.
+// The profile is symmetric about the particle, so the two runs end within a step of each other and a
+// finished run idles its half warp for at most that step.
 // live[l]: bit 0 = the upward run of line l is still going, bit 1 = the downward run.
-template <int NL, bool EXACT, bool COUNT, bool F32>
-__device__ __forceinline__ void march(const double *__restrict__ sl, const float *__restrict__ fl, const double *__restrict__ tab,
-                                      const float4 *__restrict__ tab32, double *__restrict__ row0, int64_t line_stride, int nbins,
-                                      double bintov, double tautail, int lane, Tally &tally)
+struct MarchGeom {
+    int dir, sub, half, zmax, j0;
+    unsigned grp_lt, up_lanes, dn_lanes;
+};
+
+__device__ __forceinline__ MarchGeom march_geom(int lane, int nbins, int zmax)
 {
-    const int half = nbins / 2;
-    const double vel = SF(S_VEL), step = SF(S_STEP), xb0 = SF(S_XB0), pix = SF(S_PIX);
-    const int zmax = (int) SF(S_ZMAX);
-    const int j0 = wrap_bin(zmax, nbins);
-    // pixel width >= btherm/2 anywhere?  (bintov is rounded differently per pixel by at most an ulp)
-    const bool any_sub = !(bintov * (1 + 1e-12) < SF(S_HALFB));
-    const int recmax = EXACT ? 0 : (int) SF(S_RECMAX);
-    const double xu = SF(S_XU);
-    const unsigned lt_mask = (1u << lane) - 1u;
+    MarchGeom g;
+    g.dir = lane >> 4;
+    g.sub = lane & 15;
+    g.half = nbins / 2;
+    g.zmax = zmax;
+    g.j0 = wrap_bin(zmax, nbins);
+    g.up_lanes = 0x0000ffffu;
+    g.dn_lanes = 0xffff0000u;
+    g.grp_lt = ((1u << lane) - 1u) & (g.dir ? g.dn_lanes : g.up_lanes);
+    return g;
+}
+
+// add, then stop each run at its first pixel below tautail (absorption.cpp:260-263,274-277)
+template <int NL, bool COUNT>
+__device__ __forceinline__ void march_commit(const MarchGeom &g, const double (&t)[NL], const double (&cur)[NL], unsigned (&live)[NL],
+                                             bool mine, int base, int j, int ninner, double *__restrict__ row0, int64_t line_stride,
+                                             double tautail, Tally &tally)
+{
+    const bool done = base + 16 >= g.half;
+    #pragma unroll
+    for (int l = 0; l < NL; ++l) {
+        const bool on = mine && ((live[l] >> g.dir) & 1u);
+        const unsigned stop = __ballot_sync(kFull, on && (t[l] < tautail));
+        if (on && !(stop & g.grp_lt)) {  // no lane of my run below me has stopped
+            row0[l * line_stride + j] = cur[l] + t[l];
+            if (COUNT) {
+                ++tally.pix;
+                tally.inner += ninner;
+            }
+        }
+        if (done) live[l] = 0;
+        else live[l] &= ~(((stop & g.up_lanes) ? 1u : 0u) | ((stop & g.dn_lanes) ? 2u : 0u));
+    }
+    if (COUNT) ++tally.iter;
+}
+
+// Fast routes.  Which route a step takes follows from integer pixel thresholds computed once per
+// particle (setup_particle): x is affine in the outward pixel index, so "all nodes inside the table",
+// "all nodes on the wing series" and "out of reach of the Gaussian" are index ranges per direction.
+template <int NL, bool COUNT, bool F32>
+__device__ __forceinline__ void march_fast(const double *__restrict__ sl, const float *__restrict__ fl, const double *__restrict__ tab,
+                                           const float4 *__restrict__ tab32, double *__restrict__ row0, int64_t line_stride, int nbins,
+                                           double tautail, int lane, Tally &tally)
+{
+    const MarchGeom g = march_geom(lane, nbins, (int) SF(S_ZMAX));
+    const double step = SF(S_STEP), xb0 = SF(S_XB0), pix = SF(S_PIX);
+    const int2 thrN = *reinterpret_cast<const int2 *>(&SF(S_THR_N));
+    const int2 thrF = *reinterpret_cast<const int2 *>(&SF(S_THR_F));
+    const int2 thrG = *reinterpret_cast<const int2 *>(&SF(S_THR_G));
+    const int myN = g.dir ? thrN.y : thrN.x, myF = g.dir ? thrF.y : thrF.x;
+    const bool rec_ok = SF(S_RECOK) != 0.0;
     unsigned live[NL];
     #pragma unroll
-    for (int l = 0; l < NL; ++l) live[l] = half > 0 ? 3u : 0u;
-    int base_up = 0, base_dn = 0;
+    for (int l = 0; l < NL; ++l) live[l] = g.half > 0 ? 3u : 0u;
     double U0 = 0, R = 0, rho = 0;  // Gaussian recurrence state of this lane
-    int rec_cfg = -1;               // lane->pixel mapping the state belongs to: 0 both, 1 up only, 2 down only
-    for (;;) {
+    bool rec_valid = false;
+    for (int base = 0;; base += 16) {
         unsigned any = 0;
         #pragma unroll
         for (int l = 0; l < NL; ++l) any |= live[l];
         if (!any) break;
-        const bool both = any == 3u;
-        const int dir = both ? (lane >> 4) : (int) (any >> 1);
-        const int sub = both ? (lane & 15) : lane;
-        const int npx = both ? 16 : 32;
-        const int o = (dir ? base_dn : base_up) + sub;  // outward pixel index
-        const bool mine = o < half;
-        const int z = dir ? zmax - 1 - o : zmax + o;
-        int j = dir ? j0 - 1 - o : j0 + o;  // z mod nbins: |z - zmax| <= nbins/2
+        const int o = base + g.sub;  // outward pixel index
+        const bool mine = o < g.half;
+        const int dz = g.dir ? -1 - o : o;  // z - zmax
+        int j = g.j0 + dz;                  // z mod nbins: |z - zmax| <= nbins/2
         j += j < 0 ? nbins : (j >= nbins ? -nbins : 0);
-        // lanes of my direction below me, lanes of the upward / downward run
-        const unsigned grp_lt = both ? (lt_mask & (dir ? 0xffff0000u : 0x0000ffffu)) : lt_mask;
-        const unsigned up_lanes = both ? 0x0000ffffu : (dir ? 0u : kFull);
-        const unsigned dn_lanes = both ? 0xffff0000u : (dir ? kFull : 0u);
-        unsigned lmask = 0;  // lines with a live run among the directions of this step
+        unsigned lmask = 0;  // lines with a live run
         #pragma unroll
-        for (int l = 0; l < NL; ++l) lmask |= (live[l] & (both ? 3u : (1u << dir))) ? (1u << l) : 0u;
+        for (int l = 0; l < NL; ++l) lmask |= live[l] ? (1u << l) : 0u;
         // start the read of the output pixels now; they are consumed after the quadrature
         double cur[NL];
         #pragma unroll
         for (int l = 0; l < NL; ++l) {
             cur[l] = 0;
-            if (mine && ((live[l] >> dir) & 1u)) cur[l] = row0[l * line_stride + j];
+            if (mine && ((live[l] >> g.dir) & 1u)) cur[l] = row0[l * line_stride + j];
         }
-        double t[NL];
-        int ninner = 1;
-        if (EXACT || any_sub) {
-            const double vlow = __dsub_rn(__dmul_rn((double) z, bintov), vel);
-            const double vhigh_px = __dadd_rn(vlow, bintov);
-            rec_cfg = -1;
-            if (COUNT) ++tally.route[4];
-            #pragma unroll
-            for (int l = 0; l < NL; ++l) {
-                t[l] = 0;
-                if (mine && ((lmask >> l) & 1u)) t[l] = LF(l, L_CD) * pixel_sum_slow<EXACT>(vlow, vhigh_px, sl, l, tab, ninner);
-            }
-        } else {
-            // node 0 of pixel z in units of btherm: affine in the pixel offset from zmax (the reference's
-            // (vlow + vhigh)/2 differs from this by rounding only, < 1e-13 in x)
-            const double xb = fma((double) (z - zmax), -pix, xb0);
-            const double x1 = xb + step, x7 = fma(7.0, step, xb);  // x1 <= x7
-            // The table covers |x| < 24 and the wing series |x| >= 16: a pixel may take the table route
-            // if all its nodes are inside 24, the series route if all are outside 16.  Lane class:
-            // 0 table, 1 series, 2 neither (nodes on both sides of the overlap), 3 idle.
-            const bool near_ok = x1 > -FSB_GTAB_XMAX && x7 < FSB_GTAB_XMAX;
-            const bool far_ok = x1 >= kFarXMin || x7 <= -kFarXMin;
-            const bool core = mine && !(x1 >= xu || x7 <= -xu);  // within reach of the Gaussian
-            const unsigned m = __reduce_or_sync(kFull, ((mine && !near_ok) ? 1u : 0u) | ((mine && !far_ok) ? 2u : 0u) | (core ? 4u : 0u));
-            int lc;
-            unsigned cls;
-            if (!(m & 1u)) {  // every lane can use the table
-                lc = 0;
-                cls = 1u;
-            } else if (!(m & 2u)) {  // every lane can use the series
-                lc = 1;
-                cls = 2u;
-            } else {
-                lc = !mine ? 3 : (far_ok ? 1 : (near_ok ? 0 : 2));
-                cls = __reduce_or_sync(kFull, 1u << lc);
-            }
-            if (m & 4u) cls |= 16u;
-            double tot[NL];
-            #pragma unroll
-            for (int l = 0; l < NL; ++l) tot[l] = 0;
-            const bool pure_near = !(cls & 6u);
+        // node 0 of pixel z in units of btherm: affine in the pixel offset from zmax (the reference's
+        // (vlow + vhigh)/2 differs from this by rounding only, < 1e-13 in x)
+        const double xb = fma((double) dz, -pix, xb0);
+        // warp-uniform route from the thresholds of the live directions
+        const int last = min(base + 16, g.half);
+        bool all_near = true, all_far = true, gauss = false;
+        if (any & 1u) {
+            all_near = all_near && last <= thrN.x;
+            all_far = all_far && base >= thrF.x;
+            gauss = gauss || base < thrG.x;
+        }
+        if (any & 2u) {
+            all_near = all_near && last <= thrN.y;
+            all_far = all_far && base >= thrF.y;
+            gauss = gauss || base < thrG.y;
+        }
+        double tot[NL];
+        #pragma unroll
+        for (int l = 0; l < NL; ++l) tot[l] = 0;
+        if (all_far) {
             if (F32) {
                 float tf[NL];
-                const float xbf = (float) xb, stepf = FS(F_STEP);
-                if (cls & 1u) {
-                    if (COUNT) ++tally.route[(cls & 16u) ? 0 : 1];
-                    node_sum_near32<NL>(xbf, stepf, fl, tab32, (cls & 16u) != 0, lmask, tf);
-                    #pragma unroll
-                    for (int l = 0; l < NL; ++l) tot[l] = (double) tf[l];
-                }
-                if (cls & 2u) {
-                    node_sum_far32<NL>(xbf, stepf, fl, lmask, tf);
-                    #pragma unroll
-                    for (int l = 0; l < NL; ++l) tot[l] = lc == 1 ? (double) tf[l] : tot[l];
-                    if (COUNT) ++tally.route[2];
-                }
+                node_sum_far32<NL>((float) xb, FS(F_STEP), fl, lmask, tf);
+                #pragma unroll
+                for (int l = 0; l < NL; ++l) tot[l] = (double) tf[l];
             } else {
-            if (cls & 1u) {
-                if (cls & 16u) {
-                    const int cfg = both ? 0 : 1 + dir;
-                    if (rec_cfg == cfg) {
-                        // one march step outward: x -> x + Delta, Delta = -+ npx pixels
+                node_sum_far<NL>(xb, step, sl, lmask, tot);
+            }
+            rec_valid = false;
+            if (COUNT) ++tally.route[2];
+        } else if (all_near) {
+            if (F32) {
+                float tf[NL];
+                node_sum_near32<NL>((float) xb, FS(F_STEP), fl, tab32, gauss, lmask, tf);
+                #pragma unroll
+                for (int l = 0; l < NL; ++l) tot[l] = (double) tf[l];
+            } else {
+                if (gauss) {
+                    if (rec_valid) {  // one march step outward: x -> x -+ 16 pixels
                         U0 *= rho;
-                        rho *= both ? SF(S_K16) : SF(S_K32);
-                        R *= both ? (dir ? SF(S_LD16) : SF(S_LU16)) : (dir ? SF(S_LD32) : SF(S_LU32));
+                        rho *= SF(S_K16);
+                        R *= g.dir ? SF(S_LD16) : SF(S_LU16);
                     } else {
+                        const double x1 = xb + step;
                         U0 = exp(-x1 * x1);
                         R = exp(-fma(2.0, x1, step) * step);
-                        if (npx <= recmax) {
-                            const double delta = (dir ? (double) npx : (double) -npx) * pix;
+                        if (rec_ok) {
+                            const double delta = (g.dir ? 16.0 : -16.0) * pix;
                             rho = exp(-fma(2.0, x1, delta) * delta);
                         }
+                        rec_valid = rec_ok;
                     }
-                    rec_cfg = (npx <= recmax && pure_near) ? cfg : -1;
-                    if (COUNT) ++tally.route[0];
                 } else {
-                    U0 = 0;
-                    R = 0;
-                    rec_cfg = -1;
-                    if (COUNT) ++tally.route[1];
+                    rec_valid = false;
                 }
-                node_sum_near<NL>(xb, step, sl, tab, U0, R, (cls & 16u) != 0, lmask, tot);
-            } else {
-                rec_cfg = -1;
+                node_sum_near<NL>(xb, step, sl, tab, U0, R, gauss, lmask, tot);
+            }
+            if (COUNT) ++tally.route[gauss ? 0 : 1];
+        } else {
+            // transition step: lanes differ.  Lane class: 0 table, 1 series, 2 neither (own nodes on both
+            // sides of the overlap: node by node), 3 idle.
+            const bool on_any = mine && ((any >> g.dir) & 1u);
+            const int lc = !on_any ? 3 : (o >= myF ? 1 : (o < myN ? 0 : 2));
+            const unsigned cls = __reduce_or_sync(kFull, 1u << lc);
+            rec_valid = false;
+            if (cls & 1u) {
+                if (F32) {
+                    float tf[NL];
+                    node_sum_near32<NL>((float) xb, FS(F_STEP), fl, tab32, gauss, lmask, tf);
+                    #pragma unroll
+                    for (int l = 0; l < NL; ++l) tot[l] = (double) tf[l];
+                } else {
+                    if (gauss) {
+                        const double x1 = xb + step;
+                        U0 = exp(-x1 * x1);
+                        R = exp(-fma(2.0, x1, step) * step);
+                    }
+                    node_sum_near<NL>(xb, step, sl, tab, U0, R, gauss, lmask, tot);
+                }
             }
             if (cls & 2u) {
                 double tfar[NL];
-                node_sum_far<NL>(xb, step, sl, lmask, tfar);
+                if (F32) {
+                    float tf[NL];
+                    node_sum_far32<NL>((float) xb, FS(F_STEP), fl, lmask, tf);
+                    #pragma unroll
+                    for (int l = 0; l < NL; ++l) tfar[l] = (double) tf[l];
+                } else {
+                    node_sum_far<NL>(xb, step, sl, lmask, tfar);
+                }
                 #pragma unroll
                 for (int l = 0; l < NL; ++l) tot[l] = lc == 1 ? tfar[l] : tot[l];
-                if (COUNT) ++tally.route[2];
             }
-            }
-            if (cls & 4u) {  // lanes whose own nodes straddle |x| = 16: node by node
+            if (cls & 4u) {
                 if (lc == 2) {
                     #pragma unroll
                     for (int l = 0; l < NL; ++l)
                         if ((lmask >> l) & 1u) tot[l] = node_sum_generic((SF(S_XOFF) - xb) / SF(S_INVB), sl, l, tab);
                 }
-                if (COUNT) ++tally.route[3];
             }
-            #pragma unroll
-            for (int l = 0; l < NL; ++l) t[l] = LF(l, L_CD) * tot[l];
+            if (COUNT) ++tally.route[3];
         }
-        // add, then stop each run at its first pixel below tautail (absorption.cpp:260-263,274-277)
-        const bool up_done = base_up + npx >= half, dn_done = base_dn + npx >= half;
+        double t[NL];
         #pragma unroll
-        for (int l = 0; l < NL; ++l) {
-            const bool on = mine && ((live[l] >> dir) & 1u);
-            const unsigned stop = __ballot_sync(kFull, on && (t[l] < tautail));
-            if (on && !(stop & grp_lt)) {  // no lane of my run below me has stopped
-                row0[l * line_stride + j] = cur[l] + t[l];
-                if (COUNT) {
-                    ++tally.pix;
-                    tally.inner += ninner;
-                }
-            }
-            if ((stop & up_lanes) || (up_lanes && up_done)) live[l] &= ~1u;
-            if ((stop & dn_lanes) || (dn_lanes && dn_done)) live[l] &= ~2u;
-        }
-        base_up += up_lanes ? npx : 0;
-        base_dn += dn_lanes ? npx : 0;
-        if (COUNT) ++tally.iter;
-        __syncwarp();
+        for (int l = 0; l < NL; ++l) t[l] = LF(l, L_CD) * tot[l];
+        march_commit<NL, COUNT>(g, t, cur, live, mine, base, j, 1, row0, line_stride, tautail, tally);
     }
 }
 
-template <int NL, bool COUNT>
-__device__ __noinline__ void march_exact(const double *__restrict__ sl, const double *__restrict__ tab, double *__restrict__ row0,
-                                         int64_t line_stride, int nbins, double bintov, double tautail, int lane, Tally &tally)
+// Slow routes: the exact Faddeeva restatement, and pixels wider than btherm/2 (sub-sampling rule of
+// singleabs.h:110-125).  Same lane layout, per-pixel evaluation through pixel_sum_slow.
+template <int NL, bool EXACT, bool COUNT>
+__device__ __noinline__ void march_slow(const double *__restrict__ sl, const double *__restrict__ tab, double *__restrict__ row0,
+                                        int64_t line_stride, int nbins, double bintov, double tautail, int lane, Tally &tally)
 {
-    march<NL, true, COUNT, false>(sl, nullptr, tab, nullptr, row0, line_stride, nbins, bintov, tautail, lane, tally);
+    const MarchGeom g = march_geom(lane, nbins, (int) SF(S_ZMAX));
+    const double vel = SF(S_VEL);
+    unsigned live[NL];
+    #pragma unroll
+    for (int l = 0; l < NL; ++l) live[l] = g.half > 0 ? 3u : 0u;
+    for (int base = 0;; base += 16) {
+        unsigned any = 0;
+        #pragma unroll
+        for (int l = 0; l < NL; ++l) any |= live[l];
+        if (!any) break;
+        const int o = base + g.sub;
+        const bool mine = o < g.half;
+        const int dz = g.dir ? -1 - o : o;
+        const int z = g.zmax + dz;
+        int j = g.j0 + dz;
+        j += j < 0 ? nbins : (j >= nbins ? -nbins : 0);
+        double cur[NL], t[NL];
+        int ninner = 1;
+        const double vlow = __dsub_rn(__dmul_rn((double) z, bintov), vel);
+        const double vhigh_px = __dadd_rn(vlow, bintov);
+        #pragma unroll
+        for (int l = 0; l < NL; ++l) {
+            const bool on = mine && ((live[l] >> g.dir) & 1u);
+            cur[l] = on ? row0[l * line_stride + j] : 0.0;
+            t[l] = on ? LF(l, L_CD) * pixel_sum_slow<EXACT>(vlow, vhigh_px, sl, l, tab, ninner) : 0.0;
+        }
+        if (COUNT) ++tally.route[4];
+        march_commit<NL, COUNT>(g, t, cur, live, mine, base, j, ninner, row0, line_stride, tautail, tally);
+    }
 }
 
+__device__ __forceinline__ int clamp_index(double v) { return (int) fmin(fmax(v, 0.0), 1073741824.0); }
+
 // Per-particle constants, one particle per lane (absorption.cpp:218-246, singleabs.h:81-90).
-template <int KERNEL, int NL>
+template <int KERNEL, int NL, bool F32>
 __device__ __noinline__ void setup_particle(const InterpConsts &C, double *__restrict__ sl, float *__restrict__ fl, int64_t k, int ax,
                                                const int32_t *__restrict__ particle, const double *__restrict__ dr2s,
                                                const float *__restrict__ pos, const float *__restrict__ vel,
@@ -569,9 +621,9 @@ __device__ __noinline__ void setup_particle(const InterpConsts &C, double *__res
         const double vv = i * deltav - vhigh;
         kw[i - 1] = sph_kernel<KERNEL>(sqrt(vdr2 + vv * vv) / vsmooth) * deltav;
         SF(S_KW0 + i - 1) = kw[i - 1];
-        FS(F_KW0 + i - 1) = (float) kw[i - 1];
+        if (F32) FS(F_KW0 + i - 1) = (float) kw[i - 1];
     }
-    FS(F_STEP) = (float) step;
+    if (F32) FS(F_STEP) = (float) step;
     // moments of the node weights about xb, in units of btherm: M_n = sum kw_i (i step)^n
     double M[5] = {0, 0, 0, 0, 0};
     #pragma unroll
@@ -586,19 +638,17 @@ __device__ __noinline__ void setup_particle(const InterpConsts &C, double *__res
     }
     const double zmaxd = floor(velp / C.bintov);
     SF(S_ZMAX) = zmaxd;
-    SF(S_XB0) = fma(-(fma(zmaxd + 0.5, C.bintov, -velp)), inv_b, -vhigh * inv_b);
-    SF(S_PIX) = C.bintov * inv_b;
-    // march-step recurrence factors: D = npx pixels in units of btherm
+    const double xb0 = fma(-(fma(zmaxd + 0.5, C.bintov, -velp)), inv_b, -vhigh * inv_b);
     const double pix = C.bintov * inv_b;
-    const double D16 = 16.0 * pix, D32 = 32.0 * pix;
+    SF(S_XB0) = xb0;
+    SF(S_PIX) = pix;
+    // march-step recurrence factors: D = 16 pixels in units of btherm
+    const double D16 = 16.0 * pix;
     SF(S_K16) = exp(-2.0 * D16 * D16);
-    SF(S_K32) = exp(-2.0 * D32 * D32);
     SF(S_LU16) = exp(2.0 * D16 * step);
-    SF(S_LU32) = exp(2.0 * D32 * step);
     SF(S_LD16) = exp(-2.0 * D16 * step);
-    SF(S_LD32) = exp(-2.0 * D32 * step);
     // every factor stays within e^+-500 while a lane is within reach of the Gaussian core
-    SF(S_RECMAX) = (step <= 1.0 && D32 <= 10.0) ? 32.0 : ((step <= 1.0 && D16 <= 10.0) ? 16.0 : 0.0);
+    SF(S_RECOK) = (step <= 1.0 && D16 <= 10.0) ? 1.0 : 0.0;
     double ymin = 1e300;
     #pragma unroll
     for (int l = 0; l < NL; ++l) {
@@ -622,14 +672,16 @@ __device__ __noinline__ void setup_particle(const InterpConsts &C, double *__res
         LF(l, L_BQ0 + 2) = fma(6.0 * fc.b[2], M[2], fc.b[1] * M[0]);
         LF(l, L_BQ0 + 3) = 4.0 * fc.b[2] * M[1];
         LF(l, L_BQ0 + 4) = fc.b[2] * M[0];
-        #pragma unroll
-        for (int i = 0; i < 3; ++i) FLF(l, FL_A0 + i) = (float) fc.a[i];
-        #pragma unroll
-        for (int i = 0; i < 3; ++i) FLF(l, FL_PE0 + i) = (float) fc.pe[i];
-        #pragma unroll
-        for (int i = 0; i < 5; ++i) FLF(l, FL_BQ0 + i) = (float) LF(l, L_BQ0 + i);
-        FLF(l, FL_Y2) = (float) (aa * aa);
-        FLF(l, FL_YISP) = (float) (aa * 0.56418958354775628694807945156);
+        if (F32) {
+            #pragma unroll
+            for (int i = 0; i < 3; ++i) FLF(l, FL_A0 + i) = (float) fc.a[i];
+            #pragma unroll
+            for (int i = 0; i < 3; ++i) FLF(l, FL_PE0 + i) = (float) fc.pe[i];
+            #pragma unroll
+            for (int i = 0; i < 5; ++i) FLF(l, FL_BQ0 + i) = (float) LF(l, L_BQ0 + i);
+            FLF(l, FL_Y2) = (float) (aa * aa);
+            FLF(l, FL_YISP) = (float) (aa * 0.56418958354775628694807945156);
+        }
     }
     if (mode == 2) {
         #pragma unroll
@@ -637,14 +689,36 @@ __device__ __noinline__ void setup_particle(const InterpConsts &C, double *__res
     }
     const double xu2 = ymin > 0 ? 37.0 - log(ymin) : 1e300;
     SF(S_XU2) = xu2;
-    SF(S_XU) = sqrt(xu2);
+    // pixels at least btherm/2 wide are sub-sampled (singleabs.h:110-125; bintov is rounded differently per
+    // pixel by at most an ulp): generic per-pixel route
+    if (mode == 1 && !(C.bintov * (1 + 1e-12) < btherm / 2.)) mode = 3;
     SF(S_MODE) = (double) mode;
+    // Route thresholds in outward pixels.  Upward run: nodes x_i(o) = X_i - o pix; downward run:
+    // x_i(o) = X_i + (1 + o) pix; X_1 = xb0 + step <= X_7 = xb0 + 7 step.  The table covers |x| < 24 and the
+    // wing series |x| >= 16; margins of 0.01 dwarf the rounding of these expressions.
+    {
+        const double X1 = xb0 + step, X7 = fma(7.0, step, xb0), ipix = 1.0 / pix;
+        const double lim_n = FSB_GTAB_XMAX - 0.01, lim_f = kFarXMin + 0.01, xu = sqrt(fmin(xu2, 1e12));
+        const bool near_any = X7 < lim_n && X1 > -lim_n;
+        int2 tn, tf, tg;
+        tn.x = near_any ? clamp_index(floor((X1 + lim_n) * ipix)) : 0;
+        tn.y = near_any ? clamp_index(floor((lim_n - X7) * ipix - 1.0)) : 0;
+        tf.x = clamp_index(ceil((X7 + lim_f) * ipix));
+        tf.y = clamp_index(ceil((lim_f - X1) * ipix - 1.0));
+        tg.x = clamp_index(ceil((X7 + xu) * ipix));
+        tg.y = clamp_index(ceil((xu - X1) * ipix - 1.0));
+        *reinterpret_cast<int2 *>(&SF(S_THR_N)) = tn;
+        *reinterpret_cast<int2 *>(&SF(S_THR_F)) = tf;
+        *reinterpret_cast<int2 *>(&SF(S_THR_G)) = tg;
+    }
 }
 
-template <int NL> constexpr size_t tau_smem_bytes()
+// The FP32 tables and float slabs exist only in the FP32 instantiation (they would cost the FP64 kernel a
+// resident CTA per SM).
+template <int NL, bool F32> constexpr size_t tau_smem_bytes()
 {
     return sizeof(double) * (size_t) (FSB_GTAB_SIZE + kTauWarps * SlabSize<NL>::kDoubles) +
-           sizeof(float) * (size_t) (4 * FSB_GTAB_NINT + kTauWarps * FSlabSize<NL>::kFloats);
+           (F32 ? sizeof(float) * (size_t) (4 * FSB_GTAB_NINT + kTauWarps * FSlabSize<NL>::kFloats) : 0);
 }
 
 template <int KERNEL, int NL, bool COUNT, bool F32>
@@ -664,7 +738,7 @@ k_tau(InterpConsts C, Items items, int n_items, int *__restrict__ next_item, con
     static_assert((FSB_GTAB_SIZE + kTauWarps * SlabSize<NL>::kDoubles) % 2 == 0, "float4 table must stay 16-byte aligned");
     float *tab32f = reinterpret_cast<float *>(smem + FSB_GTAB_SIZE + kTauWarps * SlabSize<NL>::kDoubles);
     const float4 *tab32 = reinterpret_cast<const float4 *>(tab32f);
-    float *fslab = tab32f + 4 * FSB_GTAB_NINT + warp * FSlabSize<NL>::kFloats;
+    float *fslab = F32 ? tab32f + 4 * FSB_GTAB_NINT + warp * FSlabSize<NL>::kFloats : nullptr;
     for (int i = threadIdx.x; i < FSB_GTAB_SIZE; i += kTauThreads) tab[i] = d_gtable[i];
     if (F32)
         for (int i = threadIdx.x; i < 4 * FSB_GTAB_NINT; i += kTauThreads) tab32f[i] = d_gtable32[i];
@@ -691,14 +765,16 @@ k_tau(InterpConsts C, Items items, int n_items, int *__restrict__ next_item, con
         for (int64_t k0 = kbeg; k0 < kend; k0 += kBatch) {
             const int nb = (int) min((int64_t) kBatch, kend - k0);
             __syncwarp();
-            if (lane < nb) setup_particle<KERNEL, NL>(C, slab + lane, fslab + lane, k0 + lane, ax, particle, dr2s, pos, vel, dens, temp, hsml, cells);
+            if (lane < nb) setup_particle<KERNEL, NL, F32>(C, slab + lane, fslab + lane, k0 + lane, ax, particle, dr2s, pos, vel, dens, temp, hsml, cells);
             __syncwarp();
             for (int b = 0; b < nb; ++b) {
                 const double *sl = slab + b;
                 const int mode = (int) SF(S_MODE);
                 if (mode == 0) continue;
-                if (mode == 2) march_exact<NL, COUNT>(sl, tab, row0, line_stride, nbins, C.bintov, C.tautail, lane, tally);
-                else march<NL, false, COUNT, F32>(sl, fslab + b, tab, tab32, row0, line_stride, nbins, C.bintov, C.tautail, lane, tally);
+                if (mode == 1) march_fast<NL, COUNT, F32>(sl, fslab + b, tab, tab32, row0, line_stride, nbins, C.tautail, lane, tally);
+                else if (mode == 2) march_slow<NL, true, COUNT>(sl, tab, row0, line_stride, nbins, C.bintov, C.tautail, lane, tally);
+                else march_slow<NL, false, COUNT>(sl, tab, row0, line_stride, nbins, C.bintov, C.tautail, lane, tally);
+                __syncwarp();
             }
         }
     }
@@ -748,9 +824,8 @@ int launch_tau_k(const fsb_index *idx, const InterpConsts &c, const ItemPlan &pl
     int dev = 0, sms = 0, per_sm = 0;
     FSB_CUDA_TRY(cudaGetDevice(&dev));
     FSB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const size_t smem = tau_smem_bytes<NL>();
     const int n_items = (int) plan.n_items;
-    auto go = [&](auto kern) -> int {
+    auto go = [&](auto kern, size_t smem) -> int {
         FSB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
         FSB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTauThreads, smem));
         const int grid = std::max(1, std::min((n_items + kTauWarps - 1) / kTauWarps, sms * std::max(per_sm, 1)));
@@ -761,8 +836,10 @@ int launch_tau_k(const fsb_index *idx, const InterpConsts &c, const ItemPlan &pl
         FSB_CUDA_TRY(cudaGetLastError());
         return FSB_OK;
     };
-    if (precision == FSB_PRECISION_FP32) return ctr ? go(k_tau<KERNEL, NL, true, true>) : go(k_tau<KERNEL, NL, false, true>);
-    return ctr ? go(k_tau<KERNEL, NL, true, false>) : go(k_tau<KERNEL, NL, false, false>);
+    constexpr size_t smem64 = tau_smem_bytes<NL, false>(), smem32 = tau_smem_bytes<NL, true>();
+    if (precision == FSB_PRECISION_FP32)
+        return ctr ? go(k_tau<KERNEL, NL, true, true>, smem32) : go(k_tau<KERNEL, NL, false, true>, smem32);
+    return ctr ? go(k_tau<KERNEL, NL, true, false>, smem64) : go(k_tau<KERNEL, NL, false, false>, smem64);
 }
 
 template <int NL>
