@@ -44,49 +44,63 @@ constexpr int kTauThreads = 32 * kTauWarps;
 constexpr int kBatch = FSB_TAU_BATCH;  // particles per slab refill (one lane each), <= 32
 constexpr int kMaxTauLines = 2;
 
-// ---- slab layout: [field][kBatch] doubles per warp --------------------------------------------------
+// ---- slab layout: one record of doubles per particle, kBatch records per warp ------------------------
+// The march is bound by shared-memory wavefronts, so fields that are read together sit in 16-byte pairs
+// (even index first) and are fetched with one 128-bit broadcast load.
 enum SharedField {
-    S_VEL = 0,   // velfac*pos + pvel                                  absorption.cpp:234
-    S_INVB,      // 1/btherm
-    S_HALFB,     // btherm/2: sub-sampling threshold                    singleabs.h:110
-    S_STEP,      // node spacing in units of btherm: (2 vhigh/8)/btherm
-    S_XOFF,      // -vhigh/btherm
-    S_Q,         // exp(-2 step^2): second-order ratio of the Gaussian recurrence across nodes
-    S_KW0,       // 7 kernel weights x deltav                           singleabs.h:152-163
-    S_XU2 = S_KW0 + 7,  // x^2 beyond which exp(-x^2) is negligible against the damping wing
-    S_ZMAX,      // floor(vel/bintov)
-    S_MODE,      // 0 skip, 1 fast, 2 exact
-    S_K16,       // exp(-2 D^2), D = 16 pixels in units of btherm: march-step recurrence of the Gaussian
-    S_LU16,      // exp(+2 D step): ratio update of the inter-node factor, upward march
-    S_LD16,      // exp(-2 D step): downward march
-    S_RECOK,     // 1 when the march-step recurrence is safe (all factors within e^+-500)
+    S_STEP = 0,  // node spacing in units of btherm: (2 vhigh/8)/btherm
     S_XB0,       // xb of the centre of pixel zmax: -vhigh/b - ((zmax + 1/2) bintov - vel)/b
     S_PIX,       // pixel width in units of btherm
+    S_ZMAX,      // int2 {zmax = floor(vel/bintov), zmax mod nbins}
     S_THR_N,     // int2 {up, down}: outward pixels o < N have all nodes inside the table (|x| < 24)
     S_THR_F,     // int2: outward pixels o >= F have all nodes on the wing series (|x| >= 16)
     S_THR_G,     // int2: outward pixels o >= G are out of reach of the Gaussian
+    S_RECOK,     // 1 when the march-step recurrence is safe (all factors within e^+-500)
+    S_Q,         // exp(-2 step^2): second-order ratio of the Gaussian recurrence across nodes
+    S_K16,       // exp(-2 D^2), D = 16 pixels in units of btherm: march-step recurrence of the Gaussian
+    S_LU16,      // exp(+2 D step): ratio update of the inter-node factor, upward march
+    S_LD16,      // exp(-2 D step): downward march
+    S_KW0,       // 7 kernel weights x deltav                           singleabs.h:152-163
+    S_MODE = S_KW0 + 7,  // 0 skip, 1 fast, 2 exact, 3 sub-sampled pixels
+    S_VEL,       // velfac*pos + pvel                                  absorption.cpp:234
+    S_INVB,      // 1/btherm
+    S_HALFB,     // btherm/2: sub-sampling threshold                    singleabs.h:110
+    S_XOFF,      // -vhigh/btherm
+    S_XU2,       // x^2 beyond which exp(-x^2) is negligible against the damping wing
+    S_PAD,
     S_COUNT
 };
 enum LineField {
-    L_CD = 0,    // amp*dens/velfac
+    L_A0 = 0,    // A(s): 4 coefficients
+    L_PE0 = 4,   // Pe(s): 4 coefficients (exact mode: L_PE0 holds erfcx(aa))
+    L_BQ0 = 8,   // sum_i kw_i B(s_i) as a quartic in xb: 5 coefficients
+    L_CD = 13,   // amp*dens/velfac
     L_Y,         // aa = voigt_fac/btherm
-    L_PE0,       // Pe(s): 4 coefficients (exact mode: L_PE0 holds erfcx(aa))
-    L_A0 = L_PE0 + 4,
-    L_BQ0 = L_A0 + 4,   // sum_i kw_i B(s_i) as a quartic in xb: 5 coefficients
-    L_B0 = L_BQ0 + 5,   // B(s): 3 raw coefficients (generic route)
+    L_B0,        // B(s): 3 raw coefficients (generic route)
     L_COUNT = L_B0 + 3
 };
-template <int NL> struct SlabSize { static constexpr int kDoubles = (S_COUNT + NL * L_COUNT) * kBatch; };
+static_assert(S_COUNT % 2 == 0 && L_COUNT % 2 == 0 && S_KW0 % 2 == 0 && S_Q % 2 == 0 && S_LU16 % 2 == 0, "16-byte field pairs");
+template <int NL> struct SlabSize {
+    static constexpr int kFields = S_COUNT + NL * L_COUNT;
+    // record stride in doubles: an odd number of 16-byte units, so the 16 setup lanes spread over the banks
+    static constexpr int kStride = (kFields / 2) % 2 ? kFields : kFields + 2;
+    static constexpr int kDoubles = kStride * kBatch;
+};
 
-// FP32 fast path: float copies of the node constants, [field][kBatch] floats per warp after the doubles
+// FP32 fast path: float copies of the node constants, one record of floats per particle after the doubles
 enum FShared { F_STEP = 0, F_KW0, F_COUNT = F_KW0 + 7 };
 enum FLineField { FL_A0 = 0, FL_PE0 = 3, FL_BQ0 = 6, FL_Y2 = 11, FL_YISP, FL_COUNT };
-template <int NL> struct FSlabSize { static constexpr int kFloats = (F_COUNT + NL * FL_COUNT) * kBatch; };
-#define FS(f) fl[(f) * kBatch]
-#define FLF(l, f) fl[(F_COUNT + (l) * FL_COUNT + (f)) * kBatch]
+template <int NL> struct FSlabSize {
+    static constexpr int kStride = F_COUNT + NL * FL_COUNT;
+    static constexpr int kFloats = kStride * kBatch;
+};
+#define FS(f) fl[(f)]
+#define FLF(l, f) fl[F_COUNT + (l) * FL_COUNT + (f)]
 
-#define SF(f) sl[(f) * kBatch]
-#define LF(l, f) sl[(S_COUNT + (l) * L_COUNT + (f)) * kBatch]
+#define SF(f) sl[(f)]
+#define LF(l, f) sl[S_COUNT + (l) * L_COUNT + (f)]
+#define SF2(f) (*reinterpret_cast<const double2 *>(sl + (f)))
+#define LF2(l, f) (*reinterpret_cast<const double2 *>(sl + S_COUNT + (l) * L_COUNT + (f)))
 
 // ---- node sums ------------------------------------------------------------------------------------
 // All return sum_i kw_i H(x_i, y_l) for x_i = xb + (i+1) step, per fused line l.
@@ -98,14 +112,14 @@ template <int NL> struct FSlabSize { static constexpr int kFloats = (F_COUNT + N
 // finite garbage that the caller discards.
 template <int NL>
 __device__ __forceinline__ void node_sum_near(double xb, double step, const double *__restrict__ sl,
-                                              const double *__restrict__ tab, double U0, double R, bool gauss,
+                                              const double *__restrict__ tab, double U0, double R, double q, bool gauss,
                                               unsigned lmask, double (&tot)[NL])
 {
-    static_assert(FSB_GTAB_DEG == 7, "node_sum_near is written for a degree-7 table");
+    static_assert(FSB_GTAB_DEG == 7 && FSB_GTAB_STRIDE == 6, "node_sum_near is written for the 48-byte degree-7 table");
     double t[7], g[7];
+    const double2 *base[7];
     {
-        double2 c[7];
-        const double2 *base[7];
+        double2 v0[7], v1[7], v2[7];
         #pragma unroll
         for (int i = 0; i < 7; ++i) {
             int k;
@@ -114,54 +128,91 @@ __device__ __forceinline__ void node_sum_near(double xb, double step, const doub
             base[i] = reinterpret_cast<const double2 *>(tab + k * FSB_GTAB_STRIDE);
         }
         #pragma unroll
-        for (int i = 0; i < 7; ++i) c[i] = base[i][3];
+        for (int i = 0; i < 7; ++i) v2[i] = base[i][2];
         #pragma unroll
-        for (int i = 0; i < 7; ++i) g[i] = fma(c[i].y, t[i], c[i].x);
+        for (int i = 0; i < 7; ++i) v1[i] = base[i][1];
         #pragma unroll
-        for (int j = 2; j >= 0; --j) {
-            #pragma unroll
-            for (int i = 0; i < 7; ++i) c[i] = base[i][j];
-            #pragma unroll
-            for (int i = 0; i < 7; ++i) g[i] = fma(g[i], t[i], c[i].y);
-            #pragma unroll
-            for (int i = 0; i < 7; ++i) g[i] = fma(g[i], t[i], c[i].x);
-        }
+        for (int i = 0; i < 7; ++i) v0[i] = base[i][0];
+        #pragma unroll
+        for (int i = 0; i < 7; ++i) g[i] = g_poly(v0[i], v1[i], v2[i], t[i]);
     }
+#ifdef FSB_EXP_DBLLOAD
+    {   // timing experiment only: repeat the 21 table loads (results feed an impossible store)
+        double dummy = 0;
+        #pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            #pragma unroll
+            for (int i = 0; i < 7; ++i) {
+                double a, b;
+                asm volatile("ld.volatile.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"((unsigned) __cvta_generic_to_shared(base[i] + j)));
+                dummy += a + b;
+            }
+        }
+        if (dummy == 1.2345e300) tot[0] = dummy;
+    }
+#endif
     // t[] is reused for s = x^2
     #pragma unroll
     for (int i = 0; i < 7; ++i) {
         const double x = fma((double) (i + 1), step, xb);
         t[i] = x * x;
     }
-    const double q = SF(S_Q);
+    double kw[7];
+    {
+        const double2 k01 = SF2(S_KW0), k23 = SF2(S_KW0 + 2), k45 = SF2(S_KW0 + 4), k6m = SF2(S_KW0 + 6);
+        kw[0] = k01.x, kw[1] = k01.y, kw[2] = k23.x, kw[3] = k23.y, kw[4] = k45.x, kw[5] = k45.y, kw[6] = k6m.x;
+    }
+    // kernel-weighted table values: each line then costs one FMA per node on top of its polynomial A
     #pragma unroll
-    for (int l = 0; l < NL; ++l) {
-        if (NL > 1 && !((lmask >> l) & 1u)) {
-            tot[l] = 0;
-            continue;
-        }
-        const double a0 = LF(l, L_A0), a1 = LF(l, L_A0 + 1), a2 = LF(l, L_A0 + 2), a3 = LF(l, L_A0 + 3);
-        double acc = fma(fma(fma(fma(LF(l, L_BQ0 + 4), xb, LF(l, L_BQ0 + 3)), xb, LF(l, L_BQ0 + 2)), xb, LF(l, L_BQ0 + 1)), xb,
-                         LF(l, L_BQ0));
-        if (gauss) {
-            const double p0 = LF(l, L_PE0), p1 = LF(l, L_PE0 + 1), p2 = LF(l, L_PE0 + 2), p3 = LF(l, L_PE0 + 3);
+    for (int i = 0; i < 7; ++i) g[i] *= kw[i];
+    if (gauss) {
+        // Gaussians of the 7 nodes by the two-term recurrence, shared by the fused lines, also kernel-weighted
+        double uw[7];
+        {
             double u = U0, r = R;
             #pragma unroll
             for (int i = 0; i < 7; ++i) {
-                const double A = fma(fma(fma(a3, t[i], a2), t[i], a1), t[i], a0);
-                const double Pe = fma(fma(fma(p3, t[i], p2), t[i], p1), t[i], p0);
-                acc = fma(fma(u, Pe, g[i] * A), SF(S_KW0 + i), acc);
+                uw[i] = u * kw[i];
                 u *= r;
                 r *= q;
             }
-        } else {  // the Gaussian is negligible for every lane of this step
+        }
+        #pragma unroll
+        for (int l = 0; l < NL; ++l) {
+            if (NL > 1 && !((lmask >> l) & 1u)) {
+                tot[l] = 0;
+                continue;
+            }
+            const double2 a01 = LF2(l, L_A0), a23 = LF2(l, L_A0 + 2), p01 = LF2(l, L_PE0), p23 = LF2(l, L_PE0 + 2);
+            const double2 b01 = LF2(l, L_BQ0), b23 = LF2(l, L_BQ0 + 2);
+            double acc = fma(fma(fma(fma(LF(l, L_BQ0 + 4), xb, b23.y), xb, b23.x), xb, b01.y), xb, b01.x);
+            double acc2 = 0;
             #pragma unroll
             for (int i = 0; i < 7; ++i) {
-                const double A = fma(fma(fma(a3, t[i], a2), t[i], a1), t[i], a0);
-                acc = fma(g[i] * A, SF(S_KW0 + i), acc);
+                const double A = fma(fma(fma(a23.y, t[i], a23.x), t[i], a01.y), t[i], a01.x);
+                const double Pe = fma(fma(fma(p23.y, t[i], p23.x), t[i], p01.y), t[i], p01.x);
+                acc = fma(uw[i], Pe, acc);
+                acc2 = fma(g[i], A, acc2);
             }
+            tot[l] = acc + acc2;
         }
-        tot[l] = acc;
+    } else {  // the Gaussian is negligible for every lane of this step
+        #pragma unroll
+        for (int l = 0; l < NL; ++l) {
+            if (NL > 1 && !((lmask >> l) & 1u)) {
+                tot[l] = 0;
+                continue;
+            }
+            const double2 a01 = LF2(l, L_A0), a23 = LF2(l, L_A0 + 2);
+            const double2 b01 = LF2(l, L_BQ0), b23 = LF2(l, L_BQ0 + 2);
+            double acc = fma(fma(fma(fma(LF(l, L_BQ0 + 4), xb, b23.y), xb, b23.x), xb, b01.y), xb, b01.x);
+            #pragma unroll
+            for (int i = 0; i < 7; ++i) {
+                const double A = fma(fma(fma(a23.y, t[i], a23.x), t[i], a01.y), t[i], a01.x);
+                acc = fma(g[i], A, acc);
+            }
+            tot[l] = acc;
+        }
     }
 }
 
@@ -172,11 +223,15 @@ __device__ __forceinline__ void node_sum_far(double xb, double step, const doubl
                                              double (&tot)[NL])
 {
     const double isp = 0.56418958354775628694807945156;
-    double u[7], p1[7], p3[7], p5[7];
+    double u[7], p1[7], p3[7], p5[7], kw[7];
+    {
+        const double2 k01 = SF2(S_KW0), k23 = SF2(S_KW0 + 2), k45 = SF2(S_KW0 + 4), k6m = SF2(S_KW0 + 6);
+        kw[0] = k01.x, kw[1] = k01.y, kw[2] = k23.x, kw[3] = k23.y, kw[4] = k45.x, kw[5] = k45.y, kw[6] = k6m.x;
+    }
     #pragma unroll
     for (int i = 0; i < 7; ++i) {
         const double x = fma((double) (i + 1), step, xb);
-        u[i] = 1.0 / (x * x);
+        u[i] = fast_rcp(x * x);
     }
     #pragma unroll
     for (int i = 0; i < 7; ++i) far_polys(u[i], p1[i], p3[i], p5[i]);
@@ -191,7 +246,7 @@ __device__ __forceinline__ void node_sum_far(double xb, double step, const doubl
         #pragma unroll
         for (int i = 0; i < 7; ++i) {
             const double v = y2 * u[i];
-            acc = fma(u[i] * fma(v, fma(v, p5[i], -p3[i]), p1[i]), SF(S_KW0 + i), acc);
+            acc = fma(u[i] * fma(v, fma(v, p5[i], -p3[i]), p1[i]), kw[i], acc);
         }
         tot[l] = isp * y * acc;
     }
@@ -343,14 +398,14 @@ struct MarchGeom {
     unsigned grp_lt, up_lanes, dn_lanes;
 };
 
-__device__ __forceinline__ MarchGeom march_geom(int lane, int nbins, int zmax)
+__device__ __forceinline__ MarchGeom march_geom(int lane, int nbins, int2 zj)
 {
     MarchGeom g;
     g.dir = lane >> 4;
     g.sub = lane & 15;
     g.half = nbins / 2;
-    g.zmax = zmax;
-    g.j0 = wrap_bin(zmax, nbins);
+    g.zmax = zj.x;
+    g.j0 = zj.y;
     g.up_lanes = 0x0000ffffu;
     g.dn_lanes = 0xffff0000u;
     g.grp_lt = ((1u << lane) - 1u) & (g.dir ? g.dn_lanes : g.up_lanes);
@@ -384,63 +439,52 @@ __device__ __forceinline__ void march_commit(const MarchGeom &g, const double (&
 // Fast routes.  Which route a step takes follows from integer pixel thresholds computed once per
 // particle (setup_particle): x is affine in the outward pixel index, so "all nodes inside the table",
 // "all nodes on the wing series" and "out of reach of the Gaussian" are index ranges per direction.
+//
+// Control state is kept in a handful of warp-uniform integers so a march step costs few instructions
+// beyond the quadrature: `live` has bit (2 l + d) set while direction d (0 up, 1 down) of line l is going;
+// near_lim / far_beg / gauss_end are the route limits of the directions still live and are refreshed only
+// when a direction ends.
 template <int NL, bool COUNT, bool F32>
 __device__ __forceinline__ void march_fast(const double *__restrict__ sl, const float *__restrict__ fl, const double *__restrict__ tab,
                                            const float4 *__restrict__ tab32, double *__restrict__ row0, int64_t line_stride, int nbins,
                                            double tautail, int lane, Tally &tally)
 {
-    const MarchGeom g = march_geom(lane, nbins, (int) SF(S_ZMAX));
-    const double step = SF(S_STEP), xb0 = SF(S_XB0), pix = SF(S_PIX);
-    const int2 thrN = *reinterpret_cast<const int2 *>(&SF(S_THR_N));
-    const int2 thrF = *reinterpret_cast<const int2 *>(&SF(S_THR_F));
-    const int2 thrG = *reinterpret_cast<const int2 *>(&SF(S_THR_G));
-    const int myN = g.dir ? thrN.y : thrN.x, myF = g.dir ? thrF.y : thrF.x;
-    const bool rec_ok = SF(S_RECOK) != 0.0;
-    unsigned live[NL];
-    #pragma unroll
-    for (int l = 0; l < NL; ++l) live[l] = g.half > 0 ? 3u : 0u;
+    constexpr unsigned kUpBits = NL == 2 ? 0x5u : 0x1u, kDnBits = NL == 2 ? 0xau : 0x2u;
+    const int dir = lane >> 4, sub = lane & 15, half = nbins >> 1;
+    const unsigned grp_lt = ((1u << lane) - 1u) & (dir ? 0xffff0000u : 0x0000ffffu);
+    const double2 sx = SF2(S_STEP), pz = SF2(S_PIX), nf = SF2(S_THR_N), gr = SF2(S_THR_G);
+    const double step = sx.x, xb0 = sx.y, pix = pz.x;
+    const int2 zj = make_int2(__double2loint(pz.y), __double2hiint(pz.y));
+    const int2 thrN = make_int2(__double2loint(nf.x), __double2hiint(nf.x));
+    const int2 thrF = make_int2(__double2loint(nf.y), __double2hiint(nf.y));
+    const int2 thrG = make_int2(__double2loint(gr.x), __double2hiint(gr.x));
+    const bool rec_ok = gr.y != 0.0;
+    unsigned live = half > 0 ? (kUpBits | kDnBits) : 0u;
+    int near_lim = min(thrN.x, thrN.y), far_beg = max(thrF.x, thrF.y), gauss_end = max(thrG.x, thrG.y);
     double U0 = 0, R = 0, rho = 0;  // Gaussian recurrence state of this lane
     bool rec_valid = false;
-    for (int base = 0;; base += 16) {
-        unsigned any = 0;
-        #pragma unroll
-        for (int l = 0; l < NL; ++l) any |= live[l];
-        if (!any) break;
-        const int o = base + g.sub;  // outward pixel index
-        const bool mine = o < g.half;
-        const int dz = g.dir ? -1 - o : o;  // z - zmax
-        int j = g.j0 + dz;                  // z mod nbins: |z - zmax| <= nbins/2
+    for (int base = 0; live; base += 16) {
+        const int o = base + sub;           // outward pixel index
+        const int dz = dir ? ~o : o;        // z - zmax  (~o = -1 - o)
+        int j = zj.y + dz;                  // z mod nbins: |z - zmax| <= nbins/2
         j += j < 0 ? nbins : (j >= nbins ? -nbins : 0);
-        unsigned lmask = 0;  // lines with a live run
-        #pragma unroll
-        for (int l = 0; l < NL; ++l) lmask |= live[l] ? (1u << l) : 0u;
+        const unsigned mybits = o < half ? (live >> dir) & kUpBits : 0u;  // bit 2 l: my run of line l is going
         // start the read of the output pixels now; they are consumed after the quadrature
+        double *const pj = row0 + j;
         double cur[NL];
         #pragma unroll
-        for (int l = 0; l < NL; ++l) {
-            cur[l] = 0;
-            if (mine && ((live[l] >> g.dir) & 1u)) cur[l] = row0[l * line_stride + j];
-        }
+        for (int l = 0; l < NL; ++l) cur[l] = (mybits >> (2 * l)) & 1u ? pj[l * line_stride] : 0.0;
+        unsigned lmask = 0;  // lines with a live run
+        #pragma unroll
+        for (int l = 0; l < NL; ++l) lmask |= (live >> (2 * l)) & 3u ? (1u << l) : 0u;
         // node 0 of pixel z in units of btherm: affine in the pixel offset from zmax (the reference's
         // (vlow + vhigh)/2 differs from this by rounding only, < 1e-13 in x)
         const double xb = fma((double) dz, -pix, xb0);
-        // warp-uniform route from the thresholds of the live directions
-        const int last = min(base + 16, g.half);
-        bool all_near = true, all_far = true, gauss = false;
-        if (any & 1u) {
-            all_near = all_near && last <= thrN.x;
-            all_far = all_far && base >= thrF.x;
-            gauss = gauss || base < thrG.x;
-        }
-        if (any & 2u) {
-            all_near = all_near && last <= thrN.y;
-            all_far = all_far && base >= thrF.y;
-            gauss = gauss || base < thrG.y;
-        }
+        const bool gauss = base < gauss_end;
         double tot[NL];
         #pragma unroll
         for (int l = 0; l < NL; ++l) tot[l] = 0;
-        if (all_far) {
+        if (base >= far_beg) {
             if (F32) {
                 float tf[NL];
                 node_sum_far32<NL>((float) xb, FS(F_STEP), fl, lmask, tf);
@@ -451,39 +495,41 @@ __device__ __forceinline__ void march_fast(const double *__restrict__ sl, const 
             }
             rec_valid = false;
             if (COUNT) ++tally.route[2];
-        } else if (all_near) {
+        } else if (min(base + 16, half) <= near_lim) {
             if (F32) {
                 float tf[NL];
                 node_sum_near32<NL>((float) xb, FS(F_STEP), fl, tab32, gauss, lmask, tf);
                 #pragma unroll
                 for (int l = 0; l < NL; ++l) tot[l] = (double) tf[l];
             } else {
+                const double2 qk = SF2(S_Q);  // {q, K16}
                 if (gauss) {
                     if (rec_valid) {  // one march step outward: x -> x -+ 16 pixels
+                        const double2 lud = SF2(S_LU16);
                         U0 *= rho;
-                        rho *= SF(S_K16);
-                        R *= g.dir ? SF(S_LD16) : SF(S_LU16);
+                        rho *= qk.y;
+                        R *= dir ? lud.y : lud.x;
                     } else {
                         const double x1 = xb + step;
                         U0 = exp(-x1 * x1);
                         R = exp(-fma(2.0, x1, step) * step);
-                        if (rec_ok) {
-                            const double delta = (g.dir ? 16.0 : -16.0) * pix;
+                        rec_valid = rec_ok;
+                        if (rec_valid) {
+                            const double delta = (dir ? 16.0 : -16.0) * pix;
                             rho = exp(-fma(2.0, x1, delta) * delta);
                         }
-                        rec_valid = rec_ok;
                     }
                 } else {
                     rec_valid = false;
                 }
-                node_sum_near<NL>(xb, step, sl, tab, U0, R, gauss, lmask, tot);
+                node_sum_near<NL>(xb, step, sl, tab, U0, R, qk.x, gauss, lmask, tot);
             }
             if (COUNT) ++tally.route[gauss ? 0 : 1];
         } else {
             // transition step: lanes differ.  Lane class: 0 table, 1 series, 2 neither (own nodes on both
             // sides of the overlap: node by node), 3 idle.
-            const bool on_any = mine && ((any >> g.dir) & 1u);
-            const int lc = !on_any ? 3 : (o >= myF ? 1 : (o < myN ? 0 : 2));
+            const int myN = dir ? thrN.y : thrN.x, myF = dir ? thrF.y : thrF.x;
+            const int lc = !mybits ? 3 : (o >= myF ? 1 : (o < myN ? 0 : 2));
             const unsigned cls = __reduce_or_sync(kFull, 1u << lc);
             rec_valid = false;
             if (cls & 1u) {
@@ -498,7 +544,7 @@ __device__ __forceinline__ void march_fast(const double *__restrict__ sl, const 
                         U0 = exp(-x1 * x1);
                         R = exp(-fma(2.0, x1, step) * step);
                     }
-                    node_sum_near<NL>(xb, step, sl, tab, U0, R, gauss, lmask, tot);
+                    node_sum_near<NL>(xb, step, sl, tab, U0, R, SF(S_Q), gauss, lmask, tot);
                 }
             }
             if (cls & 2u) {
@@ -523,10 +569,31 @@ __device__ __forceinline__ void march_fast(const double *__restrict__ sl, const 
             }
             if (COUNT) ++tally.route[3];
         }
-        double t[NL];
+        // add, then stop each run at its first pixel below tautail (absorption.cpp:260-263,274-277)
+        unsigned ended = 0;
         #pragma unroll
-        for (int l = 0; l < NL; ++l) t[l] = LF(l, L_CD) * tot[l];
-        march_commit<NL, COUNT>(g, t, cur, live, mine, base, j, 1, row0, line_stride, tautail, tally);
+        for (int l = 0; l < NL; ++l) {
+            const double t = LF(l, L_CD) * tot[l];
+            const bool on = (mybits >> (2 * l)) & 1u;
+            const unsigned stop = __ballot_sync(kFull, on && (t < tautail));
+            if (on && !(stop & grp_lt)) {  // no lane of my run below me has stopped
+                pj[l * line_stride] = cur[l] + t;
+                if (COUNT) {
+                    ++tally.pix;
+                    ++tally.inner;
+                }
+            }
+            ended |= ((stop & 0xffffu ? 1u : 0u) | (stop >> 16 ? 2u : 0u)) << (2 * l);
+        }
+        if (COUNT) ++tally.iter;
+        if (base + 16 >= half) ended = ~0u;
+        if (ended & live) {
+            live &= ~ended;
+            const bool up = live & kUpBits, dn = live & kDnBits;
+            near_lim = min(up ? thrN.x : 0x7fffffff, dn ? thrN.y : 0x7fffffff);
+            far_beg = max(up ? thrF.x : 0, dn ? thrF.y : 0);
+            gauss_end = max(up ? thrG.x : 0, dn ? thrG.y : 0);
+        }
     }
 }
 
@@ -536,7 +603,7 @@ template <int NL, bool EXACT, bool COUNT>
 __device__ __noinline__ void march_slow(const double *__restrict__ sl, const double *__restrict__ tab, double *__restrict__ row0,
                                         int64_t line_stride, int nbins, double bintov, double tautail, int lane, Tally &tally)
 {
-    const MarchGeom g = march_geom(lane, nbins, (int) SF(S_ZMAX));
+    const MarchGeom g = march_geom(lane, nbins, *reinterpret_cast<const int2 *>(&SF(S_ZMAX)));
     const double vel = SF(S_VEL);
     unsigned live[NL];
     #pragma unroll
@@ -637,7 +704,12 @@ __device__ __noinline__ void setup_particle(const InterpConsts &C, double *__res
         }
     }
     const double zmaxd = floor(velp / C.bintov);
-    SF(S_ZMAX) = zmaxd;
+    {
+        int2 zj;
+        zj.x = (int) zmaxd;
+        zj.y = wrap_bin(zj.x, C.nbins);
+        *reinterpret_cast<int2 *>(&SF(S_ZMAX)) = zj;
+    }
     const double xb0 = fma(-(fma(zmaxd + 0.5, C.bintov, -velp)), inv_b, -vhigh * inv_b);
     const double pix = C.bintov * inv_b;
     SF(S_XB0) = xb0;
@@ -765,13 +837,13 @@ k_tau(InterpConsts C, Items items, int n_items, int *__restrict__ next_item, con
         for (int64_t k0 = kbeg; k0 < kend; k0 += kBatch) {
             const int nb = (int) min((int64_t) kBatch, kend - k0);
             __syncwarp();
-            if (lane < nb) setup_particle<KERNEL, NL, F32>(C, slab + lane, fslab + lane, k0 + lane, ax, particle, dr2s, pos, vel, dens, temp, hsml, cells);
+            if (lane < nb) setup_particle<KERNEL, NL, F32>(C, slab + lane * SlabSize<NL>::kStride, fslab + lane * FSlabSize<NL>::kStride, k0 + lane, ax, particle, dr2s, pos, vel, dens, temp, hsml, cells);
             __syncwarp();
             for (int b = 0; b < nb; ++b) {
-                const double *sl = slab + b;
+                const double *sl = slab + b * SlabSize<NL>::kStride;
                 const int mode = (int) SF(S_MODE);
                 if (mode == 0) continue;
-                if (mode == 1) march_fast<NL, COUNT, F32>(sl, fslab + b, tab, tab32, row0, line_stride, nbins, C.tautail, lane, tally);
+                if (mode == 1) march_fast<NL, COUNT, F32>(sl, fslab + b * FSlabSize<NL>::kStride, tab, tab32, row0, line_stride, nbins, C.tautail, lane, tally);
                 else if (mode == 2) march_slow<NL, true, COUNT>(sl, tab, row0, line_stride, nbins, C.bintov, C.tautail, lane, tally);
                 else march_slow<NL, false, COUNT>(sl, tab, row0, line_stride, nbins, C.bintov, C.tautail, lane, tally);
                 __syncwarp();

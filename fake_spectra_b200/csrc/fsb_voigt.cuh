@@ -5,12 +5,13 @@
 // voigt fast  : this library's own evaluation for the small damping parameters of real lines
 //               (0 <= y <= kFastYMax): expansion of w about the real axis to order y^7,
 //                   H(x,y) = U(x) Pe(s) + G(x) A(s) + B(s),   s = x^2,  U = exp(-s),
-//                   G(x) = 1 - 2 x Dawson(x)   (193 piecewise degree-7 polynomials, |x| < 24),
+//                   G(x) = 1 - 2 x Dawson(x)   (193 piecewise degree-7 polynomials, |x| < 24, stored in
+//                   mixed precision: 48 bytes per piece, see fsb_voigt_tables.h),
 //               with Pe, A, B polynomials in s whose coefficients depend on y only (per-particle
 //               constants).  Beyond |x| >= 16 the Gaussian has vanished and the profile is the
 //               Taylor series in y of the damping wing, -y L' + y^3 L'''/6 - y^5 L^(5)/120 with
 //               L = Im w on the real axis expanded in u = 1/x^2 (polynomials P1, P3, P5 below).
-//               Agrees with voigt_exact to < 3e-13 relative on its domain (tests/test_gpu_parity).
+//               Agrees with voigt_exact to < 1e-11 relative on its domain (tests/test_gpu_parity).
 #pragma once
 
 #include <cuda_runtime.h>
@@ -176,8 +177,10 @@ constexpr double kFarXMin = 16.0;     // the damping-wing series is used from he
 constexpr double kFastYMax = 0.03;    // above: voigt_exact (error of the y^7 truncation < 3e-13 below)
 constexpr double kFastYMin = 1e-30;   // below (and > 0): voigt_exact (Gaussian cut-off would pass exp underflow)
 
-// Global-memory master copy of the G(x) table; kernels stage it in shared memory.
-__device__ __align__(16) const double d_gtable[FSB_GTAB_SIZE] = FSB_GTAB_VALUES;
+// Global-memory master copy of the G(x) table (raw 8-byte words: three doubles, then five floats and a
+// pad per interval); kernels stage it in shared memory and address it as doubles.
+__device__ __align__(16) const unsigned long long d_gtable_words[FSB_GTAB_SIZE] = FSB_GTAB_WORDS;
+#define d_gtable (reinterpret_cast<const double *>(d_gtable_words))
 
 // FP32 fast path: degree-3 pieces on the same intervals, {c0, c1, c2, c3} per interval.
 __device__ __align__(16) const float d_gtable32[4 * FSB_GTAB_NINT] = FSB_GTAB32_VALUES;
@@ -221,18 +224,24 @@ __device__ __forceinline__ void g_index(double ax, int &k, double &t)
     t = fma(m - magic, -1.0 / FSB_GTAB_INV_DELTA, ax);
 }
 
-// Degree-7 polynomial of interval k at offset t: four 16-byte loads (tab 16-byte aligned).
+// Degree-7 polynomial of one interval at offset t from its three 16-byte pieces {c0, c1}, {c2, (c3, c4)},
+// {(c5, c6), (c7, -)}: the t^3..t^7 part runs in single precision (|t| <= 1/16 scales its rounding error by
+// 2^-12 or less), the rest in double.
+__device__ __forceinline__ double g_poly(double2 v0, double2 v1, double2 v2, double t)
+{
+    const float tf = (float) t;
+    float hi = __int_as_float(__double2loint(v2.y));                 // c7
+    hi = fmaf(hi, tf, __int_as_float(__double2hiint(v2.x)));         // c6
+    hi = fmaf(hi, tf, __int_as_float(__double2loint(v2.x)));         // c5
+    hi = fmaf(hi, tf, __int_as_float(__double2hiint(v1.y)));         // c4
+    hi = fmaf(hi, tf, __int_as_float(__double2loint(v1.y)));         // c3
+    return fma(fma(fma((double) hi, t, v1.x), t, v0.y), t, v0.x);
+}
+
 __device__ __forceinline__ double g_eval(const double *__restrict__ tab, int k, double t)
 {
     const double2 *c = reinterpret_cast<const double2 *>(tab + k * FSB_GTAB_STRIDE);
-    const double2 c67 = c[3], c45 = c[2], c23 = c[1], c01 = c[0];
-    double g = fma(c67.y, t, c67.x);
-    g = fma(g, t, c45.y);
-    g = fma(g, t, c45.x);
-    g = fma(g, t, c23.y);
-    g = fma(g, t, c23.x);
-    g = fma(g, t, c01.y);
-    return fma(g, t, c01.x);
+    return g_poly(c[0], c[1], c[2], t);
 }
 
 // G(|x|) for |x| < 16 from the staged table (tab may be shared or global memory).
@@ -253,6 +262,18 @@ __device__ __forceinline__ void far_polys(double u, double &p1, double &p3, doub
     p1 = fma(fma(fma(fma(fma(fma(fma(15836.1328125, u, 2111.484375), u, 324.84375), u, 59.0625), u, 13.125), u, 3.75), u, 1.5), u, 1.0);
     p3 = fma(fma(fma(fma(fma(8445.9375, u, 1082.8125), u, 157.5), u, 26.25), u, 5.0), u, 1.0);
     p5 = fma(10.5, u, 1.0);
+}
+
+// 1/s for a normal positive s (the wing series has s = x^2 >= 256): hardware seed (relative error 2^-23) and
+// two Newton steps, none of the library routine's special-case handling.  Within an ulp of 1/s.
+__device__ __forceinline__ double fast_rcp(double s)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(s));
+    double e = fma(-s, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-s, r, 1.0);
+    return fma(r, e, r);
 }
 
 __device__ __forceinline__ double voigt_far(double s, double y)

@@ -12,7 +12,7 @@ case $S in
 test) echo "== pytest -m gpu"; timeout 900 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1; echo "rc=$?" >> $OUT/pytest_gpu.log; tail -15 $OUT/pytest_gpu.log;;
 smoke) echo "== smoke"; timeout 300 python __graft_entry__.py smoke > $OUT/smoke.log 2>&1; tail -3 $OUT/smoke.log;;
 probe) echo "== probe"; timeout 600 python scripts/gpu_probe.py c1 c2s > $OUT/probe.log 2>&1; tail -6 $OUT/probe.log;;
-variants) echo "== variants"; for L in fake_spectra_b200/libfsb200*.so; do echo "-- $L"; FSB200_LIB=$PWD/$L timeout 600 python scripts/gpu_probe.py c1 c2s 2>&1 | tail -2 | tee -a $OUT/variants.log; done;;
+variants) echo "== variants"; for L in fake_spectra_b200/libfsb200*.so; do echo "-- $L"; FSB200_LIB=$PWD/$L timeout 600 python scripts/gpu_probe.py ${PROBE:-c1 c2s} 2>&1 | tail -3 | tee -a $OUT/variants.log; done;;
 bench) echo "== bench default"; timeout 900 python bench.py --steps 3 --warmup 3 > $OUT/bench.json 2> $OUT/bench.err; tail -2 $OUT/bench.json; tail -3 $OUT/bench.err;;
 launches) echo "== ncu launch list (mini workload)"
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_mini.csv \

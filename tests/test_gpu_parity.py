@@ -106,7 +106,9 @@ def test_voigt_sweep_golden(torch_cuda, golden_dir, voigt):
     y = torch_cuda.from_numpy(z["y"]).cuda()
     got = native.voigt_profile(x, y, voigt=voigt).cpu().numpy()
     rel, same_zero = cases.rel_err(got, z["h"])
-    assert same_zero and rel < 1e-12, rel
+    # exact = restatement of the reference's Faddeeva::w; fast = this library's expansion, whose mixed-precision
+    # G(x) table (48 bytes per piece) is designed to <= 1e-11 on H: a decade inside the 1e-10 budget on tau
+    assert same_zero and rel < (1e-12 if voigt == 1 else 1.5e-11), rel
 
 
 @pytest.mark.parametrize("kernel,line,res", [(1, "HI1215", 1.0), (0, "HI1215", 1.0), (3, "CIV1548", 2.5),
