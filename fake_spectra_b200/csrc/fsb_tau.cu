@@ -30,14 +30,14 @@ namespace fsb {
 namespace {
 
 #ifndef FSB_TAU_MIN_BLOCKS
-#define FSB_TAU_MIN_BLOCKS 4  // resident CTAs per SM the register allocation must allow
+#define FSB_TAU_MIN_BLOCKS 1  // resident CTAs per SM the register allocation must allow (x FSB_TAU_WARPS = 16 warps per SM)
 #endif
 #ifndef FSB_TAU_BATCH
 #define FSB_TAU_BATCH 16
 #endif
 
 #ifndef FSB_TAU_WARPS
-#define FSB_TAU_WARPS 4
+#define FSB_TAU_WARPS 16  // one persistent CTA per SM: one copy of the G(x) table per SM; measured 4 % faster than 4 x 4 warps
 #endif
 constexpr int kTauWarps = FSB_TAU_WARPS;
 constexpr int kTauThreads = 32 * kTauWarps;
@@ -79,7 +79,7 @@ enum LineField {
     L_B0,        // B(s): 3 raw coefficients (generic route)
     L_COUNT = L_B0 + 3
 };
-static_assert(S_COUNT % 2 == 0 && L_COUNT % 2 == 0 && S_KW0 % 2 == 0 && S_Q % 2 == 0 && S_LU16 % 2 == 0, "16-byte field pairs");
+static_assert(L_CD == L_BQ0 + 5 && (L_BQ0 + 4) % 2 == 0 && S_COUNT % 2 == 0 && L_COUNT % 2 == 0 && S_KW0 % 2 == 0 && S_Q % 2 == 0 && S_LU16 % 2 == 0, "16-byte field pairs");
 template <int NL> struct SlabSize {
     static constexpr int kFields = S_COUNT + NL * L_COUNT;
     // record stride in doubles: an odd number of 16-byte units, so the 16 setup lanes spread over the banks
@@ -106,114 +106,121 @@ template <int NL> struct FSlabSize {
 // All return sum_i kw_i H(x_i, y_l) for x_i = xb + (i+1) step, per fused line l.
 
 // NEAR: every node at |x| < 16.  U0 = exp(-x_1^2), R = exp(-(2 x_1 + step) step), q = exp(-2 step^2)
-// (gauss = false when the Gaussian is negligible for the whole warp step).  The table Horner runs node-interleaved (7
-// independent chains); x and s are recomputed where needed rather than kept live, and the Gaussians
-// are produced on the fly by the node recurrence.  Lanes with nodes beyond the table compute
-// finite garbage that the caller discards.
+// (gauss = false when the Gaussian is negligible for the whole warp step).  Nodes are processed in groups
+// of FSB_TAU_NODE_GROUP, interleaved within a group for instruction-level parallelism (the table lookups of
+// a group are in flight together); the Gaussians come from the node recurrence, carried across groups.
+// Lanes with nodes beyond the table compute finite garbage that the caller discards.  Totals are scaled
+// by the line amplitude L_CD.
+#ifndef FSB_TAU_NODE_GROUP
+#define FSB_TAU_NODE_GROUP 7
+#endif
+template <int NL> struct NearCoefs {
+    double2 a01[NL], a23[NL], p01[NL], p23[NL];
+};
+
+template <int NL, int I0, int N, bool GAUSS>
+__device__ __forceinline__ void near_group(double xb, double step, const double *__restrict__ sl, const double *__restrict__ tab,
+                                           const NearCoefs<NL> &c, double &u, double &r, double q, unsigned lmask,
+                                           double (&acc)[NL], double (&acc2)[NL])
+{
+    double t[N], g[N];
+    {
+        const double2 *base[N];
+        double2 v0[N], v1[N], v2[N];
+        #pragma unroll
+        for (int i = 0; i < N; ++i) {
+            int k;
+            g_index(fabs(fma((double) (I0 + i + 1), step, xb)), k, t[i]);
+            k = (int) min((unsigned) k, (unsigned) (FSB_GTAB_NINT - 1));
+            base[i] = reinterpret_cast<const double2 *>(tab + k * FSB_GTAB_STRIDE);
+        }
+        #pragma unroll
+        for (int i = 0; i < N; ++i) v2[i] = base[i][2];
+        #pragma unroll
+        for (int i = 0; i < N; ++i) v1[i] = base[i][1];
+        #pragma unroll
+        for (int i = 0; i < N; ++i) v0[i] = base[i][0];
+#ifdef FSB_EXP_DBLLOAD
+        {   // timing experiment only: repeat the table loads (results feed an impossible accumulate)
+            double dummy = 0;
+            #pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                #pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    double a, b;
+                    asm volatile("ld.volatile.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"((unsigned) __cvta_generic_to_shared(base[i] + j)));
+                    dummy += a + b;
+                }
+            }
+            if (dummy == 1.2345e300) acc[0] = dummy;
+        }
+#endif
+        #pragma unroll
+        for (int i = 0; i < N; ++i) g[i] = g_poly(v0[i], v1[i], v2[i], t[i]);
+    }
+    // t[] is reused for s = x^2; g[] becomes the kernel-weighted table value, uw[] the kernel-weighted Gaussian
+    double uw[N];
+    #pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const double x = fma((double) (I0 + i + 1), step, xb);
+        t[i] = x * x;
+        const double kw = SF(S_KW0 + I0 + i);
+        g[i] *= kw;
+        if (GAUSS) {
+            uw[i] = u * kw;
+            u *= r;
+            r *= q;
+        }
+    }
+    #pragma unroll
+    for (int l = 0; l < NL; ++l) {
+        if (NL > 1 && !((lmask >> l) & 1u)) continue;
+        #pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const double A = fma(fma(fma(c.a23[l].y, t[i], c.a23[l].x), t[i], c.a01[l].y), t[i], c.a01[l].x);
+            acc2[l] = fma(g[i], A, acc2[l]);
+            if (GAUSS) {
+                const double Pe = fma(fma(fma(c.p23[l].y, t[i], c.p23[l].x), t[i], c.p01[l].y), t[i], c.p01[l].x);
+                acc[l] = fma(uw[i], Pe, acc[l]);
+            }
+        }
+    }
+}
+
+template <int NL, bool GAUSS>
+__device__ __forceinline__ void node_sum_near_g(double xb, double step, const double *__restrict__ sl, const double *__restrict__ tab,
+                                                double U0, double R, double q, unsigned lmask, double (&tot)[NL])
+{
+    static_assert(FSB_GTAB_DEG == 7 && FSB_GTAB_STRIDE == 6, "written for the 48-byte degree-7 table");
+    constexpr int G = FSB_TAU_NODE_GROUP;
+    NearCoefs<NL> c;
+    double acc[NL], acc2[NL], cd[NL];
+    #pragma unroll
+    for (int l = 0; l < NL; ++l) {
+        c.a01[l] = LF2(l, L_A0), c.a23[l] = LF2(l, L_A0 + 2);
+        if (GAUSS) c.p01[l] = LF2(l, L_PE0), c.p23[l] = LF2(l, L_PE0 + 2);
+        // sum_i kw_i B(s_i): a quartic in xb
+        const double2 b01 = LF2(l, L_BQ0), b23 = LF2(l, L_BQ0 + 2), b4c = LF2(l, L_BQ0 + 4);
+        acc[l] = fma(fma(fma(fma(b4c.x, xb, b23.y), xb, b23.x), xb, b01.y), xb, b01.x);
+        acc2[l] = 0;
+        cd[l] = b4c.y;
+    }
+    double u = U0, r = R;
+    near_group<NL, 0, (G < 7 ? G : 7), GAUSS>(xb, step, sl, tab, c, u, r, q, lmask, acc, acc2);
+    if (G < 7) near_group<NL, (G < 7 ? G : 0), (G < 7 ? (7 - G < G ? 7 - G : G) : 1), GAUSS>(xb, step, sl, tab, c, u, r, q, lmask, acc, acc2);
+    if (2 * G < 7) near_group<NL, (2 * G < 7 ? 2 * G : 0), (2 * G < 7 ? 7 - 2 * G : 1), GAUSS>(xb, step, sl, tab, c, u, r, q, lmask, acc, acc2);
+    static_assert(3 * G >= 7, "FSB_TAU_NODE_GROUP must be at least 3");
+    #pragma unroll
+    for (int l = 0; l < NL; ++l) tot[l] = (NL > 1 && !((lmask >> l) & 1u)) ? 0.0 : cd[l] * (acc[l] + acc2[l]);
+}
+
 template <int NL>
 __device__ __forceinline__ void node_sum_near(double xb, double step, const double *__restrict__ sl,
                                               const double *__restrict__ tab, double U0, double R, double q, bool gauss,
                                               unsigned lmask, double (&tot)[NL])
 {
-    static_assert(FSB_GTAB_DEG == 7 && FSB_GTAB_STRIDE == 6, "node_sum_near is written for the 48-byte degree-7 table");
-    double t[7], g[7];
-    const double2 *base[7];
-    {
-        double2 v0[7], v1[7], v2[7];
-        #pragma unroll
-        for (int i = 0; i < 7; ++i) {
-            int k;
-            g_index(fabs(fma((double) (i + 1), step, xb)), k, t[i]);
-            k = (int) min((unsigned) k, (unsigned) (FSB_GTAB_NINT - 1));
-            base[i] = reinterpret_cast<const double2 *>(tab + k * FSB_GTAB_STRIDE);
-        }
-        #pragma unroll
-        for (int i = 0; i < 7; ++i) v2[i] = base[i][2];
-        #pragma unroll
-        for (int i = 0; i < 7; ++i) v1[i] = base[i][1];
-        #pragma unroll
-        for (int i = 0; i < 7; ++i) v0[i] = base[i][0];
-        #pragma unroll
-        for (int i = 0; i < 7; ++i) g[i] = g_poly(v0[i], v1[i], v2[i], t[i]);
-    }
-#ifdef FSB_EXP_DBLLOAD
-    {   // timing experiment only: repeat the 21 table loads (results feed an impossible store)
-        double dummy = 0;
-        #pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            #pragma unroll
-            for (int i = 0; i < 7; ++i) {
-                double a, b;
-                asm volatile("ld.volatile.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"((unsigned) __cvta_generic_to_shared(base[i] + j)));
-                dummy += a + b;
-            }
-        }
-        if (dummy == 1.2345e300) tot[0] = dummy;
-    }
-#endif
-    // t[] is reused for s = x^2
-    #pragma unroll
-    for (int i = 0; i < 7; ++i) {
-        const double x = fma((double) (i + 1), step, xb);
-        t[i] = x * x;
-    }
-    double kw[7];
-    {
-        const double2 k01 = SF2(S_KW0), k23 = SF2(S_KW0 + 2), k45 = SF2(S_KW0 + 4), k6m = SF2(S_KW0 + 6);
-        kw[0] = k01.x, kw[1] = k01.y, kw[2] = k23.x, kw[3] = k23.y, kw[4] = k45.x, kw[5] = k45.y, kw[6] = k6m.x;
-    }
-    // kernel-weighted table values: each line then costs one FMA per node on top of its polynomial A
-    #pragma unroll
-    for (int i = 0; i < 7; ++i) g[i] *= kw[i];
-    if (gauss) {
-        // Gaussians of the 7 nodes by the two-term recurrence, shared by the fused lines, also kernel-weighted
-        double uw[7];
-        {
-            double u = U0, r = R;
-            #pragma unroll
-            for (int i = 0; i < 7; ++i) {
-                uw[i] = u * kw[i];
-                u *= r;
-                r *= q;
-            }
-        }
-        #pragma unroll
-        for (int l = 0; l < NL; ++l) {
-            if (NL > 1 && !((lmask >> l) & 1u)) {
-                tot[l] = 0;
-                continue;
-            }
-            const double2 a01 = LF2(l, L_A0), a23 = LF2(l, L_A0 + 2), p01 = LF2(l, L_PE0), p23 = LF2(l, L_PE0 + 2);
-            const double2 b01 = LF2(l, L_BQ0), b23 = LF2(l, L_BQ0 + 2);
-            double acc = fma(fma(fma(fma(LF(l, L_BQ0 + 4), xb, b23.y), xb, b23.x), xb, b01.y), xb, b01.x);
-            double acc2 = 0;
-            #pragma unroll
-            for (int i = 0; i < 7; ++i) {
-                const double A = fma(fma(fma(a23.y, t[i], a23.x), t[i], a01.y), t[i], a01.x);
-                const double Pe = fma(fma(fma(p23.y, t[i], p23.x), t[i], p01.y), t[i], p01.x);
-                acc = fma(uw[i], Pe, acc);
-                acc2 = fma(g[i], A, acc2);
-            }
-            tot[l] = acc + acc2;
-        }
-    } else {  // the Gaussian is negligible for every lane of this step
-        #pragma unroll
-        for (int l = 0; l < NL; ++l) {
-            if (NL > 1 && !((lmask >> l) & 1u)) {
-                tot[l] = 0;
-                continue;
-            }
-            const double2 a01 = LF2(l, L_A0), a23 = LF2(l, L_A0 + 2);
-            const double2 b01 = LF2(l, L_BQ0), b23 = LF2(l, L_BQ0 + 2);
-            double acc = fma(fma(fma(fma(LF(l, L_BQ0 + 4), xb, b23.y), xb, b23.x), xb, b01.y), xb, b01.x);
-            #pragma unroll
-            for (int i = 0; i < 7; ++i) {
-                const double A = fma(fma(fma(a23.y, t[i], a23.x), t[i], a01.y), t[i], a01.x);
-                acc = fma(g[i], A, acc);
-            }
-            tot[l] = acc;
-        }
-    }
+    if (gauss) node_sum_near_g<NL, true>(xb, step, sl, tab, U0, R, q, lmask, tot);
+    else node_sum_near_g<NL, false>(xb, step, sl, tab, U0, R, q, lmask, tot);
 }
 
 // FAR: every node at |x| >= 16 (the Gaussian is < e^-256).  Lanes with nodes inside compute garbage
@@ -248,7 +255,7 @@ __device__ __forceinline__ void node_sum_far(double xb, double step, const doubl
             const double v = y2 * u[i];
             acc = fma(u[i] * fma(v, fma(v, p5[i], -p3[i]), p1[i]), kw[i], acc);
         }
-        tot[l] = isp * y * acc;
+        tot[l] = (LF(l, L_CD) * isp * y) * acc;
     }
 }
 
@@ -489,7 +496,7 @@ __device__ __forceinline__ void march_fast(const double *__restrict__ sl, const 
                 float tf[NL];
                 node_sum_far32<NL>((float) xb, FS(F_STEP), fl, lmask, tf);
                 #pragma unroll
-                for (int l = 0; l < NL; ++l) tot[l] = (double) tf[l];
+                for (int l = 0; l < NL; ++l) tot[l] = LF(l, L_CD) * (double) tf[l];
             } else {
                 node_sum_far<NL>(xb, step, sl, lmask, tot);
             }
@@ -500,7 +507,7 @@ __device__ __forceinline__ void march_fast(const double *__restrict__ sl, const 
                 float tf[NL];
                 node_sum_near32<NL>((float) xb, FS(F_STEP), fl, tab32, gauss, lmask, tf);
                 #pragma unroll
-                for (int l = 0; l < NL; ++l) tot[l] = (double) tf[l];
+                for (int l = 0; l < NL; ++l) tot[l] = LF(l, L_CD) * (double) tf[l];
             } else {
                 const double2 qk = SF2(S_Q);  // {q, K16}
                 if (gauss) {
@@ -537,7 +544,7 @@ __device__ __forceinline__ void march_fast(const double *__restrict__ sl, const 
                     float tf[NL];
                     node_sum_near32<NL>((float) xb, FS(F_STEP), fl, tab32, gauss, lmask, tf);
                     #pragma unroll
-                    for (int l = 0; l < NL; ++l) tot[l] = (double) tf[l];
+                    for (int l = 0; l < NL; ++l) tot[l] = LF(l, L_CD) * (double) tf[l];
                 } else {
                     if (gauss) {
                         const double x1 = xb + step;
@@ -553,7 +560,7 @@ __device__ __forceinline__ void march_fast(const double *__restrict__ sl, const 
                     float tf[NL];
                     node_sum_far32<NL>((float) xb, FS(F_STEP), fl, lmask, tf);
                     #pragma unroll
-                    for (int l = 0; l < NL; ++l) tfar[l] = (double) tf[l];
+                    for (int l = 0; l < NL; ++l) tfar[l] = LF(l, L_CD) * (double) tf[l];
                 } else {
                     node_sum_far<NL>(xb, step, sl, lmask, tfar);
                 }
@@ -564,7 +571,7 @@ __device__ __forceinline__ void march_fast(const double *__restrict__ sl, const 
                 if (lc == 2) {
                     #pragma unroll
                     for (int l = 0; l < NL; ++l)
-                        if ((lmask >> l) & 1u) tot[l] = node_sum_generic((SF(S_XOFF) - xb) / SF(S_INVB), sl, l, tab);
+                        if ((lmask >> l) & 1u) tot[l] = LF(l, L_CD) * node_sum_generic((SF(S_XOFF) - xb) / SF(S_INVB), sl, l, tab);
                 }
             }
             if (COUNT) ++tally.route[3];
@@ -573,7 +580,7 @@ __device__ __forceinline__ void march_fast(const double *__restrict__ sl, const 
         unsigned ended = 0;
         #pragma unroll
         for (int l = 0; l < NL; ++l) {
-            const double t = LF(l, L_CD) * tot[l];
+            const double t = tot[l];  // already scaled by the line amplitude
             const bool on = (mybits >> (2 * l)) & 1u;
             const unsigned stop = __ballot_sync(kFull, on && (t < tautail));
             if (on && !(stop & grp_lt)) {  // no lane of my run below me has stopped
