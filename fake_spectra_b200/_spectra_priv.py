@@ -24,7 +24,7 @@ def _is_f32(a):
 
 def _Particle_Interpolate(compute_tau, nbins, kernel, box, velfac, atime, lambda_cm, gamma, fosc, amumass, tautail,
                           pos, vel, dens, temp, h, axis, cofm, precision=None, voigt=None, out=None,
-                          extra_lines=(), extra_weights=()):
+                          extra_lines=(), extra_weights=(), seg_pairs=0):
     """Optical depth (compute_tau != 0) or column density on every sightline.
 
     Arguments, order and units as py_module.cpp:115; returns a new float64 array [NumLos, nbins].
@@ -34,7 +34,8 @@ def _Particle_Interpolate(compute_tau, nbins, kernel, box, velfac, atime, lambda
     float64 result buffer; ``extra_lines`` = [(lambda_cm, gamma, fosc), ...] further lines of the
     same ion computed from the same upload and candidate index, result [1+len, NumLos, nbins];
     ``extra_weights`` (column density only) = further float32 density-like arrays interpolated in
-    the same geometry pass, result [1+len, NumLos, nbins]."""
+    the same geometry pass, result [1+len, NumLos, nbins]; ``seg_pairs`` = candidate pairs per work item
+    (0 = automatic; see fsb_params.seg_pairs)."""
     for a in (pos, vel, dens, temp, h):
         if not _is_f32(a):
             raise TypeError("One of the data arrays does not have 32-bit float type")
@@ -61,11 +62,11 @@ def _Particle_Interpolate(compute_tau, nbins, kernel, box, velfac, atime, lambda
     cofm, axis = np.ascontiguousarray(cofm), np.ascontiguousarray(axis)
     p = _lib.make_params(nbins, kernel, box, velfac, atime, lambda_cm, gamma, fosc, amumass, tautail,
                          precision=DEFAULT_PRECISION if precision is None else precision,
-                         voigt=DEFAULT_VOIGT if voigt is None else voigt)
+                         voigt=DEFAULT_VOIGT if voigt is None else voigt, seg_pairs=seg_pairs)
     prec = DEFAULT_PRECISION if precision is None else precision
     vgt = DEFAULT_VOIGT if voigt is None else voigt
     plist = [p] + [_lib.make_params(nbins, kernel, box, velfac, atime, lam, gam, fo, amumass, tautail, precision=prec,
-                                    voigt=vgt) for (lam, gam, fo) in extra_lines]
+                                    voigt=vgt, seg_pairs=seg_pairs) for (lam, gam, fo) in extra_lines]
     ncols = len(plist) if compute_tau or not extra_weights else 1 + len(extra_weights)
     shape = (numlos, int(nbins)) if ncols == 1 else (ncols, numlos, int(nbins))
     if out is None:

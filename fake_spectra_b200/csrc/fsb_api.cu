@@ -132,11 +132,13 @@ extern "C" int fsb_device_info(int32_t *sm_count, int32_t *clock_khz, int32_t *c
     return FSB_OK;
 }
 
-extern "C" int fsb_compute_tau_multi(const fsb_index *idx, const fsb_params *p, int32_t nlines, const float *pos,
-                                     const float *vel, const float *dens, const float *temp, const float *h, double *tau,
-                                     fsb_counters *counters, void *stream_v)
+namespace {
+// host == NULL: results stay on the device.  Otherwise every group of fused lines is also delivered to
+// host[line][nlos][nbins]: streamed out while its kernel runs when the launch supports it, copied after it otherwise.
+int compute_tau_multi_impl(const fsb_index *idx, const fsb_params *p, int32_t nlines, const float *pos, const float *vel,
+                           const float *dens, const float *temp, const float *h, double *tau, fsb_counters *counters,
+                           cudaStream_t stream, double *host, cudaStream_t copy_stream)
 {
-    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
     FSB_REQUIRE(nlines >= 1, "nlines must be >= 1");
     FSB_REQUIRE(idx != nullptr && p != nullptr, "NULL index or params");
     FSB_REQUIRE(idx->npairs == 0 || (pos && vel && dens && temp && h && tau), "NULL array");
@@ -154,10 +156,33 @@ extern "C" int fsb_compute_tau_multi(const fsb_index *idx, const fsb_params *p, 
         InterpConsts c;
         FSB_TRY(make_consts(idx, &p[i0], n, c));
         for (int32_t k = 0; k < n; ++k) line_consts(p[i0 + k], c.line[k]);
-        FSB_TRY(launch_tau(idx, c, pos, vel, dens, temp, h, nullptr, tau + (size_t) i0 * (size_t) idx->nlos * (size_t) c.nbins,
-                           counters, p[i0].precision, stream));
+        const size_t off = (size_t) i0 * (size_t) idx->nlos * (size_t) c.nbins;
+        HostSink sink;
+        sink.host = host ? host + off : nullptr;
+        sink.copy_stream = copy_stream;
+        FSB_TRY(launch_tau(idx, c, pos, vel, dens, temp, h, nullptr, tau + off, counters, p[i0].precision, stream,
+                           host ? &sink : nullptr));
+        if (host && !sink.streamed) {
+            const size_t bytes = sizeof(double) * (size_t) n * (size_t) idx->nlos * (size_t) c.nbins;
+            cudaEvent_t done;
+            FSB_CUDA_TRY(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+            cudaError_t e = cudaEventRecord(done, stream);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(copy_stream, done, 0);
+            if (e == cudaSuccess && bytes) e = cudaMemcpyAsync(host + off, tau + off, bytes, cudaMemcpyDeviceToHost, copy_stream);
+            cudaEventDestroy(done);
+            FSB_CUDA_TRY(e);
+        }
     }
     return FSB_OK;
+}
+}  // namespace
+
+extern "C" int fsb_compute_tau_multi(const fsb_index *idx, const fsb_params *p, int32_t nlines, const float *pos,
+                                     const float *vel, const float *dens, const float *temp, const float *h, double *tau,
+                                     fsb_counters *counters, void *stream_v)
+{
+    return compute_tau_multi_impl(idx, p, nlines, pos, vel, dens, temp, h, tau, counters, static_cast<cudaStream_t>(stream_v),
+                                  nullptr, nullptr);
 }
 
 extern "C" int fsb_compute_tau(const fsb_index *idx, const fsb_params *p, const float *pos, const float *vel,
@@ -233,6 +258,18 @@ struct DevBuf {
 };
 }  // namespace
 
+namespace {
+struct OwnedStream {
+    cudaStream_t s = nullptr;
+    int create()
+    {
+        FSB_CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        return FSB_OK;
+    }
+    ~OwnedStream() { if (s) cudaStreamDestroy(s); }
+};
+}  // namespace
+
 extern "C" int fsb_particle_interpolate_multi_host(int32_t compute_tau, const fsb_params *p, int32_t nlines,
                                                    const float *pos, const float *vel, const float *dens,
                                                    const float *temp, const float *h, int64_t npart, const int32_t *axis,
@@ -242,7 +279,12 @@ extern "C" int fsb_particle_interpolate_multi_host(int32_t compute_tau, const fs
     FSB_REQUIRE(nlines >= 1, "nlines must be >= 1");
     FSB_REQUIRE(nlos >= 0 && npart >= 0 && p[0].nbins > 0, "bad sizes");
     FSB_TRY(retain_pool_memory());
-    cudaStream_t s = nullptr;
+    // own streams (declared first: destroyed after the buffers that are freed on them): compute, and a copy
+    // stream that carries finished rows to the host while the tau kernel is still running
+    OwnedStream compute, copy;
+    FSB_TRY(compute.create());
+    FSB_TRY(copy.create());
+    cudaStream_t s = compute.s;
     DevBuf dpos, dvel, ddens, dtemp, dh, daxis, dcofm, dout;
     const size_t np = (size_t) npart, nl = (size_t) nlos;
     FSB_TRY(dpos.upload(pos, sizeof(float) * 3 * np, s));
@@ -260,29 +302,43 @@ extern "C" int fsb_particle_interpolate_multi_host(int32_t compute_tau, const fs
     const size_t out_bytes = row_bytes * (size_t) nlines;
     FSB_TRY(dout.upload(nullptr, out_bytes, s));
     FSB_CUDA_TRY(cudaMemsetAsync(dout.ptr, 0, std::max<size_t>(out_bytes, 8), s));
-    if (nlines == 1 || p[0].kernel == FSB_KERNEL_VORONOI) {
-        for (int32_t i = 0; i < nlines; ++i)
-            FSB_TRY(fsb_particle_interpolate(compute_tau, &p[compute_tau ? i : 0], (const float *) dpos.ptr, (const float *) dvel.ptr,
-                                             (const float *) ddens.ptr + (compute_tau ? 0 : (size_t) i * np),
-                                             (const float *) dtemp.ptr, (const float *) dh.ptr, npart,
-                                             (const int32_t *) daxis.ptr, (const double *) dcofm.ptr, nlos,
-                                             (double *) dout.ptr + (size_t) i * nl * (size_t) p[0].nbins, s));
+    bool delivered = false;
+    int rc = FSB_OK;
+    if (p[0].kernel == FSB_KERNEL_VORONOI) {
+        for (int32_t i = 0; i < nlines && rc == FSB_OK; ++i)
+            rc = fsb_particle_interpolate(compute_tau, &p[compute_tau ? i : 0], (const float *) dpos.ptr, (const float *) dvel.ptr,
+                                          (const float *) ddens.ptr + (compute_tau ? 0 : (size_t) i * np),
+                                          (const float *) dtemp.ptr, (const float *) dh.ptr, npart,
+                                          (const int32_t *) daxis.ptr, (const double *) dcofm.ptr, nlos,
+                                          (double *) dout.ptr + (size_t) i * nl * (size_t) p[0].nbins, s);
     } else {
         fsb_index *idx = nullptr;
-        FSB_TRY(fsb_index_build(p[0].box, (const double *) dcofm.ptr, (const int32_t *) daxis.ptr, nlos, (const float *) dpos.ptr,
-                                (const float *) dh.ptr, npart, s, &idx));
-        const int rc = compute_tau
-                           ? fsb_compute_tau_multi(idx, p, nlines, (const float *) dpos.ptr, (const float *) dvel.ptr,
-                                                   (const float *) ddens.ptr, (const float *) dtemp.ptr,
-                                                   (const float *) dh.ptr, (double *) dout.ptr, nullptr, s)
-                           : fsb_compute_colden(idx, p, (const float *) dpos.ptr, (const float *) ddens.ptr, nlines,
-                                                (const float *) dh.ptr, (double *) dout.ptr, nullptr, s);
-        fsb_index_free(idx, s);
-        FSB_TRY(rc);
+        rc = fsb_index_build(p[0].box, (const double *) dcofm.ptr, (const int32_t *) daxis.ptr, nlos, (const float *) dpos.ptr,
+                             (const float *) dh.ptr, npart, s, &idx);
+        if (rc == FSB_OK) {
+            if (compute_tau) {
+                rc = compute_tau_multi_impl(idx, p, nlines, (const float *) dpos.ptr, (const float *) dvel.ptr,
+                                            (const float *) ddens.ptr, (const float *) dtemp.ptr, (const float *) dh.ptr,
+                                            (double *) dout.ptr, nullptr, s, out, copy.s);
+                delivered = rc == FSB_OK;
+            } else {
+                rc = fsb_compute_colden(idx, p, (const float *) dpos.ptr, (const float *) ddens.ptr, nlines,
+                                        (const float *) dh.ptr, (double *) dout.ptr, nullptr, s);
+            }
+            fsb_index_free(idx, s);
+        }
     }
-    if (out_bytes) FSB_CUDA_TRY(cudaMemcpyAsync(out, dout.ptr, out_bytes, cudaMemcpyDeviceToHost, s));
-    FSB_CUDA_TRY(cudaStreamSynchronize(s));
-    return FSB_OK;
+    if (rc == FSB_OK && !delivered && out_bytes) {
+        const cudaError_t e = cudaMemcpyAsync(out, dout.ptr, out_bytes, cudaMemcpyDeviceToHost, s);
+        if (e != cudaSuccess) { set_error("cudaMemcpyAsync (result): %s", cudaGetErrorString(e)); rc = FSB_ECUDA; }
+    }
+    // both streams drain before the buffers go out of scope, also on the error path
+    const cudaError_t e1 = cudaStreamSynchronize(s), e2 = cudaStreamSynchronize(copy.s);
+    if (rc == FSB_OK && (e1 != cudaSuccess || e2 != cudaSuccess)) {
+        set_error("stream synchronize: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+        rc = FSB_ECUDA;
+    }
+    return rc;
 }
 
 extern "C" int fsb_particle_interpolate_host(int32_t compute_tau, const fsb_params *p, const float *pos, const float *vel,

@@ -94,10 +94,18 @@ struct InterpConsts {
 
 constexpr int kMaxFused = 4;
 
+// Host destination of a tau launch: finished sightline rows are copied out on copy_stream while the kernel
+// is still running (the kernel raises one flag in pinned host memory per chunk of sightlines).
+struct HostSink {
+    double *host = nullptr;       // same layout as the device output of this launch: [nlines][nlos][nbins]
+    cudaStream_t copy_stream = nullptr;
+    bool streamed = false;        // out: the launch copied its rows; false = the caller still has to
+};
+
 // launches implemented in the .cu files
 int launch_tau(const fsb_index *idx, const InterpConsts &c, const float *pos, const float *vel, const float *dens,
                const float *temp, const float *h, const float *cells, double *out, fsb_counters *counters,
-               int precision, cudaStream_t stream);
+               int precision, cudaStream_t stream, HostSink *sink = nullptr);
 int launch_colden(const fsb_index *idx, const InterpConsts &c, const float *pos, const float *dens, int64_t dens_stride,
                   const float *h, const float *cells, double *out, fsb_counters *counters, cudaStream_t stream);
 int tau_max_fused_lines();

@@ -22,6 +22,8 @@
 //   MIXED  the rare warp step that straddles |x| = 16, and pixels wider than btherm/2
 //          (sub-sampling rule of singleabs.h:110-125): generic per-node evaluation
 //   EXACT  FSB_VOIGT_EXACT or y outside (1e-30, 0.03]: restatement of the reference's Faddeeva::w
+#include <stdlib.h>
+
 #include "fsb_items.cuh"
 #include "fsb_voigt.cuh"
 
@@ -800,14 +802,14 @@ template <int NL, bool F32> constexpr size_t tau_smem_bytes()
            (F32 ? sizeof(float) * (size_t) (4 * FSB_GTAB_NINT + kTauWarps * FSlabSize<NL>::kFloats) : 0);
 }
 
-template <int KERNEL, int NL, bool COUNT, bool F32>
+template <int KERNEL, int NL, bool COUNT, bool F32, bool STREAM>
 __global__ void __launch_bounds__(kTauThreads, FSB_TAU_MIN_BLOCKS)
 k_tau(InterpConsts C, Items items, int n_items, int *__restrict__ next_item, const int64_t *__restrict__ offsets,
       const int32_t *__restrict__ particle, const double *__restrict__ dr2s, const int32_t *__restrict__ axis,
       const float *__restrict__ pos, const float *__restrict__ vel, const float *__restrict__ dens,
       const float *__restrict__ temp, const float *__restrict__ hsml, const float *__restrict__ cells,
       double *__restrict__ out, double *__restrict__ scratch, int64_t scratch_stride,
-      unsigned long long *__restrict__ counters)
+      unsigned long long *__restrict__ counters, int *__restrict__ chunk_done, int *host_flags, int chunk_lines)
 {
     extern __shared__ __align__(16) double smem[];
     double *tab = smem;  // [FSB_GTAB_SIZE], 16-byte aligned
@@ -835,7 +837,24 @@ k_tau(InterpConsts C, Items items, int n_items, int *__restrict__ next_item, con
         if (item >= n_items) break;
         int line;
         int64_t kbeg, kend;
-        if (!locate_item(items, offsets, C.nlos, item, line, kbeg, kend)) continue;
+        // one item per sightline and a host sink: the last row of a chunk of sightlines to finish raises the
+        // chunk's flag in pinned host memory; the host copies that chunk out while the kernel carries on
+        auto row_done = [&](int finished_line) {
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) {
+                const int c = finished_line / chunk_lines;
+                const int in_chunk = min(chunk_lines, C.nlos - c * chunk_lines);
+                if (atomicAdd(&chunk_done[c], 1) + 1 == in_chunk) {
+                    __threadfence_system();
+                    *reinterpret_cast<volatile int *>(host_flags + c) = 1;
+                }
+            }
+        };
+        if (!locate_item(items, offsets, C.nlos, item, line, kbeg, kend)) {
+            if (STREAM && item < C.nlos) row_done(item);
+            continue;
+        }
         double *row0 = items.item_start ? scratch + (int64_t) item * nbins : out + (int64_t) line * nbins;
         const int64_t line_stride = items.item_start ? scratch_stride : out_stride;
         const int ax = axis[line] - 1;
@@ -856,6 +875,7 @@ k_tau(InterpConsts C, Items items, int n_items, int *__restrict__ next_item, con
                 __syncwarp();
             }
         }
+        if (STREAM) row_done(line);
     }
     if (COUNT) {
         unsigned long long pix = tally.pix, vg = 7ull * tally.inner;
@@ -898,7 +918,7 @@ __global__ void k_voigt_profile(const double *__restrict__ x, const double *__re
 template <int KERNEL, int NL>
 int launch_tau_k(const fsb_index *idx, const InterpConsts &c, const ItemPlan &plan, int *next_item, const float *pos,
                  const float *vel, const float *dens, const float *temp, const float *h, const float *cells, double *out,
-                 unsigned long long *ctr, int precision, cudaStream_t stream)
+                 unsigned long long *ctr, int precision, cudaStream_t stream, int *chunk_done, int *host_flags, int chunk_lines)
 {
     int dev = 0, sms = 0, per_sm = 0;
     FSB_CUDA_TRY(cudaGetDevice(&dev));
@@ -911,26 +931,34 @@ int launch_tau_k(const fsb_index *idx, const InterpConsts &c, const ItemPlan &pl
         count_launch();
         kern<<<grid, kTauThreads, smem, stream>>>(c, plan.items, n_items, next_item, idx->offsets, idx->particle, idx->dr2, idx->axis,
                                                   pos, vel, dens, temp, h, cells, out, plan.scratch_rows.as<double>(),
-                                                  plan.n_items * (int64_t) c.nbins, ctr);
+                                                  plan.n_items * (int64_t) c.nbins, ctr, chunk_done, host_flags, chunk_lines);
         FSB_CUDA_TRY(cudaGetLastError());
         return FSB_OK;
     };
     constexpr size_t smem64 = tau_smem_bytes<NL, false>(), smem32 = tau_smem_bytes<NL, true>();
+    // the row-streaming variant exists without counters only (the host one-shot entry never asks for them)
+    if (chunk_done && !ctr)
+        return precision == FSB_PRECISION_FP32 ? go(k_tau<KERNEL, NL, false, true, true>, smem32)
+                                               : go(k_tau<KERNEL, NL, false, false, true>, smem64);
+    if (chunk_done) {
+        set_error("launch_tau: row streaming and counters are exclusive");
+        return FSB_EINVAL;
+    }
     if (precision == FSB_PRECISION_FP32)
-        return ctr ? go(k_tau<KERNEL, NL, true, true>, smem32) : go(k_tau<KERNEL, NL, false, true>, smem32);
-    return ctr ? go(k_tau<KERNEL, NL, true, false>, smem64) : go(k_tau<KERNEL, NL, false, false>, smem64);
+        return ctr ? go(k_tau<KERNEL, NL, true, true, false>, smem32) : go(k_tau<KERNEL, NL, false, true, false>, smem32);
+    return ctr ? go(k_tau<KERNEL, NL, true, false, false>, smem64) : go(k_tau<KERNEL, NL, false, false, false>, smem64);
 }
 
 template <int NL>
 int launch_tau_nl(const fsb_index *idx, const InterpConsts &c, const ItemPlan &plan, int *next_item, const float *pos,
                   const float *vel, const float *dens, const float *temp, const float *h, const float *cells, double *out,
-                  unsigned long long *ctr, int precision, cudaStream_t stream)
+                  unsigned long long *ctr, int precision, cudaStream_t stream, int *chunk_done, int *host_flags, int chunk_lines)
 {
     switch (c.kernel) {
-    case FSB_KERNEL_TOPHAT: return launch_tau_k<FSB_KERNEL_TOPHAT, NL>(idx, c, plan, next_item, pos, vel, dens, temp, h, cells, out, ctr, precision, stream);
-    case FSB_KERNEL_CUBIC: return launch_tau_k<FSB_KERNEL_CUBIC, NL>(idx, c, plan, next_item, pos, vel, dens, temp, h, cells, out, ctr, precision, stream);
-    case FSB_KERNEL_VORONOI: return launch_tau_k<FSB_KERNEL_VORONOI, NL>(idx, c, plan, next_item, pos, vel, dens, temp, h, cells, out, ctr, precision, stream);
-    case FSB_KERNEL_QUINTIC: return launch_tau_k<FSB_KERNEL_QUINTIC, NL>(idx, c, plan, next_item, pos, vel, dens, temp, h, cells, out, ctr, precision, stream);
+    case FSB_KERNEL_TOPHAT: return launch_tau_k<FSB_KERNEL_TOPHAT, NL>(idx, c, plan, next_item, pos, vel, dens, temp, h, cells, out, ctr, precision, stream, chunk_done, host_flags, chunk_lines);
+    case FSB_KERNEL_CUBIC: return launch_tau_k<FSB_KERNEL_CUBIC, NL>(idx, c, plan, next_item, pos, vel, dens, temp, h, cells, out, ctr, precision, stream, chunk_done, host_flags, chunk_lines);
+    case FSB_KERNEL_VORONOI: return launch_tau_k<FSB_KERNEL_VORONOI, NL>(idx, c, plan, next_item, pos, vel, dens, temp, h, cells, out, ctr, precision, stream, chunk_done, host_flags, chunk_lines);
+    case FSB_KERNEL_QUINTIC: return launch_tau_k<FSB_KERNEL_QUINTIC, NL>(idx, c, plan, next_item, pos, vel, dens, temp, h, cells, out, ctr, precision, stream, chunk_done, host_flags, chunk_lines);
     default: set_error("unknown kernel id %d", c.kernel); return FSB_EINVAL;
     }
 }
@@ -939,11 +967,25 @@ int launch_tau_nl(const fsb_index *idx, const InterpConsts &c, const ItemPlan &p
 
 int tau_max_fused_lines() { return kMaxTauLines; }
 
+namespace {
+struct PinnedFlags {  // zero-initialised ints in pinned, device-visible host memory
+    int *ptr = nullptr;
+    int alloc(size_t n)
+    {
+        FSB_CUDA_TRY(cudaHostAlloc(reinterpret_cast<void **>(&ptr), sizeof(int) * n, cudaHostAllocMapped | cudaHostAllocPortable));
+        for (size_t i = 0; i < n; ++i) ptr[i] = 0;
+        return FSB_OK;
+    }
+    ~PinnedFlags() { if (ptr) cudaFreeHost(ptr); }
+};
+}  // namespace
+
 // c.nlines (1..kMaxTauLines) lines of one ion in one pass; out[l][nlos][nbins].
 int launch_tau(const fsb_index *idx, const InterpConsts &c, const float *pos, const float *vel, const float *dens,
                const float *temp, const float *h, const float *cells, double *out, fsb_counters *counters, int precision,
-               cudaStream_t stream)
+               cudaStream_t stream, HostSink *sink)
 {
+    if (sink) sink->streamed = false;
     if (idx->nlos == 0 || idx->npairs == 0) return FSB_OK;
     if (precision != FSB_PRECISION_FP64 && precision != FSB_PRECISION_FP32) {
         set_error("launch_tau: unknown precision %d", precision);
@@ -959,9 +1001,68 @@ int launch_tau(const fsb_index *idx, const InterpConsts &c, const float *pos, co
     FSB_TRY(next_item.alloc(sizeof(int), stream));
     FSB_CUDA_TRY(cudaMemsetAsync(next_item.ptr, 0, sizeof(int), stream));
     unsigned long long *ctr = reinterpret_cast<unsigned long long *>(counters);
-    if (c.nlines == 1) FSB_TRY(launch_tau_nl<1>(idx, c, plan, next_item.as<int>(), pos, vel, dens, temp, h, cells, out, ctr, precision, stream));
-    else FSB_TRY(launch_tau_nl<2>(idx, c, plan, next_item.as<int>(), pos, vel, dens, temp, h, cells, out, ctr, precision, stream));
+    // streaming to the host: chunks of sightlines of about 16 MB per fused line
+    const size_t row_bytes = sizeof(double) * (size_t) c.nbins;
+    size_t chunk_bytes = (size_t) 16 << 20, min_lines = 64;
+    if (const char *env = getenv("FSB200_STREAM_CHUNK_BYTES")) {  // test hook: small chunks exercise the streaming path on small cases
+        chunk_bytes = (size_t) std::max(1ll, atoll(env));
+        min_lines = 1;
+    }
+    const int chunk_lines = (int) std::min<size_t>((size_t) idx->nlos, std::max<size_t>(min_lines, chunk_bytes / row_bytes));
+    const int nchunks = (idx->nlos + chunk_lines - 1) / chunk_lines;
+    const bool stream_out = sink && sink->host && !ctr && !plan.segmented && nchunks >= 4;
+    Scratch chunk_done;
+    PinnedFlags flags;
+    if (stream_out) {
+        FSB_TRY(chunk_done.alloc(sizeof(int) * (size_t) nchunks, stream));
+        FSB_CUDA_TRY(cudaMemsetAsync(chunk_done.ptr, 0, sizeof(int) * (size_t) nchunks, stream));
+        FSB_TRY(flags.alloc((size_t) nchunks));
+    }
+    int *cd = stream_out ? chunk_done.as<int>() : nullptr;
+    if (c.nlines == 1) FSB_TRY(launch_tau_nl<1>(idx, c, plan, next_item.as<int>(), pos, vel, dens, temp, h, cells, out, ctr, precision, stream, cd, flags.ptr, chunk_lines));
+    else FSB_TRY(launch_tau_nl<2>(idx, c, plan, next_item.as<int>(), pos, vel, dens, temp, h, cells, out, ctr, precision, stream, cd, flags.ptr, chunk_lines));
     FSB_TRY(reduce_items(plan, idx, c.nbins, c.nlines, out, stream));
+    if (stream_out) {
+        // follow the kernel: copy each chunk as soon as its flag is up; if the kernel ends first (or fails), the
+        // remaining chunks are copied after it in stream order
+        const volatile int *vf = flags.ptr;
+        cudaEvent_t kernel_done;
+        FSB_CUDA_TRY(cudaEventCreateWithFlags(&kernel_done, cudaEventDisableTiming));
+        FSB_CUDA_TRY(cudaEventRecord(kernel_done, stream));
+        bool finished = false;
+        int rc = FSB_OK;
+        for (int ch = 0; ch < nchunks && rc == FSB_OK; ++ch) {
+            unsigned spins = 0;
+            while (!finished && vf[ch] == 0) {
+                if ((++spins & 0x3ffu) == 0) {
+                    const cudaError_t q = cudaEventQuery(kernel_done);
+                    if (q == cudaSuccess) finished = true;
+                    else if (q != cudaErrorNotReady) {
+                        set_error("tau kernel failed while streaming rows: %s", cudaGetErrorString(q));
+                        rc = FSB_ECUDA;
+                        break;
+                    }
+                }
+            }
+            if (rc != FSB_OK) break;
+            if (finished) {
+                const cudaError_t w = cudaStreamWaitEvent(sink->copy_stream, kernel_done, 0);
+                if (w != cudaSuccess) { set_error("cudaStreamWaitEvent: %s", cudaGetErrorString(w)); rc = FSB_ECUDA; break; }
+            }
+            const int l0 = ch * chunk_lines, nl = std::min(chunk_lines, idx->nlos - l0);
+            for (int l = 0; l < c.nlines && rc == FSB_OK; ++l) {
+                const size_t off = ((size_t) l * (size_t) idx->nlos + (size_t) l0) * (size_t) c.nbins;
+                const cudaError_t e = cudaMemcpyAsync(sink->host + off, out + off, row_bytes * (size_t) nl, cudaMemcpyDeviceToHost, sink->copy_stream);
+                if (e != cudaSuccess) { set_error("cudaMemcpyAsync (row streaming): %s", cudaGetErrorString(e)); rc = FSB_ECUDA; }
+            }
+        }
+        cudaEventDestroy(kernel_done);
+        // flags and chunk counters are released below: wait for the kernel that writes them
+        const cudaError_t e = cudaStreamSynchronize(stream);
+        if (rc == FSB_OK && e != cudaSuccess) { set_error("tau kernel: %s", cudaGetErrorString(e)); rc = FSB_ECUDA; }
+        if (rc != FSB_OK) return rc;
+        sink->streamed = true;
+    }
     return FSB_OK;
 }
 

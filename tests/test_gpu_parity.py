@@ -309,3 +309,30 @@ def test_bad_axis_is_an_error_not_a_crash(priv):
     bad[2] = 4
     with pytest.raises(FsbError):
         interp(priv, 1, p, dict(d, axis=bad))
+
+
+@pytest.mark.parametrize("nlines", [1, 2])
+def test_host_entry_streams_rows_while_kernel_runs(priv, torch_cuda, monkeypatch, nlines):
+    """The host one-shot entry copies finished sightline rows to the host while the tau kernel is still
+    running (one flag per chunk of sightlines).  With small chunks forced, the streamed result must be
+    bit-identical to the device-resident path, including sightlines without any candidate particle."""
+    from fake_spectra_b200 import _lib, native
+    d = cases.random_case(nside=14, nlos=150, axis="cycle", seed=31)
+    d["cofm"][::7] = d["cofm"][3]                    # duplicate sightlines
+    d["h"][:] = np.minimum(d["h"], 0.35 * d["box"] / 14)  # small smoothing lengths: some lists are empty
+    p = cases.params(d)
+    lam_b, gam_b, fosc_b = cases.params(d, line="HI1025")["lambda_cm"], cases.params(d, line="HI1025")["gamma"], cases.params(d, line="HI1025")["fosc"]
+    extra = [(lam_b, gam_b, fosc_b)] if nlines == 2 else []
+    args = (1, p["nbins"], p["kernel"], p["box"], p["velfac"], p["atime"], p["lambda_cm"], p["gamma"], p["fosc"],
+            p["amumass"], p["tautail"], d["pos"], d["vel"], d["dens"], d["temp"], d["h"], d["axis"], d["cofm"])
+    one = 1 << 30  # one work item per sightline: rows are only streamed when no sightline is split
+    plain = priv._Particle_Interpolate(*args, extra_lines=extra, seg_pairs=one)
+    monkeypatch.setenv("FSB200_STREAM_CHUNK_BYTES", str(8 * p["nbins"] * 4))   # 4 sightlines per chunk
+    streamed = priv._Particle_Interpolate(*args, extra_lines=extra, seg_pairs=one)
+    assert np.array_equal(plain, streamed)
+    t = dev(torch_cuda, d)
+    idx = native.CandidateIndex(d["box"], t["cofm"], t["axis"], t["pos"], t["h"])
+    prms = [_lib.make_params(**p, seg_pairs=one)] + ([_lib.make_params(**cases.params(d, line="HI1025"), seg_pairs=one)] if nlines == 2 else [])
+    resident = idx.compute_tau(prms if nlines == 2 else prms[0], t["pos"], t["vel"], t["dens"], t["temp"], t["h"]).cpu().numpy()
+    assert np.array_equal(resident.reshape(streamed.shape), streamed)
+    assert (np.abs(streamed).reshape(-1, p["nbins"]).sum(axis=1) == 0).any(), "case should contain empty sightlines"
