@@ -283,6 +283,31 @@ def run_b200(args):
     except Exception:
         hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
 
+    # ---- row f2: the consumers of tau while it is still resident (HBM-bound streaming reductions) ----
+    flux_stats = None
+    if rank == 0:
+        from fake_spectra_b200 import fluxstatistics as fstat
+        flat = out.view(-1)
+        fstat.flux_sums(flat)  # warm-up
+        torch.cuda.synchronize()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        npass = 5
+        f0.record()
+        for _ in range(npass):
+            sums = fstat.flux_sums(flat)
+        f1.record()
+        torch.cuda.synchronize()
+        pass_s = f0.elapsed_time(f1) * 1e-3 / npass
+        t0 = time.perf_counter()
+        scale = fstat.mean_flux(out[0], 0.7)
+        torch.cuda.synchronize()
+        newton_s = time.perf_counter() - t0
+        flux_stats = {"bound": "hbm", "kernel": "k_flux_sums", "pixels": int(flat.numel()), "ms_per_pass": pass_s * 1e3,
+                      "algorithmic_bytes": 8.0 * flat.numel(), "achieved": 8.0 * flat.numel() / pass_s / 1e9, "peak": hbm_peak,
+                      "unit": "GB/s", "frac": 8.0 * flat.numel() / pass_s / 1e9 / hbm_peak,
+                      "mean_flux": sums[0] / max(sums[2], 1),
+                      "rescale_to_0.7": {"scale": scale, "ms": newton_s * 1e3, "pixels": int(out[0].numel())}}
+
     # ---- end to end through the reference-facing boundary: host buffers in, host buffer out ----
     e2e = None
     if not args.no_e2e:
@@ -375,6 +400,7 @@ def run_b200(args):
                             "achieved": index_bytes / index_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                             "frac": index_bytes / index_s / 1e9 / hbm_peak, "peak_source": hbm_src,
                             "share_of_step": index_s / (elapsed / args.steps)},
+            "flux_stats": flux_stats,
             "cpu_baseline": cpu, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "check_mean_tau": sanity,
         }

@@ -56,6 +56,13 @@ SIGNATURES = {
     "fsb_assign_cells": (C.c_int, [_P, C.c_double, _P, _P, _P, _P, _P]),
     "fsb_measure_fma_peak": (C.c_int, [C.c_int32, C.POINTER(C.c_double), _P]),
     "fsb_voigt_profile": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, _P]),
+    "fsb_rescale_mean_flux": (C.c_int, [_P, C.c_int64, C.c_double, C.c_double, C.c_double, C.POINTER(C.c_double),
+                                        C.POINTER(C.c_int32), _P]),
+    "fsb_flux_sums": (C.c_int, [_P, C.c_int64, C.c_double, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                C.POINTER(C.c_int64), _P]),
+    "fsb_flux_pdf": (C.c_int, [_P, C.c_int64, C.c_double, C.c_int32, _P, _P]),
+    "fsb_delta_flux": (C.c_int, [_P, C.c_int64, C.c_double, C.c_double, _P, _P]),
+    "fsb_power_accumulate": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_double, _P, _P]),
 }
 
 _lib = None

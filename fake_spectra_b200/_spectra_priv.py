@@ -106,3 +106,12 @@ def _near_lines(box, pos, hh, axis, cofm):
                                          _ptr(out), C.byref(count))
     _lib.check(rc, "_near_lines")
     return out[:count.value].copy()
+
+
+def _rescale_mean_flux(tau, mean_flux_desired, nbins, tol, thresh):
+    """Scale factor that brings the mean flux of ``tau`` (float64, first ``nbins`` elements) to
+    ``mean_flux_desired`` (Py_mean_flux, py_module.cpp:263-282: same arguments, same TypeError)."""
+    if not (isinstance(tau, np.ndarray) and tau.dtype == np.float64):
+        raise TypeError("Optical depth must have 64-bit float type")
+    from . import fluxstatistics
+    return fluxstatistics.mean_flux(np.ravel(np.ascontiguousarray(tau))[:int(nbins)], mean_flux_desired, tol, thresh)

@@ -1,0 +1,152 @@
+"""Flux statistics of optical depths: mean-flux rescaling, flux PDF and 1-D flux power spectrum
+(mirror of the reference's fluxstatistics.py:20-108, 197-215 on the device).
+
+Same function names, arguments and return values as the reference.  ``tau`` may be a numpy array
+(uploaded once) or a CUDA tensor that is already resident, e.g. what
+``native.CandidateIndex.compute_tau`` returns: nothing is copied back but the small results.  The
+reductions, the histogram and the |rfft|^2 accumulation are this library's kernels (fsb_stats.cu);
+the FFT itself is cuFFT through ``torch.fft.rfft``.  There is no CPU fallback.
+
+The 3-D flux power (nbodykit) is outside the hot path and not provided.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _lib
+
+
+def _device_tau(tau):
+    """tau as a contiguous float64 CUDA tensor (reference: tau.astype(np.float64), fluxstatistics.py:41)."""
+    import torch
+    if isinstance(tau, torch.Tensor):
+        if not tau.is_cuda:
+            tau = tau.cuda()
+        return tau.to(torch.float64).contiguous()
+    if not torch.cuda.is_available():
+        raise RuntimeError("fake_spectra_b200.fluxstatistics needs a CUDA device (no CPU fallback)")
+    return torch.from_numpy(np.ascontiguousarray(tau, dtype=np.float64)).cuda()
+
+
+def _stream():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def obs_mean_tau(redshift):
+    """Effective optical depth 0.0023 (1+z)^3.65 of 0711.1862 (fluxstatistics.py:20-23)."""
+    return 0.0023 * (1.0 + redshift) ** 3.65
+
+
+def mean_flux(tau, mean_flux_desired, tol=1e-5, thresh=1e30):
+    """Scale factor s with <exp(-s tau)> = mean_flux_desired over the pixels with tau <= thresh
+    (fluxstatistics.py:25-41 -> get_mean_flux_scale, py_module.cpp:235-262)."""
+    if np.size(tau) == 0 if not hasattr(tau, "numel") else tau.numel() == 0:
+        return 0
+    import torch
+    t = _device_tau(tau)
+    scale = C.c_double(0)
+    with torch.cuda.device(t.device):
+        rc = _lib.load().fsb_rescale_mean_flux(C.c_void_p(t.data_ptr()), t.numel(), float(mean_flux_desired), float(tol),
+                                               float(thresh), C.byref(scale), None, _stream())
+    _lib.check(rc, "fsb_rescale_mean_flux")
+    return scale.value
+
+
+def flux_pdf(tau, nbins=20, mean_flux_desired=None):
+    """Normalised histogram of the flux exp(-tau) on nbins equal bins of [0, 1]
+    (fluxstatistics.py:43-52): returns (bin centres, density)."""
+    import torch
+    t = _device_tau(tau)
+    scale = 1.
+    if mean_flux_desired is not None:
+        scale = mean_flux(t, mean_flux_desired)
+    counts = torch.zeros(int(nbins), dtype=torch.int64, device=t.device)
+    with torch.cuda.device(t.device):
+        rc = _lib.load().fsb_flux_pdf(C.c_void_p(t.data_ptr()), t.numel(), float(scale), int(nbins),
+                                      C.c_void_p(counts.data_ptr()), _stream())
+    _lib.check(rc, "fsb_flux_pdf")
+    counts = counts.cpu().numpy()
+    bins = np.arange(nbins + 1) / (1. * nbins)
+    # numpy.histogram(density=True): counts / total / bin width
+    fpdf = counts / np.diff(bins) / counts.sum()
+    cbins = (bins[1:] + bins[:-1]) / 2.
+    return cbins, fpdf
+
+
+def _powerspectrum(inarray, axis=-1):
+    """|rfft|^2 / n^2 along ``axis`` (fluxstatistics.py:54-61); device tensors stay on the device."""
+    import torch
+    if isinstance(inarray, torch.Tensor):
+        f = torch.fft.rfft(inarray, dim=axis)
+        return (f.real ** 2 + f.imag ** 2) / inarray.shape[axis] ** 2
+    t = _device_tau(inarray)
+    f = torch.fft.rfft(t, dim=axis)
+    return ((f.real ** 2 + f.imag ** 2) / t.shape[axis] ** 2).cpu().numpy()
+
+
+def _window_function(k, *, R, dv):
+    """Spectrograph response: Gaussian of FWHM R times the pixel sinc (fluxstatistics.py:63-72)."""
+    sigma = R / (2 * np.sqrt(2 * np.log(2)))
+    return np.exp(-0.5 * (k * sigma) ** 2) * np.sinc(k * dv / 2 / math.pi)
+
+
+def _flux_power_bins(vmax, npix):
+    """k of the rfft modes in s/km (fluxstatistics.py:197-215)."""
+    kf = np.fft.rfftfreq(npix)
+    return kf * 2.0 * math.pi * npix / vmax
+
+
+def flux_power(tau, vmax, spec_res=8, mean_flux_desired=None, window=False, batch=8192):
+    """Mean 1-D flux power spectrum of delta_F = exp(-tau)/<F> - 1 over the sightlines
+    (fluxstatistics.py:74-108): returns (k [s/km], P_F [km/s]), both of length npix//2 + 1.
+    Sightlines are processed in batches of ``batch`` to bound the rfft workspace."""
+    import torch
+    t = _device_tau(tau)
+    if t.dim() != 2:
+        raise ValueError("tau must have shape (NumLos, npix)")
+    nspec, npix = t.shape
+    lib = _lib.load()
+    scale = 1.
+    if mean_flux_desired is not None:
+        scale = mean_flux(t, mean_flux_desired)
+    else:
+        mean_flux_desired = _mean_exp(t)  # np.mean(np.exp(-tau)), fluxstatistics.py:96
+    nk = npix // 2 + 1
+    power = torch.zeros(nk, dtype=torch.float64, device=t.device)
+    dflux = torch.empty((min(batch, nspec), npix), dtype=torch.float64, device=t.device)
+    with torch.cuda.device(t.device):
+        for s0 in range(0, nspec, batch):
+            s1 = min(nspec, s0 + batch)
+            part = t[s0:s1]
+            out = dflux[: s1 - s0]
+            _lib.check(lib.fsb_delta_flux(C.c_void_p(part.data_ptr()), part.numel(), float(scale), float(mean_flux_desired),
+                                          C.c_void_p(out.data_ptr()), _stream()), "fsb_delta_flux")
+            f = torch.view_as_real(torch.fft.rfft(out, dim=1)).contiguous()
+            # vmax * |F|^2 / npix^2, averaged over all sightlines
+            _lib.check(lib.fsb_power_accumulate(C.c_void_p(f.data_ptr()), s1 - s0, nk, vmax / (1. * npix * npix) / nspec,
+                                                C.c_void_p(power.data_ptr()), _stream()), "fsb_power_accumulate")
+    mean_flux_power = power.cpu().numpy()
+    kf = _flux_power_bins(vmax, npix)
+    if window and spec_res > 0:
+        mean_flux_power /= _window_function(kf, R=spec_res, dv=vmax / npix) ** 2
+    return kf, mean_flux_power
+
+
+def flux_sums(tau, scale=1.0, thresh=1e30):
+    """(sum exp(-scale tau), sum tau exp(-scale tau), pixels used) over tau <= thresh: one pass of the
+    reduction behind mean_flux.  sum / used at scale 1 is the mean flux (spectra.py:1276)."""
+    import torch
+    t = _device_tau(tau)
+    sf, stf, used = C.c_double(0), C.c_double(0), C.c_int64(0)
+    with torch.cuda.device(t.device):
+        rc = _lib.load().fsb_flux_sums(C.c_void_p(t.data_ptr()), t.numel(), float(scale), float(thresh), C.byref(sf),
+                                       C.byref(stf), C.byref(used), _stream())
+    _lib.check(rc, "fsb_flux_sums")
+    return sf.value, stf.value, used.value
+
+
+def _mean_exp(t):
+    sf, _, used = flux_sums(t)
+    return sf / used if used else float("nan")

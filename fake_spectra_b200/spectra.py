@@ -649,6 +649,38 @@ class Spectra:
             ntau = ntau[number, :]
         return ntau
 
+    # -- flux statistics (spectra.py:1254-1301): the reductions run on the device, fluxstatistics.py ------
+    def _filter_tau(self, tau, tau_thresh=None):
+        """The reference masks damped absorbers here (spectra.py:1254-1270); that filter is outside the
+        hot path and not provided: only tau_thresh=None is accepted."""
+        if tau_thresh is not None:
+            raise NotImplementedError("tau_thresh filtering of damped absorbers is not provided")
+        return tau
+
+    def get_mean_flux(self, elem="H", ion=1, line=1215, tau_thresh=None):
+        """Mean flux <exp(-tau)> along the sightlines (spectra.py:1272-1276)."""
+        from . import fluxstatistics as fstat
+        tau = self._filter_tau(self.get_tau(elem, ion, line), tau_thresh=tau_thresh)
+        sf, _, used = fstat.flux_sums(tau)
+        return sf / used
+
+    def get_flux_pdf(self, elem="H", ion=1, line=1215, nbins=20, mean_flux_desired=None, tau_thresh=None):
+        """Flux PDF: (bin centres, normalised histogram of exp(-tau)) (spectra.py:1278-1282)."""
+        from . import fluxstatistics as fstat
+        tau = self._filter_tau(self.get_tau(elem, ion, line), tau_thresh=tau_thresh)
+        return fstat.flux_pdf(tau, nbins=nbins, mean_flux_desired=mean_flux_desired)
+
+    def get_flux_power_1D(self, elem="H", ion=1, line=1215, mean_flux_desired=None, window=False, tau_thresh=None):
+        """1-D power spectrum of delta_F = exp(-tau)/<F> - 1 averaged over the sightlines, without the k = 0
+        mode: (k [s/km], P_F [km/s]) (spectra.py:1284-1301)."""
+        from . import fluxstatistics as fstat
+        tau = self._filter_tau(self.get_tau(elem, ion, line), tau_thresh=tau_thresh)
+        if mean_flux_desired is not None and window is True and self.spec_res > 0:
+            raise ValueError("Cannot sensibly rescale mean flux with gaussian smoothing")
+        kf, avg_flux_power = fstat.flux_power(tau, self.vmax, spec_res=self.spec_res, mean_flux_desired=mean_flux_desired,
+                                              window=window)
+        return kf[1:], avg_flux_power[1:]
+
     def get_cofm(self, num=None):
         """Find a bunch more sightlines: should be overridden by child classes"""
         raise NotImplementedError

@@ -172,6 +172,29 @@ FSB_API int fsb_assign_cells(const fsb_index *idx, double box, const double *cof
  * else FP32: 8 independent chains per thread, best of several launches.  Synchronous. */
 FSB_API int fsb_measure_fma_peak(int32_t fp64, double *tflops, void *stream);
 
+/* ---- flux statistics on device-resident tau ----------------------------- */
+/* Replaces get_mean_flux_scale / _rescale_mean_flux (py_module.cpp:235-282): the factor s with
+ * mean(exp(-s tau)) = mean_flux_desired over the pixels with tau <= thresh, by the reference's Newton
+ * iteration (same update, same clamp, same stopping rule |ds| <= tol s).  tau: n DEVICE doubles;
+ * *scale_out and *iterations (may be NULL) are HOST.  n == 0 gives 0 (fluxstatistics.py:39-40).
+ * Synchronises `stream` once per iteration. */
+FSB_API int fsb_rescale_mean_flux(const double *tau, int64_t n, double mean_flux_desired, double tol, double thresh,
+                          double *scale_out, int32_t *iterations, void *stream);
+/* One evaluation of the sums of that iteration, over the pixels with tau <= thresh: sum exp(-scale tau),
+ * sum tau exp(-scale tau) and their number (HOST outputs).  The mean flux of Spectra.get_mean_flux
+ * (spectra.py:1272-1276) is sum_flux / used at scale 1.  Synchronises `stream`. */
+FSB_API int fsb_flux_sums(const double *tau, int64_t n, double scale, double thresh, double *sum_flux, double *sum_tau_flux,
+                  int64_t *used, void *stream);
+/* counts[nbins] (DEVICE, overwritten) = histogram of exp(-scale tau) on nbins equal bins of [0, 1] with
+ * numpy.histogram's edge rules: the counts behind fluxstatistics.flux_pdf (fluxstatistics.py:43-52). */
+FSB_API int fsb_flux_pdf(const double *tau, int64_t n, double scale, int32_t nbins, uint64_t *counts, void *stream);
+/* out[i] = exp(-scale tau[i]) / mean_flux - 1 (fluxstatistics.py:100), DEVICE arrays. */
+FSB_API int fsb_delta_flux(const double *tau, int64_t n, double scale, double mean_flux, double *out, void *stream);
+/* power[k] += factor * sum_s (re^2 + im^2) of rfft_interleaved[s][k] (nspec x nk complex doubles, DEVICE):
+ * the accumulation of fluxstatistics.py:54-61,102-104 for one batch of sightlines. */
+FSB_API int fsb_power_accumulate(const double *rfft_interleaved, int64_t nspec, int32_t nk, double factor, double *power,
+                         void *stream);
+
 /* ---- Voigt profile, for tests ------------------------------------------------------------- */
 /* out[i] = Re w(x[i] + i y[i]) (singleabs.h:56-61) with the strategy `voigt` (FSB_VOIGT_*). */
 FSB_API int fsb_voigt_profile(const double *x, const double *y, double *out, int64_t n, int32_t voigt, void *stream);

@@ -124,6 +124,8 @@ class Oracle(_Base):
         lib.fso_assign_cells.argtypes = [_f64p, _i32p, C.c_double, C.c_int, _i32p, C.c_int, _f32p, _f32p]
         lib.fso_assign_cells.restype = C.c_int
         lib.fso_omp_max_threads.restype = C.c_int
+        lib.fso_mean_flux_scale.argtypes = [_f64p, C.c_double, C.c_longlong, C.c_double, C.c_double, C.POINTER(C.c_int)]
+        lib.fso_mean_flux_scale.restype = C.c_double
 
     def _call_tau(self, *a):
         import time
@@ -165,6 +167,15 @@ class Oracle(_Base):
 
     def tau_kern_outer(self, btherm, vdr2, vsmooth, aa, kernel, vlow, vhigh):
         return self.lib.fso_tau_kern_outer_pub(btherm, vdr2, vsmooth, aa, kernel, vlow, vhigh)
+
+    def mean_flux_scale(self, tau, mean_flux_desired, tol=1e-5, thresh=1e30, return_iterations=False):
+        """get_mean_flux_scale, py_module.cpp:235-262 (0 for an empty array: fluxstatistics.py:39-40)."""
+        tau = _f64(np.ravel(tau))
+        if tau.size == 0:
+            return (0.0, 0) if return_iterations else 0.0
+        it = C.c_int(0)
+        s = float(self.lib.fso_mean_flux_scale(tau, float(mean_flux_desired), tau.size, float(tol), float(thresh), C.byref(it)))
+        return (s, it.value) if return_iterations else s
 
     def near_particles(self, cofm, axis, box, pos, h):
         """-> (offsets int64[nlos+1], particle int32[npairs], dr2 float64[npairs])."""

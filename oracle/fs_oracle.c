@@ -840,3 +840,33 @@ int fso_compute_colden(int nbins, double lambda, double gamma, double fosc, doub
 
 int fso_omp_max_threads(void) { return omp_get_max_threads(); }
 void fso_omp_set_threads(int n) { omp_set_num_threads(n); }
+
+/* ------------------------------------------------------------------------------------------
+ * Mean-flux rescaling.  ref: py_module.cpp:235-262 (get_mean_flux_scale):
+ * Newton-Raphson on the scale s so that mean(exp(-s tau)) over the pixels with tau <= thresh equals
+ * the desired mean flux.  Pinned by the reference's own known answers (tests/test_statistics.py:8-19,
+ * restated in tests/test_oracle_stats.py).
+ * ---------------------------------------------------------------------------------------- */
+double fso_mean_flux_scale(const double *tau, double mean_flux_desired, long long nbins, double tol, double thresh,
+                           int *iterations)
+{
+    double scale, newscale = 1;
+    int it = 0;
+    do {
+        scale = newscale;
+        double mean_flux = 0, tau_mean_flux = 0;
+        long long nbins_used = 0;
+        for (long long i = 0; i < nbins; i++) {
+            if (tau[i] > thresh) continue;
+            const double temp = exp(-scale * tau[i]);
+            mean_flux += temp;
+            tau_mean_flux += temp * tau[i];
+            nbins_used++;
+        }
+        newscale = scale + (mean_flux - mean_flux_desired * nbins_used) / tau_mean_flux;
+        if (newscale <= 0) newscale = 1e-10;
+        ++it;
+    } while (fabs(newscale - scale) > tol * newscale && it < 100000);
+    if (iterations) *iterations = it;
+    return newscale;
+}
