@@ -17,8 +17,38 @@ namespace fsb {
 namespace {
 
 constexpr int kStatThreads = 256;
-constexpr int kStatBlocksPerSM = 8;
+constexpr int kStatBlocksPerSM = 6;  // 256 threads x 40 registers: six CTAs are resident per SM
 constexpr int kMaxStatBlocks = 148 * kStatBlocksPerSM * 2;  // room for larger parts
+
+// exp(t) for t <= 0 (fluxes): t = (64 e + j) ln2/64 + r with |r| <= ln2/128, exp(t) = 2^e 2^(j/64) exp(r); 2^(j/64)
+// from a 64-entry table staged in shared memory, exp(r) by its degree-5 Taylor polynomial (remainder 3e-17).
+// About 10 FP64 instructions instead of the library routine's ~30, which would make these streaming passes
+// FP64-bound instead of HBM-bound.  Within 1.5 ulp; results below 1e-300 flush to zero.
+__device__ const double d_exp2_64[64] = {1.00000000000000000e+00, 1.01088928605170048e+00, 1.02189714865411663e+00, 1.03302487902122841e+00, 1.04427378242741375e+00, 1.05564517836055716e+00, 1.06714040067682370e+00, 1.07876079775711986e+00, 1.09050773266525769e+00, 1.10238258330784089e+00, 1.11438674259589243e+00, 1.12652161860824185e+00, 1.13878863475669156e+00, 1.15118922995298267e+00, 1.16372485877757748e+00, 1.17639699165028122e+00, 1.18920711500272103e+00, 1.20215673145270308e+00, 1.21524735998046896e+00, 1.22848053610687002e+00, 1.24185781207348400e+00, 1.25538075702469110e+00, 1.26905095719173322e+00, 1.28287001607877826e+00, 1.29683955465100964e+00, 1.31096121152476441e+00, 1.32523664315974132e+00, 1.33966752405330292e+00, 1.35425554693689265e+00, 1.36900242297459052e+00, 1.38390988196383202e+00, 1.39897967253831124e+00, 1.41421356237309515e+00, 1.42961333839197002e+00, 1.44518080697704665e+00, 1.46091779418064704e+00, 1.47682614593949935e+00, 1.49290772829126484e+00, 1.50916442759342284e+00, 1.52559815074453842e+00, 1.54221082540794074e+00, 1.55900440023783693e+00, 1.57598084510788650e+00, 1.59314215134226700e+00, 1.61049033194925428e+00, 1.62802742185734783e+00, 1.64575547815396495e+00, 1.66367658032673638e+00, 1.68179283050742900e+00, 1.70010635371852348e+00, 1.71861929812247793e+00, 1.73733383527370622e+00, 1.75625216037329945e+00, 1.77537649252652119e+00, 1.79470907500310717e+00, 1.81425217550039886e+00, 1.83400808640934243e+00, 1.85397912508338547e+00, 1.87416763411029996e+00, 1.89457598158696561e+00, 1.91520656139714740e+00, 1.93606179349229435e+00, 1.95714412417540018e+00, 1.97845602638795093e+00};
+
+__device__ __forceinline__ void stage_exp_table(double *tab)
+{
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) tab[i] = d_exp2_64[i];
+    __syncthreads();
+}
+
+__device__ __forceinline__ double exp_nonpos(double t, const double *__restrict__ tab)
+{
+    const double magic = 6755399441055744.0;  // 1.5 * 2^52
+    double kd = fma(t, 9.23324826168936567683e+01, magic);
+    const int ki = __double2loint(kd);
+    kd -= magic;
+    double r = fma(kd, -1.08304246950865490362e-02, t);
+    r = fma(kd, -1.16259642343943700740e-12, r);
+    double p = fma(r, 1.0 / 120, 1.0 / 24);
+    p = fma(p, r, 1.0 / 6);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    const double v = p * tab[ki & 63];
+    const double scaled = __hiloint2double(__double2hiint(v) + ((ki >> 6) << 20), __double2loint(v));
+    return t < -690.0 ? 0.0 : (t > 0.0 ? exp(t) : scaled);  // t > 0 (negative tau) never happens for optical depths
+}
 
 struct FluxSums {
     double flux, tau_flux;     // sum exp(-s tau), sum tau exp(-s tau) over pixels with tau <= thresh
@@ -37,31 +67,41 @@ __device__ __forceinline__ void warp_reduce(double &a, double &b, unsigned long 
 
 // One Newton step's sums.  Each CTA owns a contiguous slab of pixels (coalesced 16-byte loads) and
 // writes one partial; k_flux_sums_final adds the partials in index order.
-__global__ void __launch_bounds__(kStatThreads)
+__global__ void __launch_bounds__(kStatThreads, kStatBlocksPerSM)
 k_flux_sums(const double *__restrict__ tau, int64_t n, double scale, double thresh, FluxSums *__restrict__ partial)
 {
-    const int64_t per_block = ((n + gridDim.x - 1) / gridDim.x + 1) & ~1ll;  // even: keeps double2 alignment
-    const int64_t beg = (int64_t) blockIdx.x * per_block, end = min(n, beg + per_block);
+    __shared__ double etab[64];
+    stage_exp_table(etab);
     double f = 0, tf = 0;
     unsigned long long used = 0;
     auto add = [&](double t) {
         if (t > thresh) return;
-        const double e = exp(-scale * t);
+        const double e = exp_nonpos(-scale * t, etab);
         f += e;
         tf = fma(e, t, tf);
         ++used;
     };
+    // grid-stride over 16-byte pairs, four loads in flight per thread; the element-to-thread map depends only on
+    // (n, grid), so the partial sums are reproducible
     const bool aligned = (reinterpret_cast<uintptr_t>(tau) & 15u) == 0;
-    if (aligned) {
-        const double2 *t2 = reinterpret_cast<const double2 *>(tau);
-        for (int64_t i = beg / 2 + threadIdx.x; 2 * i + 1 < end; i += kStatThreads) {
-            const double2 v = t2[i];
-            add(v.x);
-            add(v.y);
+    const int64_t head = aligned ? 0 : (n > 0 ? 1 : 0);       // one scalar element brings the rest to 16 bytes
+    const double2 *t2 = reinterpret_cast<const double2 *>(tau + head);
+    const int64_t n2 = (n - head) / 2, stride = (int64_t) gridDim.x * kStatThreads;
+    for (int64_t i = (int64_t) blockIdx.x * kStatThreads + threadIdx.x; i < n2; i += 4 * stride) {
+        double2 v[4];
+        #pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = i + u * stride < n2 ? t2[i + u * stride] : make_double2(INFINITY, INFINITY);
+        #pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (i + u * stride < n2) {
+                add(v[u].x);
+                add(v[u].y);
+            }
         }
-        if (threadIdx.x == 0 && ((end - beg) & 1) && end > beg) add(tau[end - 1]);
-    } else {
-        for (int64_t i = beg + threadIdx.x; i < end; i += kStatThreads) add(tau[i]);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (head) add(tau[0]);
+        if ((n - head) & 1) add(tau[n - 1]);
     }
     __shared__ double sf[kStatThreads / 32], stf[kStatThreads / 32];
     __shared__ unsigned long long su[kStatThreads / 32];
@@ -91,13 +131,14 @@ __global__ void __launch_bounds__(kStatThreads)
 k_flux_hist(const double *__restrict__ tau, int64_t n, double scale, int nbins, unsigned long long *__restrict__ counts)
 {
     extern __shared__ unsigned int hist[];
+    __shared__ double etab[64];
     for (int b = threadIdx.x; b < nbins; b += kStatThreads) hist[b] = 0;
-    __syncthreads();
+    stage_exp_table(etab);
     const double nb = (double) nbins;
     // shared counters are 32-bit: flush every 2^31 / threads pixels per thread at the latest (never reached:
     // a CTA sees n / gridDim pixels)
     for (int64_t i = (int64_t) blockIdx.x * kStatThreads + threadIdx.x; i < n; i += (int64_t) gridDim.x * kStatThreads) {
-        const double x = exp(-scale * tau[i]);
+        const double x = exp_nonpos(-scale * tau[i], etab);
         if (!(x >= 0.0 && x <= 1.0)) continue;
         int k = (int) (x * nb / 1.0);
         if (k == nbins) --k;
@@ -113,8 +154,10 @@ k_flux_hist(const double *__restrict__ tau, int64_t n, double scale, int nbins, 
 __global__ void __launch_bounds__(kStatThreads)
 k_delta_flux(const double *__restrict__ tau, int64_t n, double scale, double inv_mean, double *__restrict__ out)
 {
+    __shared__ double etab[64];
+    stage_exp_table(etab);
     for (int64_t i = (int64_t) blockIdx.x * kStatThreads + threadIdx.x; i < n; i += (int64_t) gridDim.x * kStatThreads)
-        out[i] = exp(-scale * tau[i]) * inv_mean - 1.0;
+        out[i] = exp_nonpos(-scale * tau[i], etab) * inv_mean - 1.0;
 }
 
 // partial[y][k] = sum over the y-th slab of spectra of |F[s][k]|^2, F interleaved (re, im) as produced by an
@@ -147,6 +190,7 @@ k_power_final(const double *__restrict__ partial, int nslabs, int nk, double fac
     power[k] += factor * acc;
 }
 
+// One wave of resident CTAs (grid-stride kernels): SMs x kStatBlocksPerSM, fewer for small inputs.
 int stat_grid(int64_t n)
 {
     int dev = 0, sms = 148;
