@@ -283,6 +283,30 @@ def run_b200(args):
     except Exception:
         hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
 
+    # ---- column density (K3) on the same index and particles: one weight column, then three in one pass ----
+    colden = None
+    if rank == 0 and not pshard:
+        idx = native.CandidateIndex(w["box"], t["cofm"], t["axis"], t["pos"], t["h"])
+        cout = out[0]
+        ctr = torch.zeros(10, dtype=torch.int64, device=dev)
+        idx.compute_colden(params[0], t["pos"], t["dens"], t["h"], out=cout.zero_(), counters=ctr)
+        torch.cuda.synchronize()
+        cpix = int(ctr.cpu()[1])
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(3):
+            idx.compute_colden(params[0], t["pos"], t["dens"], t["h"], out=cout)
+        c1.record()
+        torch.cuda.synchronize()
+        col_s = c0.elapsed_time(c1) * 1e-3 / 3
+        colden = {"kernel": "k_colden", "ms": col_s * 1e3, "pairs_per_s": idx.npairs / col_s, "pixels": cpix,
+                  "kernel_integrals_per_s": cpix / col_s,
+                  "note": "one weight column, accumulate into a resident [nlos, nbins] array; each pixel integral is a "
+                          "9-node trapezoid of the SPH kernel (absorption.cpp:53-74)"}
+        idx.free()
+        out.zero_()
+        step()  # restore tau in `out` for the statistics below
+
     # ---- row f2: the consumers of tau while it is still resident (HBM-bound streaming reductions) ----
     flux_stats = None
     if rank == 0:
@@ -400,7 +424,7 @@ def run_b200(args):
                             "achieved": index_bytes / index_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                             "frac": index_bytes / index_s / 1e9 / hbm_peak, "peak_source": hbm_src,
                             "share_of_step": index_s / (elapsed / args.steps)},
-            "flux_stats": flux_stats,
+            "colden": colden, "flux_stats": flux_stats,
             "cpu_baseline": cpu, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "check_mean_tau": sanity,
         }

@@ -116,14 +116,12 @@ template <int NL> struct FSlabSize {
 #ifndef FSB_TAU_NODE_GROUP
 #define FSB_TAU_NODE_GROUP 7
 #endif
-template <int NL> struct NearCoefs {
-    double2 a01[NL], a23[NL], p01[NL], p23[NL];
-};
-
+// One group of N nodes starting at node I0: table lookups in flight together, then the kernel-weighted table
+// value g[] and Gaussian uw[], then each fused line in turn (its coefficient pairs are loaded inside the loop and
+// a compiler barrier keeps the next line's loads from being hoisted: registers, not latency, are short here).
 template <int NL, int I0, int N, bool GAUSS>
 __device__ __forceinline__ void near_group(double xb, double step, const double *__restrict__ sl, const double *__restrict__ tab,
-                                           const NearCoefs<NL> &c, double &u, double &r, double q, unsigned lmask,
-                                           double (&acc)[NL], double (&acc2)[NL])
+                                           double &u, double &r, double q, unsigned lmask, double (&acc)[NL])
 {
     double t[N], g[N];
     {
@@ -177,15 +175,26 @@ __device__ __forceinline__ void near_group(double xb, double step, const double 
     #pragma unroll
     for (int l = 0; l < NL; ++l) {
         if (NL > 1 && !((lmask >> l) & 1u)) continue;
-        #pragma unroll
-        for (int i = 0; i < N; ++i) {
-            const double A = fma(fma(fma(c.a23[l].y, t[i], c.a23[l].x), t[i], c.a01[l].y), t[i], c.a01[l].x);
-            acc2[l] = fma(g[i], A, acc2[l]);
-            if (GAUSS) {
-                const double Pe = fma(fma(fma(c.p23[l].y, t[i], c.p23[l].x), t[i], c.p01[l].y), t[i], c.p01[l].x);
-                acc[l] = fma(uw[i], Pe, acc[l]);
+        const double2 a01 = LF2(l, L_A0), a23 = LF2(l, L_A0 + 2);
+        double a = acc[l], a2 = 0;
+        if (GAUSS) {
+            const double2 p01 = LF2(l, L_PE0), p23 = LF2(l, L_PE0 + 2);
+            #pragma unroll
+            for (int i = 0; i < N; ++i) {
+                const double A = fma(fma(fma(a23.y, t[i], a23.x), t[i], a01.y), t[i], a01.x);
+                const double Pe = fma(fma(fma(p23.y, t[i], p23.x), t[i], p01.y), t[i], p01.x);
+                a = fma(uw[i], Pe, a);
+                a2 = fma(g[i], A, a2);
+            }
+        } else {
+            #pragma unroll
+            for (int i = 0; i < N; ++i) {
+                const double A = fma(fma(fma(a23.y, t[i], a23.x), t[i], a01.y), t[i], a01.x);
+                a2 = fma(g[i], A, a2);
             }
         }
+        acc[l] = a + a2;
+        if (NL > 1) asm volatile("" ::: "memory");
     }
 }
 
@@ -195,25 +204,25 @@ __device__ __forceinline__ void node_sum_near_g(double xb, double step, const do
 {
     static_assert(FSB_GTAB_DEG == 7 && FSB_GTAB_STRIDE == 6, "written for the 48-byte degree-7 table");
     constexpr int G = FSB_TAU_NODE_GROUP;
-    NearCoefs<NL> c;
-    double acc[NL], acc2[NL], cd[NL];
+    double acc[NL];
     #pragma unroll
-    for (int l = 0; l < NL; ++l) {
-        c.a01[l] = LF2(l, L_A0), c.a23[l] = LF2(l, L_A0 + 2);
-        if (GAUSS) c.p01[l] = LF2(l, L_PE0), c.p23[l] = LF2(l, L_PE0 + 2);
-        // sum_i kw_i B(s_i): a quartic in xb
-        const double2 b01 = LF2(l, L_BQ0), b23 = LF2(l, L_BQ0 + 2), b4c = LF2(l, L_BQ0 + 4);
-        acc[l] = fma(fma(fma(fma(b4c.x, xb, b23.y), xb, b23.x), xb, b01.y), xb, b01.x);
-        acc2[l] = 0;
-        cd[l] = b4c.y;
-    }
+    for (int l = 0; l < NL; ++l) acc[l] = 0;
     double u = U0, r = R;
-    near_group<NL, 0, (G < 7 ? G : 7), GAUSS>(xb, step, sl, tab, c, u, r, q, lmask, acc, acc2);
-    if (G < 7) near_group<NL, (G < 7 ? G : 0), (G < 7 ? (7 - G < G ? 7 - G : G) : 1), GAUSS>(xb, step, sl, tab, c, u, r, q, lmask, acc, acc2);
-    if (2 * G < 7) near_group<NL, (2 * G < 7 ? 2 * G : 0), (2 * G < 7 ? 7 - 2 * G : 1), GAUSS>(xb, step, sl, tab, c, u, r, q, lmask, acc, acc2);
+    near_group<NL, 0, (G < 7 ? G : 7), GAUSS>(xb, step, sl, tab, u, r, q, lmask, acc);
+    if (G < 7) near_group<NL, (G < 7 ? G : 0), (G < 7 ? (7 - G < G ? 7 - G : G) : 1), GAUSS>(xb, step, sl, tab, u, r, q, lmask, acc);
+    if (2 * G < 7) near_group<NL, (2 * G < 7 ? 2 * G : 0), (2 * G < 7 ? 7 - 2 * G : 1), GAUSS>(xb, step, sl, tab, u, r, q, lmask, acc);
     static_assert(3 * G >= 7, "FSB_TAU_NODE_GROUP must be at least 3");
     #pragma unroll
-    for (int l = 0; l < NL; ++l) tot[l] = (NL > 1 && !((lmask >> l) & 1u)) ? 0.0 : cd[l] * (acc[l] + acc2[l]);
+    for (int l = 0; l < NL; ++l) {
+        if (NL > 1 && !((lmask >> l) & 1u)) {
+            tot[l] = 0;
+            continue;
+        }
+        // sum_i kw_i B(s_i): a quartic in xb; then the line amplitude
+        const double2 b01 = LF2(l, L_BQ0), b23 = LF2(l, L_BQ0 + 2), b4c = LF2(l, L_BQ0 + 4);
+        const double bq = fma(fma(fma(fma(b4c.x, xb, b23.y), xb, b23.x), xb, b01.y), xb, b01.x);
+        tot[l] = b4c.y * (acc[l] + bq);
+    }
 }
 
 template <int NL>
