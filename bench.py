@@ -65,6 +65,8 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2_grid256_lya_lyb", choices=sorted(WORKLOADS))
     ap.add_argument("--voigt", default="fast", choices=["fast", "exact"])
+    ap.add_argument("--precision", default="fp64", choices=["fp64", "fp32"],
+                    help="fp32 = the optional fast path (node sums in single precision, flux within 1e-5 of the reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -141,11 +143,12 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm), "power_w_max": max(power) if power else None}
 
 
-def make_params(w, line, voigt):
+def make_params(w, line, voigt, precision="fp64"):
     from fake_spectra_b200 import _lib
     lam, gam, fosc, amu = LINES[line]
     return _lib.make_params(w["nbins"], w["kernel"], w["box"], w["velfac"], w["atime"], lam, gam, fosc, amu, TAUTAIL,
-                            voigt=_lib.VOIGT_EXACT if voigt == "exact" else _lib.VOIGT_FAST)
+                            voigt=_lib.VOIGT_EXACT if voigt == "exact" else _lib.VOIGT_FAST,
+                            precision=_lib.PRECISION_FP32 if precision == "fp32" else _lib.PRECISION_FP64)
 
 
 def run_b200(args):
@@ -191,11 +194,16 @@ def run_b200(args):
 
     w = build_workload(args.workload, rank, world)
     nlines = len(w["lines"])
-    params = [make_params(w, ln, args.voigt) for ln in w["lines"]]
+    params = [make_params(w, ln, args.voigt, args.precision) for ln in w["lines"]]
+    fp32 = args.precision == "fp32"
+    # FP32 fast path, NEAR route with Gaussian, per Voigt evaluation: node x 1 FFMA, table index 2 FFMA + 1 FADD,
+    # degree-3 table Horner 3 FFMA, x^2 1 FMUL, exp(-x^2) 1 FMUL + 1 MUFU (counted 2), A 2 FFMA, Pe 2 FFMA,
+    # combine 1 FMUL + 2 FFMA = 12 FFMA + 6 = 30 flop; each further fused line A, Pe, combine = 6 FFMA + 1 = 13 flop
+    flop_first, flop_fused = (30.0, 13.0) if fp32 else (FLOP_PER_VOIGT, FLOP_PER_VOIGT_FUSED)
     names = ("pos", "vel", "dens", "temp", "h", "cofm", "axis")
     t = {k: torch.from_numpy(w[k]).to(dev) for k in names}
     out = torch.zeros((nlines, w["nlos"], w["nbins"]), dtype=torch.float64, device=dev)
-    fp64_peak = native.measure_fma_peak(True)
+    fp64_peak = native.measure_fma_peak(not fp32)  # the FMA peak of the precision the node sums run in
 
     tau_ms = []
     pshard = w["shard"] == "particles"
@@ -238,7 +246,7 @@ def run_b200(args):
         n_voigt_line.append(int(c[2]))
         routes += c[4:9]
     n_voigt_step = int(sum(n_voigt_line))
-    algo_flop_step = FLOP_PER_VOIGT * max(n_voigt_line) + FLOP_PER_VOIGT_FUSED * (n_voigt_step - max(n_voigt_line))
+    algo_flop_step = flop_first * max(n_voigt_line) + flop_fused * (n_voigt_step - max(n_voigt_line))
     step()
     for _ in range(max(args.warmup - 1, 0)):
         step()
@@ -340,12 +348,13 @@ def run_b200(args):
         lam, gam, fosc, amu = LINES[w["lines"][0]]
         extra = [LINES[ln][:3] for ln in w["lines"][1:]]
         vg = _lib.VOIGT_EXACT if args.voigt == "exact" else _lib.VOIGT_FAST
+        prec = _lib.PRECISION_FP32 if fp32 else _lib.PRECISION_FP64
 
         def e2e_step_host():
             return _spectra_priv._Particle_Interpolate(
                 1, w["nbins"], w["kernel"], w["box"], w["velfac"], w["atime"], lam, gam, fosc, amu, TAUTAIL,
                 pin["pos"].numpy(), pin["vel"].numpy(), pin["dens"].numpy(), pin["temp"].numpy(), pin["h"].numpy(),
-                pin["axis"].numpy(), pin["cofm"].numpy(), voigt=vg, out=hout.numpy(), extra_lines=extra)
+                pin["axis"].numpy(), pin["cofm"].numpy(), voigt=vg, precision=prec, out=hout.numpy(), extra_lines=extra)
 
         def e2e_step_pshard():
             # particle-sharded: upload this rank's particles, interpolate all sightlines, sum over ranks
@@ -396,8 +405,9 @@ def run_b200(args):
         line = {
             "metric": "spectra_per_s", "value": value, "unit": "spectra/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "vs_baseline": None, "dtype": "f32" if fp32 else "f64", "data": "synthetic",
             "config": {"workload": args.workload, "particles": int(w["npart"]), "sightlines_per_gpu": int(w["nlos"]),
+                       "precision": args.precision,
                        "pixels": int(w["nbins"]), "pixel_kms": w["res"], "lines": list(w["lines"]), "sph_kernel": {0: "tophat", 1: "cubic", 2: "voronoi", 3: "quintic"}[w["kernel"]],
                        "voigt": args.voigt,
                        "parallelism": ("particle-sharded x%d (%d cells per rank), NCCL all-reduce of the FP64 tau array each step"
@@ -407,13 +417,13 @@ def run_b200(args):
                        "step": "index build + tau of all lines for every sightline, inputs resident in HBM"},
             "pairs_per_s": pairs_per_s, "pairs_per_step": total_pairs, "voigt_evals_per_step": n_voigt_step * world,
             "voigt_evals_per_s": n_voigt_step * world * args.steps / elapsed,
-            "roofline": {"bound": "fp64", "kernel": "k_tau", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+            "roofline": {"bound": "fp32" if fp32 else "fp64", "kernel": "k_tau", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": achieved / fp64_peak, "traffic": traffic,
-                         "note": "algorithmic FP64 flop of this library's profile evaluation (DESIGN.md 5): %.0f per Voigt "
+                         "note": ("algorithmic FP32 flop" if fp32 else "algorithmic FP64 flop") + " of this library's profile evaluation (DESIGN.md 5): %.0f per Voigt "
                                  "evaluation of the first line + %.0f per evaluation of each fused line = %.3e flop per launch / "
                                  "mean k_tau launch time %.4f s (CUDA events, timed region); peak = DFMA rate measured on this "
-                                 "device by fsb_measure_fma_peak (MEASURED_PEAKS.json has no FP64 entry)" % (
-                                     FLOP_PER_VOIGT, FLOP_PER_VOIGT_FUSED, algo_flop_step / n_tau_launches, tau_launch_s),
+                                 "device by fsb_measure_fma_peak in the same precision (MEASURED_PEAKS.json has no FP64/FP32 FMA entry)" % (
+                                     flop_first, flop_fused, algo_flop_step / n_tau_launches, tau_launch_s),
                          "reference_equivalent_tflops": FLOP_PER_VOIGT_REFERENCE * n_voigt_step / n_tau_launches / tau_launch_s / 1e12,
                          "march_steps_by_route": dict(zip(["near_gauss", "near", "far", "straddle", "slow"], [int(v) for v in routes])),
                          "tau_share_of_step": tau_launch_s * n_tau_launches / (elapsed / args.steps),

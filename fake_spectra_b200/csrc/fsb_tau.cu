@@ -69,7 +69,7 @@ enum SharedField {
     S_HALFB,     // btherm/2: sub-sampling threshold                    singleabs.h:110
     S_XOFF,      // -vhigh/btherm
     S_XU2,       // x^2 beyond which exp(-x^2) is negligible against the damping wing
-    S_PAD,
+    S_PAD,       // mode 4: number of inner points per pixel (singleabs.h:116)
     S_COUNT
 };
 enum LineField {
@@ -615,6 +615,118 @@ __device__ __forceinline__ void march_fast(const double *__restrict__ sl, const 
     }
 }
 
+// Pixels at least btherm/2 wide (coarse spectra): tau_kern_outer's trapezoid over npoints inner positions
+// (singleabs.h:110-125), every inner position a 7-node sum by the fast routes.  Same lane layout and stop rule
+// as march_fast; the Gaussians are started afresh at every inner position (no recurrence across positions).
+// The route thresholds of these particles carry a half-pixel margin (setup_particle).
+template <int NL, bool COUNT>
+__device__ __noinline__ void march_sub(const double *__restrict__ sl, const double *__restrict__ tab, double *__restrict__ row0,
+                                       int64_t line_stride, int nbins, double bintov, double tautail, int lane, Tally &tally)
+{
+    constexpr unsigned kUpBits = NL == 2 ? 0x5u : 0x1u, kDnBits = NL == 2 ? 0xau : 0x2u;
+    const int dir = lane >> 4, sub = lane & 15, half = nbins >> 1;
+    const unsigned grp_lt = ((1u << lane) - 1u) & (dir ? 0xffff0000u : 0x0000ffffu);
+    const double2 sx = SF2(S_STEP), pz = SF2(S_PIX), nf = SF2(S_THR_N), gr = SF2(S_THR_G);
+    const double step = sx.x;
+    const int2 zj = make_int2(__double2loint(pz.y), __double2hiint(pz.y));
+    const int2 thrN = make_int2(__double2loint(nf.x), __double2hiint(nf.x));
+    const int2 thrF = make_int2(__double2loint(nf.y), __double2hiint(nf.y));
+    const int2 thrG = make_int2(__double2loint(gr.x), __double2hiint(gr.x));
+    const int npts = (int) SF(S_PAD);
+    const double vel = SF(S_VEL), inv_b = SF(S_INVB), xoff = SF(S_XOFF), q = SF(S_Q);
+    unsigned live = half > 0 ? (kUpBits | kDnBits) : 0u;
+    int near_lim = min(thrN.x, thrN.y), far_beg = max(thrF.x, thrF.y), gauss_end = max(thrG.x, thrG.y);
+    for (int base = 0; live; base += 16) {
+        const int o = base + sub;
+        const int dz = dir ? ~o : o;
+        int j = zj.y + dz;
+        j += j < 0 ? nbins : (j >= nbins ? -nbins : 0);
+        const unsigned mybits = o < half ? (live >> dir) & kUpBits : 0u;
+        double *const pj = row0 + j;
+        double cur[NL];
+        #pragma unroll
+        for (int l = 0; l < NL; ++l) cur[l] = (mybits >> (2 * l)) & 1u ? pj[l * line_stride] : 0.0;
+        unsigned lmask = 0;
+        #pragma unroll
+        for (int l = 0; l < NL; ++l) lmask |= (live >> (2 * l)) & 3u ? (1u << l) : 0u;
+        // the pixel's velocity interval exactly as absorption.cpp:252-255,268-271
+        const double vlow = __dsub_rn(__dmul_rn((double) (zj.x + dz), bintov), vel);
+        const double vhigh_px = __dadd_rn(vlow, bintov);
+        const double dv = (vhigh_px - vlow) / (npts - 1);
+        const bool gauss = base < gauss_end;
+        const bool all_far = base >= far_beg, all_near = min(base + 16, half) <= near_lim;
+        int lc = 0;
+        unsigned cls = 0;
+        if (!all_far && !all_near) {  // transition step: lane class 0 table, 1 series, 2 node by node, 3 idle
+            const int myN = dir ? thrN.y : thrN.x, myF = dir ? thrF.y : thrF.x;
+            lc = !mybits ? 3 : (o >= myF ? 1 : (o < myN ? 0 : 2));
+            cls = __reduce_or_sync(kFull, 1u << lc);
+        }
+        double acc[NL];
+        #pragma unroll
+        for (int l = 0; l < NL; ++l) acc[l] = 0;
+        for (int i = 0; i < npts; ++i) {
+            const double v = i == 0 ? vlow : (i == npts - 1 ? vhigh_px : fma((double) i, dv, vlow));
+            const double wgt = (i == 0 || i == npts - 1) ? 0.5 : 1.0;
+            const double xb = fma(-v, inv_b, xoff);
+            double tot[NL];
+            #pragma unroll
+            for (int l = 0; l < NL; ++l) tot[l] = 0;
+            if (all_far) {
+                node_sum_far<NL>(xb, step, sl, lmask, tot);
+            } else {
+                if (all_near || (cls & 1u)) {
+                    double U0 = 0, R = 0;
+                    if (gauss) {
+                        const double x1 = xb + step;
+                        U0 = exp(-x1 * x1);
+                        R = exp(-fma(2.0, x1, step) * step);
+                    }
+                    node_sum_near<NL>(xb, step, sl, tab, U0, R, q, gauss, lmask, tot);
+                }
+                if (cls & 2u) {
+                    double tfar[NL];
+                    node_sum_far<NL>(xb, step, sl, lmask, tfar);
+                    #pragma unroll
+                    for (int l = 0; l < NL; ++l) tot[l] = lc == 1 ? tfar[l] : tot[l];
+                }
+                if ((cls & 4u) && lc == 2) {
+                    #pragma unroll
+                    for (int l = 0; l < NL; ++l)
+                        if ((lmask >> l) & 1u) tot[l] = LF(l, L_CD) * node_sum_generic(v, sl, l, tab);
+                }
+            }
+            #pragma unroll
+            for (int l = 0; l < NL; ++l) acc[l] = fma(wgt, tot[l], acc[l]);
+        }
+        if (COUNT) ++tally.route[all_far ? 2 : (all_near ? (gauss ? 0 : 1) : 3)];
+        unsigned ended = 0;
+        #pragma unroll
+        for (int l = 0; l < NL; ++l) {
+            const double t = acc[l] / (npts - 1);
+            const bool on = (mybits >> (2 * l)) & 1u;
+            const unsigned stop = __ballot_sync(kFull, on && (t < tautail));
+            if (on && !(stop & grp_lt)) {
+                pj[l * line_stride] = cur[l] + t;
+                if (COUNT) {
+                    ++tally.pix;
+                    tally.inner += npts;
+                }
+            }
+            ended |= ((stop & 0xffffu ? 1u : 0u) | (stop >> 16 ? 2u : 0u)) << (2 * l);
+        }
+        if (COUNT) ++tally.iter;
+        if (base + 16 >= half) ended = ~0u;
+        if (ended & live) {
+            live &= ~ended;
+            const bool up = live & kUpBits, dn = live & kDnBits;
+            near_lim = min(up ? thrN.x : 0x7fffffff, dn ? thrN.y : 0x7fffffff);
+            far_beg = max(up ? thrF.x : 0, dn ? thrF.y : 0);
+            gauss_end = max(up ? thrG.x : 0, dn ? thrG.y : 0);
+        }
+    }
+}
+
 // Slow routes: the exact Faddeeva restatement, and pixels wider than btherm/2 (sub-sampling rule of
 // singleabs.h:110-125).  Same lane layout, per-pixel evaluation through pixel_sum_slow.
 template <int NL, bool EXACT, bool COUNT>
@@ -782,13 +894,29 @@ __device__ __noinline__ void setup_particle(const InterpConsts &C, double *__res
     // pixels at least btherm/2 wide are sub-sampled (singleabs.h:110-125; bintov is rounded differently per
     // pixel by at most an ulp): generic per-pixel route
     if (mode == 1 && !(C.bintov * (1 + 1e-12) < btherm / 2.)) mode = 3;
+    // ... and served by the fast node sums (march_sub, mode 4) when the inner-point count is the same for every
+    // pixel whatever the rounding of its width, and a pixel is narrower than the table/series overlap
+    double hm = 0;  // half a pixel in units of btherm: the inner points of a pixel reach that far from its centre
+    if (mode == 3) {
+        const double r = C.bintov / (btherm / 2.) / 2., rc = ceil(r);
+        const bool stable = fabs(r - rint(r)) > 1e-9 * r && C.bintov > (btherm / 2.) * (1 + 1e-9);
+#ifndef FSB_NO_MARCH_SUB
+        // (measured on the 1-10 km/s sweep: routing every such particle here beats routing only those with narrow
+        // kernels; a sightline that alternates between this route and the per-pixel fallback is slower than either)
+        if (stable && pix < 6.0 && rc < 1e6) {
+            mode = 4;
+            hm = 0.5 * pix * (1 + 1e-9) + 1e-9;
+            SF(S_PAD) = 2.0 * rc + 1.0;  // npoints, singleabs.h:116
+        }
+#endif
+    }
     SF(S_MODE) = (double) mode;
     // Route thresholds in outward pixels.  Upward run: nodes x_i(o) = X_i - o pix; downward run:
     // x_i(o) = X_i + (1 + o) pix; X_1 = xb0 + step <= X_7 = xb0 + 7 step.  The table covers |x| < 24 and the
     // wing series |x| >= 16; margins of 0.01 dwarf the rounding of these expressions.
     {
         const double X1 = xb0 + step, X7 = fma(7.0, step, xb0), ipix = 1.0 / pix;
-        const double lim_n = FSB_GTAB_XMAX - 0.01, lim_f = kFarXMin + 0.01, xu = sqrt(fmin(xu2, 1e12));
+        const double lim_n = FSB_GTAB_XMAX - 0.01 - hm, lim_f = kFarXMin + 0.01 + hm, xu = sqrt(fmin(xu2, 1e12)) + hm;
         const bool near_any = X7 < lim_n && X1 > -lim_n;
         int2 tn, tf, tg;
         tn.x = near_any ? clamp_index(floor((X1 + lim_n) * ipix)) : 0;
@@ -879,6 +1007,7 @@ k_tau(InterpConsts C, Items items, int n_items, int *__restrict__ next_item, con
                 const int mode = (int) SF(S_MODE);
                 if (mode == 0) continue;
                 if (mode == 1) march_fast<NL, COUNT, F32>(sl, fslab + b * FSlabSize<NL>::kStride, tab, tab32, row0, line_stride, nbins, C.tautail, lane, tally);
+                else if (mode == 4) march_sub<NL, COUNT>(sl, tab, row0, line_stride, nbins, C.bintov, C.tautail, lane, tally);
                 else if (mode == 2) march_slow<NL, true, COUNT>(sl, tab, row0, line_stride, nbins, C.bintov, C.tautail, lane, tally);
                 else march_slow<NL, false, COUNT>(sl, tab, row0, line_stride, nbins, C.bintov, C.tautail, lane, tally);
                 __syncwarp();

@@ -112,7 +112,8 @@ def test_voigt_sweep_golden(torch_cuda, golden_dir, voigt):
 
 
 @pytest.mark.parametrize("kernel,line,res", [(1, "HI1215", 1.0), (0, "HI1215", 1.0), (3, "CIV1548", 2.5),
-                                             (1, "MgII2796", 10.0), (1, "HI1025", 0.5)])
+                                             (1, "MgII2796", 10.0), (1, "HI1025", 0.5), (1, "HI1215", 10.0),
+                                             (3, "HI1215", 5.0), (0, "HI1215", 7.0)])
 def test_tau_colden_vs_oracle(priv, oracle, kernel, line, res):
     """Fresh inputs, larger than the fixtures (24^3 particles, 96 sightlines on all three axes)."""
     d = cases.random_case(nside=24, nlos=96, axis="cycle", seed=500 + kernel, los_seed=77)
@@ -336,3 +337,29 @@ def test_host_entry_streams_rows_while_kernel_runs(priv, torch_cuda, monkeypatch
     resident = idx.compute_tau(prms if nlines == 2 else prms[0], t["pos"], t["vel"], t["dens"], t["temp"], t["h"]).cpu().numpy()
     assert np.array_equal(resident.reshape(streamed.shape), streamed)
     assert (np.abs(streamed).reshape(-1, p["nbins"]).sum(axis=1) == 0).any(), "case should contain empty sightlines"
+
+
+@pytest.mark.parametrize("res", [5.0, 10.0, 25.0])
+def test_coarse_pixels_subsampling_routes(torch_cuda, oracle, res):
+    """Pixels at least btherm/2 wide are sub-sampled (singleabs.h:110-125).  Hot and cold gas mixed so that one
+    sightline holds particles on the plain route, on the fast sub-sampled route and (pixels wider than the
+    table/series overlap: res = 25 with cold gas) on the per-pixel fallback; dense particles carry the march
+    into the wings; Lya + Lyb fused and alone."""
+    from fake_spectra_b200 import _lib, native
+    d = cases.random_case(nside=14, nlos=40, axis="cycle", seed=12)
+    rng = np.random.default_rng(5)
+    d["temp"] = (10 ** (2.0 + 4.5 * rng.random(d["temp"].size))).astype(np.float32)   # 1e2 .. 3e6 K
+    d["dens"][::6] *= 1e5
+    t = dev(torch_cuda, d)
+    idx = native.CandidateIndex(d["box"], t["cofm"], t["axis"], t["pos"], t["h"])
+    pa, pb = cases.params(d, line="HI1215", res=res), cases.params(d, line="HI1025", res=res)
+    ctr = torch_cuda.zeros(10, dtype=torch_cuda.int64, device="cuda")
+    both = idx.compute_tau([_lib.make_params(**pa), _lib.make_params(**pb)], t["pos"], t["vel"], t["dens"], t["temp"], t["h"]).cpu().numpy()
+    one = idx.compute_tau(_lib.make_params(**pa), t["pos"], t["vel"], t["dens"], t["temp"], t["h"], counters=ctr).cpu().numpy()
+    for got, p in ((both[0], pa), (both[1], pb), (one, pa)):
+        want = oracle.compute_tau(**p, pos=d["pos"], vel=d["vel"], dens=d["dens"], temp=d["temp"], h=d["h"],
+                                  axis=d["axis"], cofm=d["cofm"])
+        rel, same_zero = cases.rel_err(got, want)
+        assert same_zero and rel < TOL, (res, rel)
+    c = ctr.cpu().numpy()
+    assert c[2] > 7 * c[1], "some pixels must have been sub-sampled (more than 7 Voigt evaluations per pixel)"
