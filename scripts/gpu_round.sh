@@ -13,6 +13,7 @@ test) echo "== pytest -m gpu"; timeout 900 python -m pytest tests -m gpu -x -q >
 smoke) echo "== smoke"; timeout 300 python __graft_entry__.py smoke > $OUT/smoke.log 2>&1; tail -3 $OUT/smoke.log;;
 probe) echo "== probe"; timeout 600 python scripts/gpu_probe.py c1 c2s > $OUT/probe.log 2>&1; tail -6 $OUT/probe.log;;
 variants) echo "== variants"; for L in fake_spectra_b200/libfsb200*.so; do echo "-- $L"; FSB200_LIB=$PWD/$L timeout 600 python scripts/gpu_probe.py ${PROBE:-c1 c2s} 2>&1 | tail -3 | tee -a $OUT/variants.log; done;;
+refbench) echo "== bench --impl reference"; timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/bench_reference.json 2> $OUT/bench_reference.err; tail -1 $OUT/bench_reference.json | cut -c1-400;;
 bench) echo "== bench default"; timeout 900 python bench.py --steps 3 --warmup 3 > $OUT/bench.json 2> $OUT/bench.err; tail -2 $OUT/bench.json; tail -3 $OUT/bench.err;;
 launches) echo "== ncu launch list (mini workload)"
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_mini.csv \
