@@ -241,7 +241,7 @@ __device__ __forceinline__ void node_sum_far(double xb, double step, const doubl
                                              double (&tot)[NL])
 {
     const double isp = 0.56418958354775628694807945156;
-    double u[7], p1[7], p3[7], p5[7], kw[7];
+    double u[7], p1[7], p3[7], kw[7];
     {
         const double2 k01 = SF2(S_KW0), k23 = SF2(S_KW0 + 2), k45 = SF2(S_KW0 + 4), k6m = SF2(S_KW0 + 6);
         kw[0] = k01.x, kw[1] = k01.y, kw[2] = k23.x, kw[3] = k23.y, kw[4] = k45.x, kw[5] = k45.y, kw[6] = k6m.x;
@@ -251,8 +251,16 @@ __device__ __forceinline__ void node_sum_far(double xb, double step, const doubl
         const double x = fma((double) (i + 1), step, xb);
         u[i] = fast_rcp(x * x);
     }
+    // H = (y/sqrt(pi)) u [P1(u) - v (P3(u) - v P5(u))], v = y^2 u <= 3.6e-6 (far_polys, fsb_voigt.cuh).  Here, with
+    // u <= 1/256: the u^3.. tail of P1 (<= 8e-7 of P1) runs in FP32, P3 stops at u^3 and P5 = 1 (what is dropped is
+    // below 1.5e-12 of H at y = 0.03 and falls with y^2).
     #pragma unroll
-    for (int i = 0; i < 7; ++i) far_polys(u[i], p1[i], p3[i], p5[i]);
+    for (int i = 0; i < 7; ++i) {
+        const float uf = (float) u[i];
+        const float tail = fmaf(fmaf(fmaf(fmaf(15836.1328125f, uf, 2111.484375f), uf, 324.84375f), uf, 59.0625f), uf, 13.125f);
+        p1[i] = fma(fma(fma((double) tail, u[i], 3.75), u[i], 1.5), u[i], 1.0);
+        p3[i] = fma(fma(fma(157.5, u[i], 26.25), u[i], 5.0), u[i], 1.0);
+    }
     #pragma unroll
     for (int l = 0; l < NL; ++l) {
         if (NL > 1 && !((lmask >> l) & 1u)) {
@@ -264,7 +272,7 @@ __device__ __forceinline__ void node_sum_far(double xb, double step, const doubl
         #pragma unroll
         for (int i = 0; i < 7; ++i) {
             const double v = y2 * u[i];
-            acc = fma(u[i] * fma(v, fma(v, p5[i], -p3[i]), p1[i]), kw[i], acc);
+            acc = fma(u[i] * fma(-v, p3[i] - v, p1[i]), kw[i], acc);
         }
         tot[l] = (LF(l, L_CD) * isp * y) * acc;
     }
