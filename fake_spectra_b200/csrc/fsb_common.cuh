@@ -69,6 +69,8 @@ struct fsb_index {
     int64_t *offsets = nullptr;  // [nlos+1]
     int32_t *particle = nullptr; // [npairs] ascending within a line
     double *dr2 = nullptr;       // [npairs]
+    int32_t *zorder = nullptr;   // [npairs] traversal order of the optical-depth pass: each list's positions (absolute
+                                 // pair indices) ordered by the particle's place along the sightline, 64 bins, stable
     double *cofm = nullptr;      // [nlos*3] private copy (the accumulation needs axis / cofm)
     int32_t *axis = nullptr;     // [nlos]
 };

@@ -789,11 +789,12 @@ __device__ __forceinline__ int clamp_index(double v) { return (int) fmin(fmax(v,
 // Per-particle constants, one particle per lane (absorption.cpp:218-246, singleabs.h:81-90).
 template <int KERNEL, int NL, bool F32>
 __device__ __noinline__ void setup_particle(const InterpConsts &C, double *__restrict__ sl, float *__restrict__ fl, int64_t k, int ax,
-                                               const int32_t *__restrict__ particle, const double *__restrict__ dr2s,
+                                               const int32_t *__restrict__ zorder, const int32_t *__restrict__ particle, const double *__restrict__ dr2s,
                                                const float *__restrict__ pos, const float *__restrict__ vel,
                                                const float *__restrict__ dens, const float *__restrict__ temp,
                                                const float *__restrict__ hsml, const float *__restrict__ cells)
 {
+    k = zorder[k];  // traversal order along the sightline (fsb_index.cu), not list order
     const int64_t ip = particle[k];
     const float ppos = pos[3 * ip + ax], pvel = vel[3 * ip + ax];
     const float pdens = dens[ip], ptemp = temp[ip];
@@ -962,7 +963,8 @@ template <int NL, bool F32> constexpr size_t tau_smem_bytes()
 template <int KERNEL, int NL, bool COUNT, bool F32, bool STREAM>
 __global__ void __launch_bounds__(kTauThreads, FSB_TAU_MIN_BLOCKS)
 k_tau(InterpConsts C, Items items, int n_items, int *__restrict__ next_item, const int64_t *__restrict__ offsets,
-      const int32_t *__restrict__ particle, const double *__restrict__ dr2s, const int32_t *__restrict__ axis,
+      const int32_t *__restrict__ zorder, const int32_t *__restrict__ particle, const double *__restrict__ dr2s,
+      const int32_t *__restrict__ axis,
       const float *__restrict__ pos, const float *__restrict__ vel, const float *__restrict__ dens,
       const float *__restrict__ temp, const float *__restrict__ hsml, const float *__restrict__ cells,
       double *__restrict__ out, double *__restrict__ scratch, int64_t scratch_stride,
@@ -1020,7 +1022,7 @@ k_tau(InterpConsts C, Items items, int n_items, int *__restrict__ next_item, con
         for (int64_t k0 = kbeg; k0 < kend; k0 += kBatch) {
             const int nb = (int) min((int64_t) kBatch, kend - k0);
             __syncwarp();
-            if (lane < nb) setup_particle<KERNEL, NL, F32>(C, slab + lane * SlabSize<NL>::kStride, fslab + lane * FSlabSize<NL>::kStride, k0 + lane, ax, particle, dr2s, pos, vel, dens, temp, hsml, cells);
+            if (lane < nb) setup_particle<KERNEL, NL, F32>(C, slab + lane * SlabSize<NL>::kStride, fslab + lane * FSlabSize<NL>::kStride, k0 + lane, ax, zorder, particle, dr2s, pos, vel, dens, temp, hsml, cells);
             __syncwarp();
             // plain particles first, in list order; the rare others (exact Voigt, coarse pixels) of the batch after
             // them, so that the main loop holds no call (its register allocation is what the step time hangs on).
@@ -1099,7 +1101,7 @@ int launch_tau_k(const fsb_index *idx, const InterpConsts &c, const ItemPlan &pl
         FSB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTauThreads, smem));
         const int grid = std::max(1, std::min((n_items + kTauWarps - 1) / kTauWarps, sms * std::max(per_sm, 1)));
         count_launch();
-        kern<<<grid, kTauThreads, smem, stream>>>(c, plan.items, n_items, next_item, idx->offsets, idx->particle, idx->dr2, idx->axis,
+        kern<<<grid, kTauThreads, smem, stream>>>(c, plan.items, n_items, next_item, idx->offsets, idx->zorder, idx->particle, idx->dr2, idx->axis,
                                                   pos, vel, dens, temp, h, cells, out, plan.scratch_rows.as<double>(),
                                                   plan.n_items * (int64_t) c.nbins, ctr, chunk_done, host_flags, chunk_lines);
         FSB_CUDA_TRY(cudaGetLastError());
