@@ -495,7 +495,8 @@ __device__ __forceinline__ void march_fast(const double *__restrict__ sl, const 
         int j = zj.y + dz;                  // z mod nbins: |z - zmax| <= nbins/2
         j += j < 0 ? nbins : (j >= nbins ? -nbins : 0);
         const unsigned mybits = o < half ? (live >> dir) & kUpBits : 0u;  // bit 2 l: my run of line l is going
-        // start the read of the output pixels now; they are consumed after the quadrature
+        // start the read of the output pixels now; they are consumed after the quadrature (reading them just
+        // before the add instead was measured 2 % slower even with the position-ordered traversal)
         double *const pj = row0 + j;
         double cur[NL];
         #pragma unroll
