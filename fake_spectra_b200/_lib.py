@@ -53,6 +53,8 @@ SIGNATURES = {
                                                       C.c_int64, _P, _P, C.c_int32, _P]),
     "fsb_near_lines": (C.c_int, [C.c_double, _P, _P, C.c_int64, _P, _P, C.c_int32, _P, C.POINTER(C.c_int64), _P]),
     "fsb_near_lines_host": (C.c_int, [C.c_double, _P, _P, C.c_int64, _P, _P, C.c_int32, _P, C.POINTER(C.c_int64)]),
+    "fsb_count_pairs": (C.c_int, [C.c_double, _P, _P, C.c_int64, _P, _P, C.c_int32, _P, _P]),
+    "fsb_count_pairs_host": (C.c_int, [C.c_double, _P, _P, C.c_int64, _P, _P, C.c_int32, _P]),
     "fsb_assign_cells": (C.c_int, [_P, C.c_double, _P, _P, _P, _P, _P]),
     "fsb_measure_fma_peak": (C.c_int, [C.c_int32, C.POINTER(C.c_double), _P]),
     "fsb_voigt_profile": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, _P]),

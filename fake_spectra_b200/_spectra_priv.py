@@ -115,3 +115,19 @@ def _rescale_mean_flux(tau, mean_flux_desired, nbins, tol, thresh):
         raise TypeError("Optical depth must have 64-bit float type")
     from . import fluxstatistics
     return fluxstatistics.mean_flux(np.ravel(np.ascontiguousarray(tau))[:int(nbins)], mean_flux_desired, tol, thresh)
+
+
+def _count_pairs(box, pos, hh, axis, cofm):
+    """Candidate particles per sightline (int32 [NumLos]): the list sizes, without the lists.  Not part of the
+    reference's module; used to balance sightline blocks across GPUs (sharding.balanced_blocks)."""
+    if cofm.dtype != np.float64 or axis.dtype != np.int32:
+        raise ValueError("cofm must have 64-bit float type and axis must be a 32-bit integer")
+    if not _is_f32(pos) or not _is_f32(hh):
+        raise TypeError("pos and h must have 32-bit float type")
+    pos, hh = np.ascontiguousarray(pos), np.ascontiguousarray(hh)
+    cofm, axis = np.ascontiguousarray(cofm), np.ascontiguousarray(axis)
+    counts = np.zeros(cofm.shape[0], dtype=np.int32)
+    rc = _lib.load().fsb_count_pairs_host(float(box), _ptr(pos), _ptr(hh), pos.shape[0], _ptr(axis), _ptr(cofm),
+                                          cofm.shape[0], _ptr(counts))
+    _lib.check(rc, "_count_pairs")
+    return counts

@@ -368,6 +368,25 @@ extern "C" int fsb_near_lines_host(double box, const float *pos, const float *h,
     return FSB_OK;
 }
 
+extern "C" int fsb_count_pairs_host(double box, const float *pos, const float *h, int64_t npart, const int32_t *axis,
+                                    const double *cofm, int32_t nlos, int32_t *counts)
+{
+    FSB_REQUIRE(nlos >= 0 && npart >= 0, "negative size");
+    if (nlos == 0) return FSB_OK;
+    FSB_REQUIRE(counts != nullptr, "counts is NULL");
+    cudaStream_t s = nullptr;
+    DevBuf dpos, dh, daxis, dcofm, dout;
+    FSB_TRY(dpos.upload(pos, sizeof(float) * 3 * (size_t) npart, s));
+    FSB_TRY(dh.upload(h, sizeof(float) * (size_t) npart, s));
+    FSB_TRY(daxis.upload(axis, sizeof(int32_t) * (size_t) nlos, s));
+    FSB_TRY(dcofm.upload(cofm, sizeof(double) * 3 * (size_t) nlos, s));
+    FSB_TRY(dout.upload(nullptr, sizeof(int32_t) * (size_t) nlos, s));
+    FSB_TRY(fsb_count_pairs(box, (const float *) dpos.ptr, (const float *) dh.ptr, npart, (const int32_t *) daxis.ptr,
+                            (const double *) dcofm.ptr, nlos, (int32_t *) dout.ptr, s));
+    FSB_CUDA_TRY(cudaMemcpy(counts, dout.ptr, sizeof(int32_t) * (size_t) nlos, cudaMemcpyDeviceToHost));
+    return FSB_OK;
+}
+
 extern "C" int fsb_voigt_profile(const double *x, const double *y, double *out, int64_t n, int32_t voigt, void *stream)
 {
     FSB_REQUIRE(n >= 0, "negative n");

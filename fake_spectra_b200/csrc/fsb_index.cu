@@ -647,3 +647,24 @@ extern "C" int fsb_near_lines(double box, const float *pos, const float *h, int6
     FSB_CUDA_TRY(cudaStreamSynchronize(stream));
     return FSB_OK;
 }
+
+// Candidate pairs per sightline without building the lists: the "cheap count pass" that balances sightline
+// blocks across GPUs.  counts[nlos] int32, DEVICE, overwritten.
+extern "C" int fsb_count_pairs(double box, const float *pos, const float *h, int64_t npart, const int32_t *axis,
+                               const double *cofm, int32_t nlos, int32_t *counts, void *stream_v)
+{
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    FSB_REQUIRE(nlos >= 0 && npart >= 0, "negative size");
+    FSB_REQUIRE(npart <= (int64_t) INT32_MAX, "npart exceeds int32 particle indices");
+    FSB_REQUIRE(box > 0, "box must be positive");
+    if (nlos == 0) return FSB_OK;
+    FSB_REQUIRE(counts != nullptr && axis && cofm, "NULL array");
+    FSB_CUDA_TRY(cudaMemsetAsync(counts, 0, sizeof(int32_t) * (size_t) nlos, stream));
+    if (npart == 0) return FSB_OK;
+    FSB_REQUIRE(pos && h, "NULL array");
+    BuiltTable bt;
+    FSB_TRY(build_line_table(box, cofm, axis, nlos, stream, bt));
+    count_launch(); k_pairs<0><<<(unsigned) ((npart + 255) / 256), 256, 0, stream>>>(bt.T, pos, h, npart, counts, nullptr, nullptr, nullptr);
+    FSB_CUDA_TRY(cudaGetLastError());
+    return FSB_OK;
+}

@@ -233,6 +233,22 @@ class Spectra:
         self._engines = {}
         self.part_ind = {}
 
+    def balance_sightlines(self, weights=None, segment=0):
+        """Re-partition the sightlines over the ranks (sightline-sharded mode) into contiguous blocks of equal
+        WORK instead of equal count: ``weights`` per sightline, by default the number of candidate particles of
+        snapshot segment ``segment`` (one cheap count pass on the device; every rank holds the same particles in
+        this mode, so every rank derives the same blocks without a collective).  Returns the block edges.
+        Drops cached device state; results already computed stay valid (they are stored for all sightlines)."""
+        if self._sharder.mode != "sightlines" or self._sharder.size == 1:
+            return self._sharder.set_sightlines(self.NumLos)
+        if weights is None:
+            pos = self.snapshot_set.get_data(0, "Position", segment=segment).astype(np.float32)
+            hh = self.snapshot_set.get_smooth_length(0, segment=segment).astype(np.float32)
+            weights = self._backend._count_pairs(self.box, pos, hh, self.axis, self.cofm)
+        edges = self._sharder.set_sightlines(self.NumLos, weights=np.asarray(weights))
+        self._set_my_sightlines()
+        return edges
+
     def set_sightlines(self, cofm, axis):
         """Replace the sightlines (drops cached particle lists, device state and results)."""
         self.cofm = np.asarray(cofm).astype(np.float64)

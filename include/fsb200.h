@@ -160,6 +160,14 @@ FSB_API int fsb_near_lines(double box, const float *pos, const float *h, int64_t
 FSB_API int fsb_near_lines_host(double box, const float *pos, const float *h, int64_t npart, const int32_t *axis,
                         const double *cofm, int32_t nlos, int32_t *out_index, int64_t *count);
 
+/* Candidate pairs per sightline (the sizes of the lists fsb_index_build would make) without building them:
+ * the count pass that balances sightline blocks across GPUs.  counts[nlos] int32, overwritten; DEVICE
+ * pointers + stream, or HOST pointers (synchronous).  No reference counterpart (the reference shards particles). */
+FSB_API int fsb_count_pairs(double box, const float *pos, const float *h, int64_t npart, const int32_t *axis,
+                    const double *cofm, int32_t nlos, int32_t *counts, void *stream);
+FSB_API int fsb_count_pairs_host(double box, const float *pos, const float *h, int64_t npart, const int32_t *axis,
+                         const double *cofm, int32_t nlos, int32_t *counts);
+
 /* ---- Voronoi cells (replaces IndexTable::assign_cells, index_table.cpp:152-223) ------------ */
 /* cells[2*npairs] f32 in list order: (lo, hi) extent of each candidate's cell along its
  * sightline, 3*box sentinel when it owns nothing.  Returns FSB_EVORONOI (after finishing all

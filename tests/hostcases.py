@@ -28,6 +28,10 @@ class OracleBackend:
     def _near_lines(self, box, pos, hh, axis, cofm):
         return self.oracle.near_lines(box, pos, hh, axis, cofm)
 
+    def _count_pairs(self, box, pos, hh, axis, cofm):
+        off, _, _ = self.oracle.near_particles(cofm, axis, box, pos, hh)
+        return np.diff(off).astype(np.int32)
+
 
 def snapshot(nside=10, nsegments=1, seed=4, arepo=False):
     return syn.SyntheticSnapshot(nside, seed=seed, nsegments=nsegments, arepo=arepo)

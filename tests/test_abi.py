@@ -78,3 +78,15 @@ def test_near_lines_type_errors():
         priv._near_lines(1000., a["pos"], a["h"], a["axis"].astype(np.int64), a["cofm"])
     with pytest.raises(ValueError):  # :43-46
         priv._near_lines(1000., a["pos"], a["h"], np.ones(4, np.int32), a["cofm"])
+
+
+def test_rescale_and_count_reject_wrong_dtypes_before_the_device():
+    """_rescale_mean_flux raises the reference's TypeError (py_module.cpp:274-277) and _count_pairs the
+    _near_lines errors, both before any device call."""
+    from fake_spectra_b200 import _spectra_priv as priv
+    with pytest.raises(TypeError):
+        priv._rescale_mean_flux(np.zeros(4, np.float32), 0.5, 4, 1e-5, 1e30)
+    with pytest.raises(TypeError):
+        priv._count_pairs(1.0, np.zeros((2, 3)), np.zeros(2, np.float32), np.ones(1, np.int32), np.zeros((1, 3)))
+    with pytest.raises(ValueError):
+        priv._count_pairs(1.0, np.zeros((2, 3), np.float32), np.zeros(2, np.float32), np.ones(1, np.int64), np.zeros((1, 3)))

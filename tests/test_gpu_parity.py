@@ -363,3 +363,15 @@ def test_coarse_pixels_subsampling_routes(torch_cuda, oracle, res):
         assert same_zero and rel < TOL, (res, rel)
     c = ctr.cpu().numpy()
     assert c[2] > 7 * c[1], "some pixels must have been sub-sampled (more than 7 Voigt evaluations per pixel)"
+
+
+def test_count_pairs_equals_list_sizes(priv, torch_cuda):
+    """fsb_count_pairs (the balance pass of sightline sharding) returns the sizes of the lists fsb_index_build makes."""
+    from fake_spectra_b200 import native
+    for d in (cases.random_case(nside=16, nlos=70, axis="cycle", seed=3), cases.grid_case(), cases.edge_case()):
+        t = dev(torch_cuda, d)
+        idx = native.CandidateIndex(d["box"], t["cofm"], t["axis"], t["pos"], t["h"])
+        off = idx.export()[0].cpu().numpy()
+        got = priv._count_pairs(d["box"], d["pos"], d["h"], d["axis"], d["cofm"])
+        assert got.dtype == np.int32 and np.array_equal(got, np.diff(off))
+    assert priv._count_pairs(10.0, np.zeros((0, 3), np.float32), np.zeros(0, np.float32), d["axis"], d["cofm"]).sum() == 0

@@ -160,19 +160,23 @@ def _worker(rank, world, port, mode, out_dir):
     orc.set_threads(2)
     be = hc.OracleBackend(orc)
     snap = hc.snapshot(10, 2)
-    rs = randspectra.RandSpectra(0, snap, numlos=13, thresh=0., res=2.0, quiet=True, backend=be, shard=mode)
+    balanced = mode == "sightlines-balanced"
+    rs = randspectra.RandSpectra(0, snap, numlos=13, thresh=0., res=2.0, quiet=True, backend=be,
+                                 shard="sightlines" if balanced else mode)
+    edges = rs.balance_sightlines() if balanced else None
     tau = rs.get_tau("H", 1, 1215)
     vel = rs.get_velocity("H", 1)
-    np.savez(os.path.join(out_dir, "r%d.npz" % rank), tau=tau, vel=vel, lines=[c[2] for c in be.calls], parts=[c[1] for c in be.calls])
+    np.savez(os.path.join(out_dir, "r%d.npz" % rank), tau=tau, vel=vel, lines=[c[2] for c in be.calls], parts=[c[1] for c in be.calls],
+             edges=np.zeros(0) if edges is None else edges)
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["sightlines", "particles"])
+@pytest.mark.parametrize("mode", ["sightlines", "particles", "sightlines-balanced"])
 def test_two_rank_sharding_gloo(backend, tmp_path, mode):
     """world_size 2 over gloo: both ranks end with the full arrays, equal to the unsharded run
     (bitwise for sightline sharding; to summation order for particle sharding)."""
     import torch.multiprocessing as mp
-    port = 29500 + (os.getpid() % 2000) + (7 if mode == "particles" else 0)
+    port = 29500 + (os.getpid() % 2000) + {"sightlines": 0, "particles": 7, "sightlines-balanced": 13}[mode]
     mp.spawn(_worker, args=(2, port, mode, str(tmp_path)), nprocs=2, join=True)
     ref = make_rand(backend, numlos=13, nsegments=2)
     tau, vel = ref.get_tau("H", 1, 1215), ref.get_velocity("H", 1)
@@ -181,6 +185,11 @@ def test_two_rank_sharding_gloo(backend, tmp_path, mode):
         if mode == "sightlines":
             assert np.array_equal(o["tau"], tau) and np.array_equal(o["vel"], vel)
             assert set(o["lines"]) <= {6, 7}          # each rank only interpolated its block of the 13 sightlines
+        elif mode == "sightlines-balanced":
+            # blocks of equal candidate-pair count (counted on segment 0), same edges on both ranks, same results
+            assert np.array_equal(o["tau"], tau) and np.array_equal(o["vel"], vel)
+            e = o["edges"]
+            assert e[0] == 0 and e[-1] == 13 and 0 < e[1] < 13 and np.array_equal(e, outs[0]["edges"])
         else:
             assert np.allclose(o["tau"], tau, rtol=1e-12, atol=0) and np.array_equal(o["tau"] == 0, tau == 0)
             assert np.allclose(o["vel"], vel, rtol=1e-5, atol=1e-4)
