@@ -99,3 +99,50 @@ def test_config1_full_size_rows(oracle):
                                   axis=axis[sel], cofm=cofm[sel])
         rel, same_zero = cases.rel_err(got[k], want)
         assert same_zero and rel < TOL, (k, rel)
+
+
+def test_config2_structure_three_axes_four_lines(oracle):
+    """BASELINE configs[2] in structure: 100 000 random sightlines cycling over all three axes, H I 1215/1025
+    (fused), C IV 1548 and Mg II 2796 (their own abundance), at 2x256^3 particles instead of 2x512^3 (the
+    generator would take minutes of test time at 512^3).  Same row property as config 1: a 150-sightline
+    subsample of the full run equals, bit for bit, a run on those sightlines alone, which is checked against
+    the oracle at 1e-10 for every line."""
+    import torch
+    from fake_spectra_b200 import _lib, native
+    d = syn.boundary_arrays(256, seed=42)
+    nlos = 100000
+    cofm, axis = syn.random_sightlines(d["box"], nlos, seed=23, axis="cycle")
+    assert set(np.unique(axis)) == {1, 2, 3}
+    ions = [(("HI1215", "HI1025"), 1.0), (("CIV1548",), 1e-4), (("MgII2796",), 3e-5)]
+    t = _dev(torch, dict(d, cofm=cofm, axis=axis))
+    sel = np.linspace(0, nlos - 1, 150).astype(np.int64)
+    sel_dev = torch.from_numpy(sel).cuda()
+    idx = native.CandidateIndex(d["box"], t["cofm"], t["axis"], t["pos"], t["h"])
+    rows = {}
+    for lines, scale in ions:
+        prms = [_lib.make_params(**cases.params(d, line=ln)) for ln in lines]
+        dens = (t["dens"] * scale).contiguous()
+        full = idx.compute_tau(prms if len(prms) > 1 else prms[0], t["pos"], t["vel"], dens, t["temp"], t["h"])
+        full = full.view(len(lines), nlos, -1)
+        for k, ln in enumerate(lines):
+            rows[ln] = full[k, sel_dev].cpu().numpy()
+        del full
+    idx.free()
+    sc = torch.from_numpy(np.ascontiguousarray(cofm[sel])).cuda()
+    sa = torch.from_numpy(np.ascontiguousarray(axis[sel])).cuda()
+    small = native.CandidateIndex(d["box"], sc, sa, t["pos"], t["h"])
+    near = oracle.near_lines(d["box"], d["pos"], d["h"], axis[sel], cofm[sel])
+    sub = {k: np.ascontiguousarray(d[k][near]) for k in ("pos", "vel", "dens", "temp", "h")}
+    for lines, scale in ions:
+        whole = [_lib.make_params(**cases.params(d, line=ln), seg_pairs=1 << 30) for ln in lines]
+        dens = (t["dens"] * scale).contiguous()
+        got = small.compute_tau(whole if len(whole) > 1 else whole[0], t["pos"], t["vel"], dens, t["temp"], t["h"])
+        got = got.view(len(lines), sel.size, -1).cpu().numpy()
+        for k, ln in enumerate(lines):
+            assert np.array_equal(got[k], rows[ln]), ln
+            p = cases.params(d, line=ln)
+            want = oracle.compute_tau(**p, pos=sub["pos"], vel=sub["vel"], dens=(sub["dens"] * np.float32(scale)),
+                                      temp=sub["temp"], h=sub["h"], axis=axis[sel], cofm=cofm[sel])
+            rel, same_zero = cases.rel_err(got[k], want)
+            assert same_zero and rel < TOL, (ln, rel)
+    assert rows["HI1215"].mean() > rows["HI1025"].mean() > 0 and rows["CIV1548"].max() > 0
