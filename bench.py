@@ -41,6 +41,8 @@ WORKLOADS = {
     # (nside^3 cells PER RANK of one common box), every rank computes all sightlines for its cells and the
     # FP64 tau arrays are summed with one NCCL all-reduce per step (the reference's MPI mode, spectra.py:825-831)
     "c4_tophat_pshard": dict(nside=256, numlos=16384, lines=("HI1215",), kernel=0, res=1.0, shard="particles"),
+    # BASELINE.json configs[3] at full size when run on 8 GPUs: 8 x 512^3 = 1024^3 cells in a 160 000 kpc/h box
+    "c4_tophat_pshard_1024": dict(nside=512, numlos=16384, lines=("HI1215",), kernel=0, res=1.0, shard="particles"),
     "mini_tophat_pshard": dict(nside=64, numlos=2048, lines=("HI1215",), kernel=0, res=1.0, shard="particles"),
 }
 # Algorithmic FP64 work of THIS library's profile evaluation, per Voigt evaluation
