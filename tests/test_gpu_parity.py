@@ -375,3 +375,62 @@ def test_count_pairs_equals_list_sizes(priv, torch_cuda):
         got = priv._count_pairs(d["box"], d["pos"], d["h"], d["axis"], d["cofm"])
         assert got.dtype == np.int32 and np.array_equal(got, np.diff(off))
     assert priv._count_pairs(10.0, np.zeros((0, 3), np.float32), np.zeros(0, np.float32), d["axis"], d["cofm"]).sum() == 0
+
+
+@pytest.mark.parametrize("nbins", [1, 2, 3, 7, 16, 31, 33, 64, 1001])
+def test_tiny_and_odd_pixel_counts(priv, oracle, nbins):
+    """Spectra shorter than a warp, odd pixel counts (one pixel is out of reach of the nbins/2 + nbins/2 march,
+    absorption.cpp:250-278) and a single pixel (no pixel is visited at all); the column density wraps around a
+    spectrum shorter than a particle's extent many times."""
+    d = cases.random_case(nside=10, nlos=12, axis="cycle", seed=40 + nbins)
+    d["dens"][::4] *= 1e4
+    for kernel in (1, 0):
+        p = cases.params(d, kernel=kernel, nbins=nbins)
+        want = oracle.compute_tau(**p, pos=d["pos"], vel=d["vel"], dens=d["dens"], temp=d["temp"], h=d["h"],
+                                  axis=d["axis"], cofm=d["cofm"])
+        rel, same_zero = cases.rel_err(interp(priv, 1, p, d), want)
+        assert same_zero and rel < TOL, (kernel, "tau", rel)
+        want = oracle.compute_colden(**p, pos=d["pos"], dens=d["dens"], h=d["h"], axis=d["axis"], cofm=d["cofm"])
+        rel, same_zero = cases.rel_err(interp(priv, 0, p, d), want)
+        assert same_zero and rel < TOL, (kernel, "colden", rel)
+
+
+def test_list_longer_than_the_in_kernel_sort(torch_cuda, priv, oracle):
+    """A sightline with more than 32 768 candidates (a dense filament along the line) takes the index build's
+    global-memory sort; its neighbours take the shared-memory one.  Lists, dr^2, tau and column density against
+    the oracle."""
+    from fake_spectra_b200 import native
+    d = cases.random_case(nside=10, nlos=6, axis=1, seed=77)
+    rng = np.random.default_rng(9)
+    n_extra = 36000
+    box = d["box"]
+    tube = np.empty((n_extra, 3), dtype=np.float32)
+    tube[:, 0] = rng.random(n_extra) * box
+    tube[:, 1] = d["cofm"][2, 1] + rng.normal(0, 0.01 * box, n_extra)
+    tube[:, 2] = d["cofm"][2, 2] + rng.normal(0, 0.01 * box, n_extra)
+    tube = np.mod(tube, np.float32(box)).astype(np.float32)
+    np.minimum(tube, np.nextafter(np.float32(box), np.float32(0)), out=tube)
+    def ext(a, fill):
+        return np.concatenate([a, fill]).astype(a.dtype)
+    d["pos"] = ext(d["pos"], tube)
+    d["vel"] = ext(d["vel"], (50 * rng.standard_normal((n_extra, 3))).astype(np.float32))
+    d["dens"] = ext(d["dens"], np.full(n_extra, np.median(d["dens"]) * 1e-3, np.float32))
+    d["temp"] = ext(d["temp"], np.full(n_extra, 2e4, np.float32))
+    d["h"] = ext(d["h"], np.full(n_extra, 0.06 * box, np.float32))
+    perm = rng.permutation(d["pos"].shape[0])      # interleave the filament with the rest in index order
+    for k in ("pos", "vel", "dens", "temp", "h"):
+        d[k] = np.ascontiguousarray(d[k][perm])
+    t = dev(torch_cuda, d)
+    idx = native.CandidateIndex(d["box"], t["cofm"], t["axis"], t["pos"], t["h"])
+    assert idx.max_list > 32768
+    off, part, dr2 = (x.cpu().numpy() for x in idx.export())
+    o_off, o_part, o_dr2 = oracle.near_particles(d["cofm"], d["axis"], d["box"], d["pos"], d["h"])
+    assert np.array_equal(off, o_off) and np.array_equal(part, o_part) and np.array_equal(dr2, o_dr2)
+    p = cases.params(d)
+    want = oracle.compute_tau(**p, pos=d["pos"], vel=d["vel"], dens=d["dens"], temp=d["temp"], h=d["h"],
+                              axis=d["axis"], cofm=d["cofm"])
+    rel, same_zero = cases.rel_err(interp(priv, 1, p, d), want)
+    assert same_zero and rel < TOL, rel
+    want = oracle.compute_colden(**p, pos=d["pos"], dens=d["dens"], h=d["h"], axis=d["axis"], cofm=d["cofm"])
+    rel, same_zero = cases.rel_err(interp(priv, 0, p, d), want)
+    assert same_zero and rel < TOL, rel
