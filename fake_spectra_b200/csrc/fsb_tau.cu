@@ -474,6 +474,12 @@ __device__ __forceinline__ void march_commit(const MarchGeom &g, const double (&
 // beyond the quadrature: `live` has bit (2 l + d) set while direction d (0 up, 1 down) of line l is going;
 // near_lim / far_beg / gauss_end are the route limits of the directions still live and are refreshed only
 // when a direction ends.
+// Predicated 8-byte store: no divergent region (BSSY / BSYNC) around one instruction.
+__device__ __forceinline__ void store_if(double *p, double v, bool pred)
+{
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.global.f64 [%0], %1;\n\t}" ::"l"(p), "d"(v), "r"((unsigned) pred) : "memory");
+}
+
 template <int NL, bool COUNT, bool F32>
 __device__ __forceinline__ void march_fast(const double *__restrict__ sl, const float *__restrict__ fl, const double *__restrict__ tab,
                                            const float4 *__restrict__ tab32, double *__restrict__ row0, int64_t line_stride, int nbins,
@@ -607,12 +613,11 @@ __device__ __forceinline__ void march_fast(const double *__restrict__ sl, const 
             const double t = tot[l];  // already scaled by the line amplitude
             const bool on = (mybits >> (2 * l)) & 1u;
             const unsigned stop = __ballot_sync(kFull, on && (t < tautail));
-            if (on && !(stop & grp_lt)) {  // no lane of my run below me has stopped
-                pj[l * line_stride] = cur[l] + t;
-                if (COUNT) {
-                    ++tally.pix;
-                    ++tally.inner;
-                }
+            const bool wr = on && !(stop & grp_lt);  // no lane of my run below me has stopped
+            store_if(pj + l * line_stride, cur[l] + t, wr);
+            if (COUNT && wr) {
+                ++tally.pix;
+                ++tally.inner;
             }
             ended |= ((stop & 0xffffu ? 1u : 0u) | (stop >> 16 ? 2u : 0u)) << (2 * l);
         }
@@ -719,12 +724,11 @@ __device__ __noinline__ void march_sub(const double *__restrict__ sl, const doub
             const double t = acc[l] / (npts - 1);
             const bool on = (mybits >> (2 * l)) & 1u;
             const unsigned stop = __ballot_sync(kFull, on && (t < tautail));
-            if (on && !(stop & grp_lt)) {
-                pj[l * line_stride] = cur[l] + t;
-                if (COUNT) {
-                    ++tally.pix;
-                    tally.inner += npts;
-                }
+            const bool wr = on && !(stop & grp_lt);
+            store_if(pj + l * line_stride, cur[l] + t, wr);
+            if (COUNT && wr) {
+                ++tally.pix;
+                tally.inner += npts;
             }
             ended |= ((stop & 0xffffu ? 1u : 0u) | (stop >> 16 ? 2u : 0u)) << (2 * l);
         }
