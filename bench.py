@@ -464,6 +464,8 @@ def cpu_sample(w, steps=1, nsample=None):
         impl, kind = Reference(), "reference"
     except (FileNotFoundError, OSError):
         impl, kind = Oracle(), "port"
+    # all host threads, whatever OMP_NUM_THREADS says (torchrun exports OMP_NUM_THREADS=1 to every rank)
+    impl.set_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     cores = impl.threads()
     if nsample is None:
         # ~0.56 core-seconds per sightline at 256^3 (two lines); aim at 10-30 s of CPU work per step
