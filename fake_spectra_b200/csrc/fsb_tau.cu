@@ -252,14 +252,14 @@ __device__ __forceinline__ void node_sum_far(double xb, double step, const doubl
         u[i] = fast_rcp(x * x);
     }
     // H = (y/sqrt(pi)) u [P1(u) - v (P3(u) - v P5(u))], v = y^2 u <= 3.6e-6 (far_polys, fsb_voigt.cuh).  Here, with
-    // u <= 1/256: the u^3.. tail of P1 (<= 8e-7 of P1) runs in FP32, P3 stops at u^3 and P5 = 1 (what is dropped is
-    // below 1.5e-12 of H at y = 0.03 and falls with y^2).
+    // u <= 1/144: the u^3.. tail of P1 (<= 5e-6 of P1, ten terms in all) runs in FP32, P3 stops at u^4 and P5 = 1
+    // (what is dropped is below 3e-12 of H at y = 0.03, |x| = 12, and falls with y^2 and 1/x^2).
     #pragma unroll
     for (int i = 0; i < 7; ++i) {
         const float uf = (float) u[i];
-        const float tail = fmaf(fmaf(fmaf(fmaf(15836.1328125f, uf, 2111.484375f), uf, 324.84375f), uf, 59.0625f), uf, 13.125f);
+        const float tail = fmaf(fmaf(fmaf(fmaf(fmaf(fmaf(1278767.75f, uf, 134607.125f), uf, 15836.1328125f), uf, 2111.484375f), uf, 324.84375f), uf, 59.0625f), uf, 13.125f);
         p1[i] = fma(fma(fma((double) tail, u[i], 3.75), u[i], 1.5), u[i], 1.0);
-        p3[i] = fma(fma(fma(157.5, u[i], 26.25), u[i], 5.0), u[i], 1.0);
+        p3[i] = fma(fma(fma(fma(1082.8125, u[i], 157.5), u[i], 26.25), u[i], 5.0), u[i], 1.0);
     }
     #pragma unroll
     for (int l = 0; l < NL; ++l) {

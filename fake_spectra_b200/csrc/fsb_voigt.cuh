@@ -8,7 +8,7 @@
 //                   G(x) = 1 - 2 x Dawson(x)   (193 piecewise degree-7 polynomials, |x| < 24, stored in
 //                   mixed precision: 48 bytes per piece, see fsb_voigt_tables.h),
 //               with Pe, A, B polynomials in s whose coefficients depend on y only (per-particle
-//               constants).  Beyond |x| >= 16 the Gaussian has vanished and the profile is the
+//               constants).  Beyond |x| >= 12 the Gaussian has vanished and the profile is the
 //               Taylor series in y of the damping wing, -y L' + y^3 L'''/6 - y^5 L^(5)/120 with
 //               L = Im w on the real axis expanded in u = 1/x^2 (polynomials P1, P3, P5 below).
 //               Agrees with voigt_exact to < 1e-11 relative on its domain (tests/test_gpu_parity).
@@ -173,7 +173,7 @@ __device__ double voigt_exact(double xin, double y, double erfcx_y)
 
 // ---- fast path -----------------------------------------------------------------------------
 
-constexpr double kFarXMin = 16.0;     // the damping-wing series is used from here on; the table reaches FSB_GTAB_XMAX = 24
+constexpr double kFarXMin = 12.0;     // the damping-wing series is used from here on; the table reaches FSB_GTAB_XMAX = 24
 constexpr double kFastYMax = 0.03;    // above: voigt_exact (error of the y^7 truncation < 3e-13 below)
 constexpr double kFastYMin = 1e-30;   // below (and > 0): voigt_exact (Gaussian cut-off would pass exp underflow)
 
@@ -254,13 +254,13 @@ __device__ __forceinline__ double g_table(double ax, const double *__restrict__ 
     return g_eval(tab, k, t);
 }
 
-// Damping wing for |x| >= 16, u = 1/x^2:  H = (y/sqrt(pi)) u [P1(u) - (y^2 u) P3(u) + (y^2 u)^2 P5(u)],
+// Damping wing for |x| >= 12, u = 1/x^2:  H = (y/sqrt(pi)) u [P1(u) - (y^2 u) P3(u) + (y^2 u)^2 P5(u)],
 // P1 = sum c_k (2k+1) u^k, P3 = sum c_k C(2k+3,3) u^k, P5 = sum c_k C(2k+5,5) u^k, c_k = (2k-1)!!/2^k.
 // Truncation error < 3e-14 relative for y <= 0.03 (scripts/voigt_design.py).
 __device__ __forceinline__ void far_polys(double u, double &p1, double &p3, double &p5)
 {
-    p1 = fma(fma(fma(fma(fma(fma(fma(15836.1328125, u, 2111.484375), u, 324.84375), u, 59.0625), u, 13.125), u, 3.75), u, 1.5), u, 1.0);
-    p3 = fma(fma(fma(fma(fma(8445.9375, u, 1082.8125), u, 157.5), u, 26.25), u, 5.0), u, 1.0);
+    p1 = fma(fma(fma(fma(fma(fma(fma(fma(fma(1278767.724609375, u, 134607.12890625), u, 15836.1328125), u, 2111.484375), u, 324.84375), u, 59.0625), u, 13.125), u, 3.75), u, 1.5), u, 1.0);
+    p3 = fma(fma(fma(fma(fma(fma(73901.953125, u, 8445.9375), u, 1082.8125), u, 157.5), u, 26.25), u, 5.0), u, 1.0);
     p5 = fma(10.5, u, 1.0);
 }
 
