@@ -15,10 +15,10 @@
 //
 // Per pixel the 7-node kernel x Voigt quadrature (singleabs.h:143-167) takes one of four
 // warp-uniform routes:
-//   NEAR   all nodes of all lanes at |x| < 16: branch-free, the 7 nodes interleaved for ILP;
+//   NEAR   all nodes of all lanes inside the table (|x| < 24): branch-free, the 7 nodes interleaved for ILP;
 //          G(x) from the shared-memory table, Gaussians by a two-level recurrence (across the nodes
 //          of a pixel, and from one march step to the next: no exp() in steady state)
-//   FAR    all nodes at |x| >= 16: damping-wing series in 1/x^2, shared across the fused lines
+//   FAR    all nodes at |x| >= 12: damping-wing series in 1/x^2, shared across the fused lines
 //   MIXED  the rare warp step that straddles |x| = 16, and pixels wider than btherm/2
 //          (sub-sampling rule of singleabs.h:110-125): generic per-node evaluation
 //   EXACT  FSB_VOIGT_EXACT or y outside (1e-30, 0.03]: restatement of the reference's Faddeeva::w
@@ -55,7 +55,7 @@ enum SharedField {
     S_PIX,       // pixel width in units of btherm
     S_ZMAX,      // int2 {zmax = floor(vel/bintov), zmax mod nbins}
     S_THR_N,     // int2 {up, down}: outward pixels o < N have all nodes inside the table (|x| < 24)
-    S_THR_F,     // int2: outward pixels o >= F have all nodes on the wing series (|x| >= 16)
+    S_THR_F,     // int2: outward pixels o >= F have all nodes on the wing series (|x| >= 12)
     S_THR_G,     // int2: outward pixels o >= G are out of reach of the Gaussian
     S_RECOK,     // 1 when the march-step recurrence is safe (all factors within e^+-500)
     S_Q,         // exp(-2 step^2): second-order ratio of the Gaussian recurrence across nodes
@@ -107,7 +107,7 @@ template <int NL> struct FSlabSize {
 // ---- node sums ------------------------------------------------------------------------------------
 // All return sum_i kw_i H(x_i, y_l) for x_i = xb + (i+1) step, per fused line l.
 
-// NEAR: every node at |x| < 16.  U0 = exp(-x_1^2), R = exp(-(2 x_1 + step) step), q = exp(-2 step^2)
+// NEAR: every node inside the table (|x| < 24).  U0 = exp(-x_1^2), R = exp(-(2 x_1 + step) step), q = exp(-2 step^2)
 // (gauss = false when the Gaussian is negligible for the whole warp step).  Nodes are processed in groups
 // of FSB_TAU_NODE_GROUP, interleaved within a group for instruction-level parallelism (the table lookups of
 // a group are in flight together); the Gaussians come from the node recurrence, carried across groups.
@@ -234,7 +234,7 @@ __device__ __forceinline__ void node_sum_near(double xb, double step, const doub
     else node_sum_near_g<NL, false>(xb, step, sl, tab, U0, R, q, lmask, tot);
 }
 
-// FAR: every node at |x| >= 16 (the Gaussian is < e^-256).  Lanes with nodes inside compute garbage
+// FAR: every node at |x| >= 12 (the Gaussian is < e^-144).  Lanes with nodes inside compute garbage
 // (possibly inf/NaN) that the caller discards.
 template <int NL>
 __device__ __forceinline__ void node_sum_far(double xb, double step, const double *__restrict__ sl, unsigned lmask,
@@ -943,7 +943,7 @@ __device__ __noinline__ void setup_particle(const InterpConsts &C, double *__res
     SF(S_MODE) = (double) mode;
     // Route thresholds in outward pixels.  Upward run: nodes x_i(o) = X_i - o pix; downward run:
     // x_i(o) = X_i + (1 + o) pix; X_1 = xb0 + step <= X_7 = xb0 + 7 step.  The table covers |x| < 24 and the
-    // wing series |x| >= 16; margins of 0.01 dwarf the rounding of these expressions.
+    // wing series |x| >= 12; margins of 0.01 dwarf the rounding of these expressions.
     {
         const double X1 = xb0 + step, X7 = fma(7.0, step, xb0), ipix = 1.0 / pix;
         const double lim_n = FSB_GTAB_XMAX - 0.01 - hm, lim_f = kFarXMin + 0.01 + hm, xu = sqrt(fmin(xu2, 1e12)) + hm;
