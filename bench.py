@@ -442,7 +442,8 @@ def run_b200(args):
                          "k_tau_ms_per_rank": [round(v * 1e3, 3) for v in tau_launch_s_ranks],
                          "co_bound": "shared-memory wavefronts (l1tex data pipe ~50 % of peak) and issue slots (~57 %) "
                                      "run as hot as the FP64 pipe (~45 %): profiles/README.md"},
-            "index_build": {"bound": "hbm", "ms": index_s * 1e3, "algorithmic_bytes": index_bytes,
+            "index_build": {"bound": "hbm", "limited_by": "latency and atomics: two particle passes with data-dependent cell walks, "
+                            "then a per-list sort (DESIGN.md 6); the HBM figure is there for scale", "ms": index_s * 1e3, "algorithmic_bytes": index_bytes,
                             "achieved": index_bytes / index_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                             "frac": index_bytes / index_s / 1e9 / hbm_peak, "peak_source": hbm_src,
                             "share_of_step": index_s / (elapsed / args.steps)},
