@@ -285,19 +285,36 @@ extern "C" int fsb_particle_interpolate_multi_host(int32_t compute_tau, const fs
     FSB_TRY(compute.create());
     FSB_TRY(copy.create());
     cudaStream_t s = compute.s;
+    struct DrainGuard {  // no copy from or to the caller's buffers may outlive this call, on any path
+        cudaStream_t a, b;
+        ~DrainGuard()
+        {
+            cudaStreamSynchronize(a);
+            cudaStreamSynchronize(b);
+        }
+    } drain{compute.s, copy.s};
     DevBuf dpos, dvel, ddens, dtemp, dh, daxis, dcofm, dout;
     const size_t np = (size_t) npart, nl = (size_t) nlos;
+    // what the candidate search needs goes first on the compute stream; the rest of the particle data is uploaded on
+    // the copy stream while the index is being built, and joined before the accumulation kernels
     FSB_TRY(dpos.upload(pos, sizeof(float) * 3 * np, s));
-    // column density: nlines counts weight columns, dens is [nlines][npart]
-    FSB_TRY(ddens.upload(dens, sizeof(float) * np * (compute_tau ? 1 : (size_t) nlines), s));
     FSB_TRY(dh.upload(h, sizeof(float) * np, s));
-    if (compute_tau) {
-        FSB_REQUIRE(npart == 0 || (vel && temp), "vel/temp NULL with compute_tau");
-        FSB_TRY(dvel.upload(vel, sizeof(float) * 3 * np, s));
-        FSB_TRY(dtemp.upload(temp, sizeof(float) * np, s));
-    }
     FSB_TRY(daxis.upload(axis, sizeof(int32_t) * nl, s));
     FSB_TRY(dcofm.upload(cofm, sizeof(double) * 3 * nl, s));
+    // column density: nlines counts weight columns, dens is [nlines][npart]
+    FSB_TRY(ddens.upload(dens, sizeof(float) * np * (compute_tau ? 1 : (size_t) nlines), copy.s));
+    if (compute_tau) {
+        FSB_REQUIRE(npart == 0 || (vel && temp), "vel/temp NULL with compute_tau");
+        FSB_TRY(dvel.upload(vel, sizeof(float) * 3 * np, copy.s));
+        FSB_TRY(dtemp.upload(temp, sizeof(float) * np, copy.s));
+    }
+    cudaEvent_t uploaded;  // completion of the copy-stream uploads; the compute stream joins it after the index build
+    FSB_CUDA_TRY(cudaEventCreateWithFlags(&uploaded, cudaEventDisableTiming));
+    struct EventGuard {
+        cudaEvent_t e;
+        ~EventGuard() { cudaEventDestroy(e); }
+    } uploaded_guard{uploaded};
+    FSB_CUDA_TRY(cudaEventRecord(uploaded, copy.s));
     const size_t row_bytes = sizeof(double) * nl * (size_t) p[0].nbins;
     const size_t out_bytes = row_bytes * (size_t) nlines;
     FSB_TRY(dout.upload(nullptr, out_bytes, s));
@@ -305,6 +322,7 @@ extern "C" int fsb_particle_interpolate_multi_host(int32_t compute_tau, const fs
     bool delivered = false;
     int rc = FSB_OK;
     if (p[0].kernel == FSB_KERNEL_VORONOI) {
+        FSB_CUDA_TRY(cudaStreamWaitEvent(s, uploaded, 0));
         for (int32_t i = 0; i < nlines && rc == FSB_OK; ++i)
             rc = fsb_particle_interpolate(compute_tau, &p[compute_tau ? i : 0], (const float *) dpos.ptr, (const float *) dvel.ptr,
                                           (const float *) ddens.ptr + (compute_tau ? 0 : (size_t) i * np),
@@ -315,6 +333,13 @@ extern "C" int fsb_particle_interpolate_multi_host(int32_t compute_tau, const fs
         fsb_index *idx = nullptr;
         rc = fsb_index_build(p[0].box, (const double *) dcofm.ptr, (const int32_t *) daxis.ptr, nlos, (const float *) dpos.ptr,
                              (const float *) dh.ptr, npart, s, &idx);
+        if (rc == FSB_OK) {
+            const cudaError_t ew = cudaStreamWaitEvent(s, uploaded, 0);  // velocities, densities, temperatures are in
+            if (ew != cudaSuccess) {
+                set_error("cudaStreamWaitEvent: %s", cudaGetErrorString(ew));
+                rc = FSB_ECUDA;
+            }
+        }
         if (rc == FSB_OK) {
             if (compute_tau) {
                 rc = compute_tau_multi_impl(idx, p, nlines, (const float *) dpos.ptr, (const float *) dvel.ptr,
