@@ -1,31 +1,42 @@
-"""Sightlines at random positions (host-side mirror of the reference's randspectra.py:10-37)."""
+"""Spectra along randomly placed sightlines: the host-side counterpart of the reference's RandSpectra
+(randspectra.py:10-37), same constructor arguments and the same sightlines for a given seed."""
 import numpy as np
 
-from . import abstractsnapshot as absn
-from . import spectra
+from . import abstractsnapshot
+from .spectra import Spectra
 
 
-class RandSpectra(spectra.Spectra):
-    """``numlos`` sightlines along the x axis at positions drawn with ``np.random.seed(seed)``;
-    with ``thresh > 0`` sightlines are redrawn until ``ndla`` exceed the column-density threshold."""
+def _box_of(num, base):
+    """Box side (kpc/h) from the snapshot header."""
+    snap = abstractsnapshot.AbstractSnapshotFactory(num, base)
+    try:
+        return snap.get_header_attr("BoxSize")
+    finally:
+        del snap
+
+
+class RandSpectra(Spectra):
+    """``numlos`` sightlines parallel to the x axis through uniformly random points of the box.
+
+    The points come from numpy's global generator after ``np.random.seed(seed)``, which is what makes a run
+    repeatable and identical to the reference's for the same seed.  With a positive ``thresh`` (a column
+    density, or a [low, high] pair) sightlines are redrawn until ``ndla`` of them pass it
+    (``Spectra.replace_not_DLA`` for ``elem`` / ``ion``)."""
 
     def __init__(self, num, base, MPI=None, seed=23, ndla=1000, numlos=5000, thresh=10 ** 20.3,
                  savefile="rand_spectra_DLA.hdf5", elem="H", ion=1, **kwargs):
-        f = absn.AbstractSnapshotFactory(num, base)
-        self.box = f.get_header_attr("BoxSize")
-        del f
+        self.box = _box_of(num, base)
         self.NumLos = numlos
-        axis = np.ones(self.NumLos)  # 1 for x, 2 for y, 3 for z
         np.random.seed(seed)
-        cofm = self.get_cofm()
-        spectra.Spectra.__init__(self, num, base, cofm, axis, MPI, savefile=savefile, reload_file=True, load_halo=False,
-                                 **kwargs)
-        if np.size(thresh) > 1 or thresh > 0:
+        points = self.get_cofm()
+        x_axis = np.full(numlos, 1.0)  # axis ids are 1-based: 1 = x
+        super().__init__(num, base, points, x_axis, MPI, savefile=savefile, reload_file=True, load_halo=False, **kwargs)
+        wants_filter = np.size(thresh) > 1 or thresh > 0
+        if wants_filter:
             self.replace_not_DLA(ndla, thresh, elem=elem, ion=ion)
             print("Found objects over threshold")
 
     def get_cofm(self, num=None):
-        """More sightlines at uniformly random positions in the box."""
-        if num is None:
-            num = self.NumLos
-        return self.box * np.random.random_sample((num, 3))
+        """``num`` (default: NumLos) further points, uniform in the box, from numpy's global generator."""
+        count = self.NumLos if num is None else num
+        return np.random.random_sample((count, 3)) * self.box
