@@ -134,6 +134,18 @@ def near_lines(box, pos, h, axis, cofm):
     return out[:count.value]
 
 
+def count_pairs(box, pos, h, axis, cofm):
+    """Candidate particles per sightline (int32 CUDA tensor [nlos]) without building the lists: the count pass
+    that balances sightline blocks across GPUs (sharding.balanced_blocks)."""
+    lib = _lib.load()
+    counts = torch.empty(max(cofm.shape[0], 1), dtype=torch.int32, device=pos.device)
+    with torch.cuda.device(pos.device):
+        rc = lib.fsb_count_pairs(float(box), _dptr(pos), _dptr(h), pos.shape[0], _dptr(axis), _dptr(cofm),
+                                 cofm.shape[0], _dptr(counts), _stream())
+    _lib.check(rc, "fsb_count_pairs")
+    return counts[:cofm.shape[0]]
+
+
 def voigt_profile(x, y, voigt=_lib.VOIGT_FAST):
     """Re w(x + i y) on the device (test hook)."""
     lib = _lib.load()

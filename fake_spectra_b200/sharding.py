@@ -82,31 +82,39 @@ class Sharder:
         return slice(int(e[self.rank]), int(e[self.rank + 1]))
 
     # -- recombination -------------------------------------------------------------------------------
-    def combine(self, local, numlos):
-        """local: this rank's result (torch tensor, any device), [rows, ...] with rows = its
-        sightline block ("sightlines") or all sightlines ("particles").  Returns the full
-        [numlos, ...] tensor on every rank."""
+    def combine(self, local, numlos, dim=0):
+        """local: this rank's result (torch tensor, any device); dimension ``dim`` (0 or 1) runs over its
+        sightline block ("sightlines") or over all sightlines ("particles").  Returns the full tensor (``numlos``
+        along ``dim``) on every rank.
+
+        Sightline mode moves every block exactly once: a block of rows of a row-major array is contiguous, so
+        rank r's block is received straight into its place in the full array (one all-gather when the blocks are
+        equal, one broadcast per block otherwise: no padding, no staging copies)."""
         if self.size == 1:
             return local
         if self.mode == "particles":
             local = local.contiguous()
             dist.all_reduce(local, op=dist.ReduceOp.SUM, group=self.group)
             return local
+        if dim not in (0, 1):
+            raise ValueError("dim must be 0 or 1")
         if self.edges is None or self.edges[-1] != numlos:
             self.set_sightlines(numlos)
-        tail = tuple(local.shape[1:])
-        full = torch.zeros((numlos,) + tail, dtype=local.dtype, device=local.device)
+        local = local.contiguous()
+        lead = (1,) if dim == 0 else (local.shape[0],)
+        tail = tuple(local.shape[dim + 1:])
+        loc = local.view(lead + (local.shape[dim],) + tail)
+        full = torch.empty(lead + (numlos,) + tail, dtype=local.dtype, device=local.device)
         sizes = np.diff(self.edges)
-        if np.all(sizes == sizes[0]):
-            dist.all_gather_into_tensor(full, local.contiguous(), group=self.group)
-        else:
-            parts = [full[int(self.edges[r]):int(self.edges[r + 1])] for r in range(self.size)]
-            # all_gather wants equally shaped outputs: pad every block to the largest
-            big = int(sizes.max())
-            padded = torch.zeros((big,) + tail, dtype=local.dtype, device=local.device)
-            padded[:local.shape[0]] = local
-            recv = [torch.empty_like(padded) for _ in range(self.size)]
-            dist.all_gather(recv, padded, group=self.group)
-            for r, p in enumerate(parts):
-                p.copy_(recv[r][:p.shape[0]])
-        return full
+        for k in range(lead[0]):
+            if np.all(sizes == sizes[0]):
+                dist.all_gather_into_tensor(full[k], loc[k], group=self.group)
+            else:
+                for r in range(self.size):
+                    blk = full[k, int(self.edges[r]):int(self.edges[r + 1])]
+                    if r == self.rank:
+                        blk.copy_(loc[k])
+                    if blk.numel():
+                        dist.broadcast(blk, src=dist.get_global_rank(self.group, r) if self.group is not None else r,
+                                       group=self.group)
+        return full[0] if dim == 0 else full

@@ -444,14 +444,15 @@ class Spectra:
         return self._do_interpolation_work(pos, vel, elem_den, temp, hh, amumass, line, get_tau)
 
     def _combine(self, local):
-        """Recombine the ranks' pieces (torch tensor or numpy) into the full float64 numpy array."""
+        """Recombine the ranks' pieces [K, rows, nbins] (torch tensor or numpy; rows = this rank's sightline block, or
+        all sightlines in particle-sharded mode) into the full float64 numpy array [K, NumLos, nbins]."""
         import torch
         was_numpy = isinstance(local, np.ndarray)
         t = torch.from_numpy(np.ascontiguousarray(local, dtype=np.float64)) if was_numpy else local
         if self._sharder.size > 1:
             if was_numpy and self._cuda_available() and self._backend is _spectra_priv:
                 t = t.cuda()
-            t = self._sharder.combine(t, self.NumLos)
+            t = self._sharder.combine(t, self.NumLos, dim=1)
         return t.cpu().numpy() if t.is_cuda else t.numpy()
 
     def compute_spectra(self, elem, ion, ll, get_tau):
@@ -475,7 +476,7 @@ class Spectra:
                     acc += eng.tau([self._params(self._line(elem, ion, ll), eng.amumass) for ll in lls])
                 else:
                     acc += eng.colden(self._params(self.lines[("H", 1)][1215], eng.amumass))
-            local = acc.permute(1, 0, 2).contiguous()  # rows first for the gather
+            local = acc
         else:
             arepo = self.kernel_int == 2
             out = []
@@ -486,9 +487,8 @@ class Spectra:
                 for nn in range(1, nseg):
                     result += self._interpolate_single_file(nn, elem, ion, ll, get_tau)
                 out.append(result)
-            local = np.stack(out, axis=1)
-        result = self._combine(local)  # [NumLos, nl, nbins]
-        result = np.ascontiguousarray(np.transpose(result, (1, 0, 2)))
+            local = np.stack(out, axis=0)
+        result = self._combine(local)  # [nl, NumLos, nbins]
         if self.MPI is not None:
             # the reference's MPI mode: ranks hold different particles, float32 sum (spectra.py:828-830)
             result = np.ascontiguousarray(result, np.float32)
@@ -570,11 +570,7 @@ class Spectra:
             acc = r if acc is None else acc + r
         if acc is None:
             acc = np.zeros((nweights, nlocal, self.nbins))
-        if isinstance(acc, np.ndarray):
-            local = np.ascontiguousarray(np.transpose(acc, (1, 0, 2)))
-        else:
-            local = acc.permute(1, 0, 2).contiguous()
-        result = np.transpose(self._combine(local), (1, 0, 2))
+        result = self._combine(acc)
         den = np.array(self.get_density(elem, ion))
         den[np.where(den == 0.)] = 1
         return result / den[None, :, :]
