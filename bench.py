@@ -204,7 +204,8 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
 
     def barrier():
         if world > 1:
@@ -253,7 +254,7 @@ def run_b200(args):
     setup_s = time.perf_counter() - t_setup
 
     state = {}
-    ev = {"count": [], "index": [], "tau": [], "gather": []}
+    ev = {"count": [], "index": [], "tau": [], "gather": [], "ion": []}
 
     def timed(key, fn, on):
         if not on:
@@ -266,30 +267,46 @@ def run_b200(args):
         return r
 
     def my_block(on):
-        """This rank's sightline block: contiguous, balanced by candidate pairs (one count pass over all sightlines;
-        every rank holds the same particles, so all ranks derive the same edges without a collective)."""
+        """This rank's sightline block: contiguous, balanced by candidate pairs.  Every rank counts the pairs of ALL
+        sightlines against its slice of the (replicated) particle set, the int32 counts are summed over NCCL, and every
+        rank derives the same edges from the same totals; the counts of its own block then size its candidate lists
+        (fsb_index_build_counted), so no rank makes a counting pass over the whole particle set."""
         if pshard or world == 1:
-            return slice(0, L)
-        counts = timed("count", lambda: native.count_pairs(w["box"], t["pos"], t["h"], t["axis"], t["cofm"]), on)
+            return slice(0, L), None
+
+        def count():
+            pe = sharding.even_blocks(w["npart"], world)
+            ps = slice(int(pe[rank]), int(pe[rank + 1]))
+            c = native.count_pairs(w["box"], t["pos"][ps], t["h"][ps], t["axis"], t["cofm"])
+            dist.all_reduce(c, op=dist.ReduceOp.SUM)
+            return c
+        counts = timed("count", count, on)
         sharder.set_sightlines(L, weights=counts.cpu().numpy())
-        return sharder.my_sightlines(L)
+        sl = sharder.my_sightlines(L)
+        return sl, counts[sl].contiguous()
 
     def step(time_parts=False, counters=None):
-        sl = my_block(time_parts)
+        sl, my_counts = my_block(time_parts)
         nloc = sl.stop - sl.start
         cofm, axis = t["cofm"][sl].contiguous(), t["axis"][sl].contiguous()
         out = state.get("out")
         if out is None or out.shape[1] != nloc:
             out = state["out"] = torch.empty((nlines, nloc, nbins), dtype=torch.float64, device=dev)
         out.zero_()
-        idx = timed("index", lambda: native.CandidateIndex(w["box"], cofm, axis, t["pos"], t["h"]), time_parts)
+        idx = timed("index", lambda: native.CandidateIndex(w["box"], cofm, axis, t["pos"], t["h"], counts=my_counts), time_parts)
 
         def all_tau():
             r0 = 0
+            marks = [torch.cuda.Event(enable_timing=True) for _ in range(len(groups) + 1)] if time_parts else None
             for gi, (ion, lns) in enumerate(groups):
+                if marks:
+                    marks[gi].record()
                 idx.compute_tau(params[ion], t["pos"], t["vel"], dens[ion], t["temp"], t["h"], out=out[r0:r0 + len(lns)],
                                 counters=None if counters is None else counters[gi])
                 r0 += len(lns)
+            if marks:
+                marks[-1].record()
+                ev["ion"].append(marks)
         timed("tau", all_tau, time_parts)
         state["npairs"], state["sl"] = idx.npairs, sl
         idx.free()
@@ -367,6 +384,10 @@ def run_b200(args):
     flop_ranks = gather_ranks(float(algo_flop_step))
     achieved = max(flop_ranks) / tau_s / 1e12  # per GPU: the rank with the most work
     index_ms_ranks, count_ms_ranks, gather_ms_ranks = gather_ranks(mean_ms("index")), gather_ranks(mean_ms("count")), gather_ranks(mean_ms("gather"))
+    # every cross-rank figure of the JSON line is gathered HERE, by all ranks (rank 0 alone prints)
+    voigt_all = sum(gather_ranks(float(n_voigt_step)))
+    pairs_ranks = gather_ranks(float(npairs))
+    lines_ranks = gather_ranks(float(state["sl"].stop - state["sl"].start))
     full = state["full"]
     sanity = float(full[0].mean().item())
     hbm, hbm_src = hbm_peak()
@@ -490,8 +511,8 @@ def run_b200(args):
                        "step": "(N>1: pair count + block edges,) index build, tau of all lines of all ions for every sightline"
                                "(, N>1: gather of the rows), inputs resident in HBM",
                        "setup_s": round(setup_s, 1)},
-            "pairs_per_s": pairs_per_s, "pairs_per_step": total_pairs, "voigt_evals_per_step": sum(gather_ranks(float(n_voigt_step))),
-            "voigt_evals_per_s": sum(gather_ranks(float(n_voigt_step))) * args.steps / elapsed,
+            "pairs_per_s": pairs_per_s, "pairs_per_step": total_pairs, "voigt_evals_per_step": voigt_all,
+            "voigt_evals_per_s": voigt_all * args.steps / elapsed,
             "roofline": {"bound": "fp32" if fp32 else "fp64", "kernel": "k_tau", "achieved": achieved, "peak": fma_peak, "unit": "TFLOP/s",
                          "frac": achieved / fma_peak, "traffic": traffic,
                          "note": ("algorithmic FP32 flop" if fp32 else "algorithmic FP64 flop") + " of the profile evaluation (DESIGN.md 5): %.0f per Voigt "
@@ -502,15 +523,17 @@ def run_b200(args):
                          "reference_equivalent_tflops": FLOP_PER_VOIGT_REFERENCE * n_voigt_step / tau_s / 1e12,
                          "march_steps_by_route": dict(zip(["near_gauss", "near", "far", "straddle", "slow_or_subsampled"], [int(v) for v in routes])),
                          "tau_share_of_step": tau_s * 1e3 / step_ms,
-                         "k_tau_ms_per_rank": [round(v, 3) for v in tau_ms_ranks]},
+                         "k_tau_ms_per_rank": [round(v, 3) for v in tau_ms_ranks],
+                         "k_tau_ms_per_ion_pass": {groups[gi][0]: round(float(np.mean([m[gi].elapsed_time(m[gi + 1]) for m in ev["ion"]])), 3)
+                                                   for gi in range(len(groups))} if ev["ion"] else None},
             "index_build": {"bound": "hbm", "ms": index_s * 1e3, "ms_per_rank": [round(v, 3) for v in index_ms_ranks],
                             "algorithmic_bytes": index_bytes, "achieved": index_bytes / index_s / 1e9, "peak": hbm, "unit": "GB/s",
                             "frac": index_bytes / index_s / 1e9 / hbm, "peak_source": hbm_src, "share_of_step": index_s * 1e3 / step_ms,
                             "note": "16 B per particle per axis group read + 16 B per pair written (particle, dr2, traversal order)"},
             "multi_gpu": None if world == 1 else {"count_pairs_ms_per_rank": [round(v, 3) for v in count_ms_ranks],
                                                   "gather_ms_per_rank": [round(v, 3) for v in gather_ms_ranks],
-                                                  "pairs_per_rank": [int(v) for v in gather_ranks(float(npairs))],
-                                                  "sightlines_per_rank": [int(v) for v in gather_ranks(float(state["sl"].stop - state["sl"].start))],
+                                                  "pairs_per_rank": [int(v) for v in pairs_ranks],
+                                                  "sightlines_per_rank": [int(v) for v in lines_ranks],
                                                   "weak_replicas": weak},
             "parity_check": parity,
             "cpu_baseline": cpu, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),

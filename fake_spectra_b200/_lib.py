@@ -39,6 +39,7 @@ SIGNATURES = {
     "fsb_kernel_launches": (C.c_uint64, []),
     "fsb_device_info": (C.c_int, [C.POINTER(C.c_int32)] * 4),
     "fsb_index_build": (C.c_int, [C.c_double, _P, _P, C.c_int32, _P, _P, C.c_int64, _P, C.POINTER(_P)]),
+    "fsb_index_build_counted": (C.c_int, [C.c_double, _P, _P, C.c_int32, _P, _P, C.c_int64, _P, _P, C.POINTER(_P)]),
     "fsb_index_free": (C.c_int, [_P, _P]),
     "fsb_index_sizes": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "fsb_index_export": (C.c_int, [_P, _P, _P, _P, _P]),

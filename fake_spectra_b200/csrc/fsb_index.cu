@@ -65,11 +65,15 @@ __device__ __forceinline__ int group_of_axis(int ax) { return ax == 1 ? 0 : (ax 
 
 __global__ void k_line_cells(const double *__restrict__ cofm, const int32_t *__restrict__ axis, int nlos,
                              AxisGrid g0, AxisGrid g1, AxisGrid g2, int32_t *__restrict__ cell_of_line,
-                             int32_t *__restrict__ cell_count)
+                             int32_t *__restrict__ cell_count, int32_t *__restrict__ bad_axis)
 {
     const int l = blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= nlos) return;
-    const int ax = axis[l];
+    int ax = axis[l];
+    if (ax < 1 || ax > 3) {  // reported by the caller at its next synchronisation: {line + 1, axis}
+        if (atomicCAS(&bad_axis[0], 0, l + 1) == 0) bad_axis[1] = ax;
+        ax = 1;
+    }
     const int grp = group_of_axis(ax);
     const AxisGrid g = grp == 0 ? g0 : (grp == 1 ? g1 : g2);
     double key, proj2;
@@ -89,43 +93,100 @@ __global__ void k_line_scatter(const double *__restrict__ cofm, const int32_t *_
     const int cell = cell_of_line[l];
     const int slot = cell_start[cell] + atomicAdd(&cursor[cell], 1);
     double k, p2;
-    line_coords(cofm, l, axis[l], k, p2);
+    const int ax = axis[l];
+    line_coords(cofm, l, (ax < 1 || ax > 3) ? 1 : ax, k, p2);
     line_id[slot] = l;
     key[slot] = k;
     proj2[slot] = p2;
 }
 
-// Union of up to three closed cell intervals -> disjoint ascending intervals (no cell twice).
-struct Spans {
-    int lo[3], hi[3], n;
-    __device__ __forceinline__ void add(int a, int b)
-    {
-        if (a > b) return;
-        lo[n] = a;
-        hi[n] = b;
-        ++n;
-    }
-    __device__ __forceinline__ void normalise()
-    {
-        // insertion sort by lo, then merge touching/overlapping neighbours
-        for (int i = 1; i < n; ++i)
-            for (int j = i; j > 0 && lo[j] < lo[j - 1]; --j) {
-                int t = lo[j]; lo[j] = lo[j - 1]; lo[j - 1] = t;
-                t = hi[j]; hi[j] = hi[j - 1]; hi[j - 1] = t;
-            }
-        int m = 0;
-        for (int i = 0; i < n; ++i) {
-            if (m > 0 && lo[i] <= hi[m - 1] + 1) {
-                if (hi[i] > hi[m - 1]) hi[m - 1] = hi[i];
-            } else {
-                lo[m] = lo[i];
-                hi[m] = hi[i];
-                ++m;
+// One axis group of one particle: walks the grid cells its kernel square can reach and applies the exact
+// predicate of index_table.cpp:22-113 to the sightlines binned there.
+//
+// Cells are enumerated from the UNWRAPPED square [first - h - eps, first + h + eps] x [second - h - eps,
+// second + h + eps] (eps = 1e-6 box, far above the float rounding of first +- h that the exact predicate
+// sees), taken modulo the grid: a superset of the cells that hold a line passing the predicate, whatever
+// side of the periodic box the particle's reach falls on (lines outside [0, box] sit in the edge cells,
+// where cell_of clamps them, and those are the cells a wrapped reach lands in).
+template <int MODE, int GRP>
+__device__ __forceinline__ void pairs_in_group(const LineTable &T, const AxisGrid g, float px, float py, float pz, float h,
+                                               double h2, int64_t p, int32_t *__restrict__ count,
+                                               const int64_t *__restrict__ offsets, int32_t *__restrict__ particle, bool &any)
+{
+    if (g.G == 0) return;
+    const double box = T.box;
+    // axis 1: (y,z); axis 2: (x,z); axis 3: (x,y)   (index_table.cpp:29-40,120-125)
+    const float first = GRP == 0 ? py : px;
+    const float second = GRP == 2 ? py : pz;
+
+    // B1, index_table.cpp:89-113: float add, wrap in double then round to float.
+    float ffp = __fadd_rn(first, h);
+    if ((double) ffp > box) ffp = __double2float_rn(__dsub_rn((double) ffp, box));
+    float ffm = __fsub_rn(first, h);
+    if (ffm < 0) ffm = __double2float_rn(__dadd_rn((double) ffm, box));
+    const bool wrapped = !(ffm <= ffp);
+    const double dffm = (double) ffm, dffp = (double) ffp;
+    // B2, index_table.cpp:52-68: wrap arithmetic stays in double here.
+    const float sfp = __fadd_rn(second, h);
+    const float sfm = __fsub_rn(second, h);
+    const double dsfp = (double) sfp, dsfm = (double) sfm;
+    const bool hi_wrap = dsfp > box;
+    const bool lo_wrap = sfm < 0;
+    const double wrap_hi = __dsub_rn(dsfp, box);  // lproj2 < sfp - box
+    const double wrap_lo = __dadd_rn(dsfm, box);  // lproj2 > sfm + box
+
+    const double eps = 1e-6 * box, reach = (double) h + eps;
+    const double fr0 = floor(((double) first - reach) * g.inv_cs), fr1 = floor(((double) first + reach) * g.inv_cs);
+    const double fc0 = floor(((double) second - reach) * g.inv_cs), fc1 = floor(((double) second + reach) * g.inv_cs);
+    if (!(fr1 >= fr0) || !(fc1 >= fc0)) return;  // NaN coordinates reach nothing
+    const int G = g.G;
+    const int nrow = (int) fmin(fr1 - fr0 + 1.0, (double) G), ncol = (int) fmin(fc1 - fc0 + 1.0, (double) G);
+    int row = (int) fmod(fr0, (double) G);
+    row += row < 0 ? G : 0;
+    int col0 = (int) fmod(fc0, (double) G);
+    col0 += col0 < 0 ? G : 0;
+    // the reach in columns: [col0, col0 + ncol) modulo G = one span, or two when it crosses the edge
+    const int span1_hi = min(col0 + ncol, G) - 1, span2_hi = col0 + ncol - G - 1;  // span 2 = [0, span2_hi] when >= 0
+    for (int rr = 0; rr < nrow; ++rr) {
+        const int32_t *cs = T.cell_start + g.cell_base + row * G;
+        row = row + 1 == G ? 0 : row + 1;
+        #pragma unroll 1
+        for (int sp = 0; sp < 2; ++sp) {
+            if (sp == 1 && span2_hi < 0) break;
+            const int beg = cs[sp == 0 ? col0 : 0];
+            const int end = cs[(sp == 0 ? span1_hi : span2_hi) + 1];
+            for (int s = beg; s < end; ++s) {
+                const double key = T.key[s];
+                // B1: lower_bound on both ends -> [ffm, ffp)
+                const bool in1 = !wrapped ? (key >= dffm && key < dffp) : (key < dffp || key >= dffm);
+                if (!in1) continue;
+                const double lp2 = T.proj2[s];
+                bool in2 = false;
+                if (hi_wrap && lp2 < wrap_hi) in2 = true;
+                else if (lo_wrap && lp2 > wrap_lo) in2 = true;
+                else in2 = (lp2 > dsfm && lp2 < dsfp);
+                if (!in2) continue;
+                // B3, index_table.cpp:70-87: separately rounded products and sum
+                double d1 = fabs(__dsub_rn((double) first, key));
+                if (d1 > 0.5 * box) d1 = __dsub_rn(box, d1);
+                double d2 = fabs(__dsub_rn((double) second, lp2));
+                if (d2 > 0.5 * box) d2 = __dsub_rn(box, d2);
+                const double dr2 = __dadd_rn(__dmul_rn(d1, d1), __dmul_rn(d2, d2));
+                if (!(dr2 <= h2)) continue;
+                if (MODE == 0) {
+                    atomicAdd(&count[T.line_id[s]], 1);
+                } else if (MODE == 1) {
+                    const int l = T.line_id[s];
+                    const int slot = atomicAdd(&count[l], 1);
+                    particle[offsets[l] + slot] = (int32_t) p;
+                } else {
+                    any = true;
+                    return;
+                }
             }
         }
-        n = m;
     }
-};
+}
 
 // MODE 0: count pairs per line.  MODE 1: fill the lists.  MODE 2: flag particles with >= 1 line.
 template <int MODE>
@@ -134,91 +195,22 @@ __global__ void __launch_bounds__(256) k_pairs(LineTable T, const float *__restr
                                                const int64_t *__restrict__ offsets, int32_t *__restrict__ particle,
                                                uint8_t *__restrict__ flag)
 {
-    const int64_t p = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= npart) return;
-    const float px = pos[3 * p], py = pos[3 * p + 1], pz = pos[3 * p + 2];
+    // positions arrive as [npart][3] floats: the CTA's 768 consecutive floats are staged through shared memory
+    // with coalesced 4-byte loads (a thread reading its own three floats touches every sector three times)
+    __shared__ float s_pos[3 * 256];
+    const int64_t p0 = (int64_t) blockIdx.x * 256;
+    const int nhere = (int) min((int64_t) 256, npart - p0);
+    for (int i = threadIdx.x; i < 3 * nhere; i += 256) s_pos[i] = pos[3 * p0 + i];
+    __syncthreads();
+    if ((int) threadIdx.x >= nhere) return;
+    const int64_t p = p0 + threadIdx.x;
+    const float px = s_pos[3 * threadIdx.x], py = s_pos[3 * threadIdx.x + 1], pz = s_pos[3 * threadIdx.x + 2];
     const float h = hh[p];
-    const double box = T.box;
     const double h2 = (double) __fmul_rn(h, h);  // float product: index_table.cpp:45
     bool any = false;
-
-    #pragma unroll 1
-    for (int grp = 0; grp < 3; ++grp) {
-        const AxisGrid g = T.grid[grp];
-        if (g.G == 0) continue;
-        // axis 1: (y,z); axis 2: (x,z); axis 3: (x,y)   (index_table.cpp:29-40,120-125)
-        const float first = grp == 0 ? py : px;
-        const float second = grp == 2 ? py : pz;
-
-        // B1, index_table.cpp:89-113: float add, wrap in double then round to float.
-        float ffp = __fadd_rn(first, h);
-        if ((double) ffp > box) ffp = __double2float_rn(__dsub_rn((double) ffp, box));
-        float ffm = __fsub_rn(first, h);
-        if (ffm < 0) ffm = __double2float_rn(__dadd_rn((double) ffm, box));
-        const bool wrapped = !(ffm <= ffp);
-        const double dffm = (double) ffm, dffp = (double) ffp;
-        Spans P;
-        P.n = 0;
-        if (!wrapped) {
-            P.add(cell_of(dffm, g.inv_cs, g.G), cell_of(dffp, g.inv_cs, g.G));
-        } else {
-            P.add(0, cell_of(dffp, g.inv_cs, g.G));
-            P.add(cell_of(dffm, g.inv_cs, g.G), g.G - 1);
-        }
-        P.normalise();
-
-        // B2, index_table.cpp:52-68: wrap arithmetic stays in double here.
-        const float sfp = __fadd_rn(second, h);
-        const float sfm = __fsub_rn(second, h);
-        const double dsfp = (double) sfp, dsfm = (double) sfm;
-        const bool hi_wrap = dsfp > box;
-        const bool lo_wrap = sfm < 0;
-        const double wrap_hi = __dsub_rn(dsfp, box);  // lproj2 < sfp - box
-        const double wrap_lo = __dadd_rn(dsfm, box);  // lproj2 > sfm + box
-        Spans S;
-        S.n = 0;
-        S.add(cell_of(dsfm, g.inv_cs, g.G), cell_of(dsfp, g.inv_cs, g.G));
-        if (hi_wrap) S.add(0, cell_of(wrap_hi, g.inv_cs, g.G));
-        if (lo_wrap) S.add(cell_of(wrap_lo, g.inv_cs, g.G), g.G - 1);
-        S.normalise();
-
-        for (int ip = 0; ip < P.n && !(MODE == 2 && any); ++ip)
-            for (int row = P.lo[ip]; row <= P.hi[ip] && !(MODE == 2 && any); ++row)
-                for (int is = 0; is < S.n && !(MODE == 2 && any); ++is) {
-                    const int c0 = g.cell_base + row * g.G;
-                    const int beg = T.cell_start[c0 + S.lo[is]];
-                    const int end = T.cell_start[c0 + S.hi[is] + 1];
-                    for (int s = beg; s < end && !(MODE == 2 && any); ++s) {
-                        const double key = T.key[s];
-                        // B1: lower_bound on both ends -> [ffm, ffp)
-                        const bool in1 = !wrapped ? (key >= dffm && key < dffp) : (key < dffp || key >= dffm);
-                        if (!in1) continue;
-                        const double lp2 = T.proj2[s];
-                        bool in2 = false;
-                        if (hi_wrap && lp2 < wrap_hi) in2 = true;
-                        else if (lo_wrap && lp2 > wrap_lo) in2 = true;
-                        else in2 = (lp2 > dsfm && lp2 < dsfp);
-                        if (!in2) continue;
-                        // B3, index_table.cpp:70-87: separately rounded products and sum
-                        double d1 = fabs(__dsub_rn((double) first, key));
-                        if (d1 > 0.5 * box) d1 = __dsub_rn(box, d1);
-                        double d2 = fabs(__dsub_rn((double) second, lp2));
-                        if (d2 > 0.5 * box) d2 = __dsub_rn(box, d2);
-                        const double dr2 = __dadd_rn(__dmul_rn(d1, d1), __dmul_rn(d2, d2));
-                        if (!(dr2 <= h2)) continue;
-                        if (MODE == 0) {
-                            atomicAdd(&count[T.line_id[s]], 1);
-                        } else if (MODE == 1) {
-                            const int l = T.line_id[s];
-                            const int slot = atomicAdd(&count[l], 1);
-                            particle[offsets[l] + slot] = (int32_t) p;
-                        } else {
-                            any = true;
-                        }
-                    }
-                }
-        if (MODE == 2 && any) break;
-    }
+    pairs_in_group<MODE, 0>(T, T.grid[0], px, py, pz, h, h2, p, count, offsets, particle, any);
+    if (!(MODE == 2 && any)) pairs_in_group<MODE, 1>(T, T.grid[1], px, py, pz, h, h2, p, count, offsets, particle, any);
+    if (!(MODE == 2 && any)) pairs_in_group<MODE, 2>(T, T.grid[2], px, py, pz, h, h2, p, count, offsets, particle, any);
     if (MODE == 2) flag[p] = any ? 1 : 0;
 }
 
@@ -414,37 +406,23 @@ __global__ void __launch_bounds__(1024) k_flag_compact(const uint8_t *__restrict
 }
 
 struct BuiltTable {
-    Scratch cell_start, line_id, key, proj2;
+    Scratch cell_start, line_id, key, proj2, bad_axis;
     LineTable T;
 };
 
-// Bin the sightlines of each axis group on its perpendicular grid.
-int build_line_table(double box, const double *cofm, const int32_t *axis, int32_t nlos, cudaStream_t stream,
+// Bin the sightlines of each axis group on its perpendicular grid.  The grid is sized by the PARTICLES' reach
+// (cells of about two mean particle spacings: a particle then reaches a handful of cells whatever the number of
+// sightlines, and with few sightlines most of those cells are empty), but never coarser than one sightline per
+// cell.  No host synchronisation: an axis outside 1..3 is recorded in bad_axis (device) for check_axes().
+int build_line_table(double box, const double *cofm, const int32_t *axis, int32_t nlos, int64_t npart, cudaStream_t stream,
                      BuiltTable &bt)
 {
-    // group sizes are needed on the host to pick the grids
-    std::vector<int32_t> h_axis(nlos > 0 ? nlos : 1);
-    FSB_CUDA_TRY(cudaMemcpyAsync(h_axis.data(), axis, sizeof(int32_t) * (size_t) nlos, cudaMemcpyDeviceToHost, stream));
-    FSB_CUDA_TRY(cudaStreamSynchronize(stream));
-    int64_t ngrp[3] = {0, 0, 0};
-    for (int32_t i = 0; i < nlos; ++i) {
-        if (h_axis[i] < 1 || h_axis[i] > 3) {
-            set_error("axis[%d] = %d: sightline axes are 1-based, 1..3 (spectra.py:681-683)", i, h_axis[i]);
-            return FSB_EINVAL;
-        }
-        ngrp[h_axis[i] - 1]++;
-    }
+    int G = (int) llround(cbrt((double) std::max<int64_t>(npart, 1)) / 2.0);
+    G = std::max(G, (int) ceil(sqrt((double) std::max(nlos, 1))));
+    G = std::max(1, std::min(G, kMaxGrid));
     int32_t total_cells = 0;
     for (int g = 0; g < 3; ++g) {
         AxisGrid &ag = bt.T.grid[g];
-        if (ngrp[g] == 0) {
-            ag.G = 0;
-            ag.cell_base = total_cells;
-            ag.inv_cs = 0;
-            continue;
-        }
-        int G = (int) ceil(sqrt((double) ngrp[g]));
-        G = std::max(1, std::min(G, kMaxGrid));
         ag.G = G;
         ag.cell_base = total_cells;
         ag.inv_cs = (double) G / box;
@@ -458,12 +436,14 @@ int build_line_table(double box, const double *cofm, const int32_t *axis, int32_
     FSB_TRY(bt.line_id.alloc(sizeof(int32_t) * (size_t) std::max(nlos, 1), stream));
     FSB_TRY(bt.key.alloc(sizeof(double) * (size_t) std::max(nlos, 1), stream));
     FSB_TRY(bt.proj2.alloc(sizeof(double) * (size_t) std::max(nlos, 1), stream));
+    FSB_TRY(bt.bad_axis.alloc(sizeof(int32_t) * 2, stream));
+    FSB_CUDA_TRY(cudaMemsetAsync(bt.bad_axis.ptr, 0, sizeof(int32_t) * 2, stream));
     FSB_CUDA_TRY(cudaMemsetAsync(cell_count.ptr, 0, sizeof(int32_t) * (size_t) (total_cells + 1), stream));
     FSB_CUDA_TRY(cudaMemsetAsync(cursor.ptr, 0, sizeof(int32_t) * (size_t) (total_cells + 1), stream));
     if (nlos > 0) {
         const int threads = 256, blocks = (nlos + threads - 1) / threads;
         count_launch(); k_line_cells<<<blocks, threads, 0, stream>>>(cofm, axis, nlos, bt.T.grid[0], bt.T.grid[1], bt.T.grid[2],
-                                                     cell_of_line.as<int32_t>(), cell_count.as<int32_t>());
+                                                     cell_of_line.as<int32_t>(), cell_count.as<int32_t>(), bt.bad_axis.as<int32_t>());
         count_launch(); k_scan_single<int32_t, int32_t><<<1, 1024, 0, stream>>>(cell_count.as<int32_t>(), bt.cell_start.as<int32_t>(),
                                                                  total_cells, nullptr);
         count_launch(); k_line_scatter<<<blocks, threads, 0, stream>>>(cofm, axis, nlos, cell_of_line.as<int32_t>(),
@@ -481,6 +461,16 @@ int build_line_table(double box, const double *cofm, const int32_t *axis, int32_
     return FSB_OK;
 }
 
+// After the caller's synchronisation point: turns a recorded bad axis into FSB_EINVAL.
+int check_axes(const int32_t h_bad[2])
+{
+    if (h_bad[0] != 0) {
+        set_error("axis[%d] = %d: sightline axes are 1-based, 1..3 (spectra.py:681-683)", h_bad[0] - 1, h_bad[1]);
+        return FSB_EINVAL;
+    }
+    return FSB_OK;
+}
+
 }  // namespace
 
 }  // namespace fsb
@@ -488,7 +478,7 @@ int build_line_table(double box, const double *cofm, const int32_t *axis, int32_
 using namespace fsb;
 
 static int index_build_impl(fsb_index *idx, double box, const double *cofm, const int32_t *axis, int32_t nlos,
-                            const float *pos, const float *h, int64_t npart, cudaStream_t stream)
+                            const float *pos, const float *h, int64_t npart, const int32_t *counts_in, cudaStream_t stream)
 {
     const size_t nl = (size_t) std::max(nlos, 1);
     FSB_TRY(retain_pool_memory());
@@ -501,7 +491,7 @@ static int index_build_impl(fsb_index *idx, double box, const double *cofm, cons
     }
 
     BuiltTable bt;
-    FSB_TRY(build_line_table(box, cofm, axis, nlos, stream, bt));
+    FSB_TRY(build_line_table(box, cofm, axis, nlos, npart, stream, bt));
 
     Scratch count, max_list;
     FSB_TRY(count.alloc(sizeof(int32_t) * (nl + 1), stream));
@@ -509,16 +499,22 @@ static int index_build_impl(fsb_index *idx, double box, const double *cofm, cons
     FSB_CUDA_TRY(cudaMemsetAsync(count.ptr, 0, sizeof(int32_t) * (nl + 1), stream));
     const int threads = 256;
     const unsigned pblocks = (unsigned) ((npart + threads - 1) / threads);
-    if (npart > 0 && nlos > 0) {
+    // list sizes: counted here, or handed in by a caller that already ran fsb_count_pairs on these sightlines
+    if (counts_in) {
+        if (nlos > 0) FSB_CUDA_TRY(cudaMemcpyAsync(count.ptr, counts_in, sizeof(int32_t) * (size_t) nlos, cudaMemcpyDeviceToDevice, stream));
+    } else if (npart > 0 && nlos > 0) {
         count_launch(); k_pairs<0><<<pblocks, threads, 0, stream>>>(bt.T, pos, h, npart, count.as<int32_t>(), nullptr, nullptr, nullptr);
         FSB_CUDA_TRY(cudaGetLastError());
     }
     count_launch(); k_scan_single<int32_t, int64_t><<<1, 1024, 0, stream>>>(count.as<int32_t>(), idx->offsets, nlos, max_list.as<int64_t>());
     FSB_CUDA_TRY(cudaGetLastError());
     int64_t h_total = 0, h_max = 0;
+    int32_t h_bad[2] = {0, 0};
     FSB_CUDA_TRY(cudaMemcpyAsync(&h_total, idx->offsets + nlos, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
     FSB_CUDA_TRY(cudaMemcpyAsync(&h_max, max_list.ptr, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
+    FSB_CUDA_TRY(cudaMemcpyAsync(h_bad, bt.bad_axis.ptr, sizeof(h_bad), cudaMemcpyDeviceToHost, stream));
     FSB_CUDA_TRY(cudaStreamSynchronize(stream));
+    FSB_TRY(check_axes(h_bad));
     idx->npairs = h_total;
     idx->max_list = h_max;
 
@@ -562,8 +558,8 @@ static int index_build_impl(fsb_index *idx, double box, const double *cofm, cons
     return FSB_OK;
 }
 
-extern "C" int fsb_index_build(double box, const double *cofm, const int32_t *axis, int32_t nlos, const float *pos,
-                               const float *h, int64_t npart, void *stream_v, fsb_index **out)
+extern "C" int fsb_index_build_counted(double box, const double *cofm, const int32_t *axis, int32_t nlos, const float *pos,
+                                       const float *h, int64_t npart, const int32_t *counts, void *stream_v, fsb_index **out)
 {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
     FSB_REQUIRE(out != nullptr, "out is NULL");
@@ -577,13 +573,19 @@ extern "C" int fsb_index_build(double box, const double *cofm, const int32_t *ax
     idx->nlos = nlos;
     idx->npart = npart;
     idx->box = box;
-    const int rc = index_build_impl(idx, box, cofm, axis, nlos, pos, h, npart, stream);
+    const int rc = index_build_impl(idx, box, cofm, axis, nlos, pos, h, npart, counts, stream);
     if (rc != FSB_OK) {
         fsb_index_free(idx, stream);
         return rc;
     }
     *out = idx;
     return FSB_OK;
+}
+
+extern "C" int fsb_index_build(double box, const double *cofm, const int32_t *axis, int32_t nlos, const float *pos,
+                               const float *h, int64_t npart, void *stream_v, fsb_index **out)
+{
+    return fsb_index_build_counted(box, cofm, axis, nlos, pos, h, npart, nullptr, stream_v, out);
 }
 
 extern "C" int fsb_index_free(fsb_index *idx, void *stream_v)
@@ -631,7 +633,7 @@ extern "C" int fsb_near_lines(double box, const float *pos, const float *h, int6
     if (npart == 0 || nlos == 0) return FSB_OK;
     FSB_REQUIRE(pos && h && axis && cofm && out_index, "NULL array");
     BuiltTable bt;
-    FSB_TRY(build_line_table(box, cofm, axis, nlos, stream, bt));
+    FSB_TRY(build_line_table(box, cofm, axis, nlos, npart, stream, bt));
     Scratch flag, block_count, block_start;
     const int threads = 1024;
     const int64_t nblocks = (npart + threads - 1) / threads;
@@ -643,8 +645,11 @@ extern "C" int fsb_near_lines(double box, const float *pos, const float *h, int6
     count_launch(); k_scan_single<int32_t, int64_t><<<1, 1024, 0, stream>>>(block_count.as<int32_t>(), block_start.as<int64_t>(), nblocks, nullptr);
     count_launch(); k_flag_compact<<<(unsigned) nblocks, threads, 0, stream>>>(flag.as<uint8_t>(), npart, block_start.as<int64_t>(), out_index);
     FSB_CUDA_TRY(cudaGetLastError());
+    int32_t h_bad[2] = {0, 0};
+    FSB_CUDA_TRY(cudaMemcpyAsync(h_bad, bt.bad_axis.ptr, sizeof(h_bad), cudaMemcpyDeviceToHost, stream));
     FSB_CUDA_TRY(cudaMemcpyAsync(count, block_start.as<int64_t>() + nblocks, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
     FSB_CUDA_TRY(cudaStreamSynchronize(stream));
+    FSB_TRY(check_axes(h_bad));
     return FSB_OK;
 }
 
@@ -663,8 +668,12 @@ extern "C" int fsb_count_pairs(double box, const float *pos, const float *h, int
     if (npart == 0) return FSB_OK;
     FSB_REQUIRE(pos && h, "NULL array");
     BuiltTable bt;
-    FSB_TRY(build_line_table(box, cofm, axis, nlos, stream, bt));
+    FSB_TRY(build_line_table(box, cofm, axis, nlos, npart, stream, bt));
     count_launch(); k_pairs<0><<<(unsigned) ((npart + 255) / 256), 256, 0, stream>>>(bt.T, pos, h, npart, counts, nullptr, nullptr, nullptr);
     FSB_CUDA_TRY(cudaGetLastError());
-    return FSB_OK;
+    // the line table is released when this function returns: finish the pass first (also reports a bad axis)
+    int32_t h_bad[2] = {0, 0};
+    FSB_CUDA_TRY(cudaMemcpyAsync(h_bad, bt.bad_axis.ptr, sizeof(h_bad), cudaMemcpyDeviceToHost, stream));
+    FSB_CUDA_TRY(cudaStreamSynchronize(stream));
+    return check_axes(h_bad);
 }

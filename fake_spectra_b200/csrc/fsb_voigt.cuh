@@ -177,11 +177,6 @@ constexpr double kFarXMin = 12.0;     // the damping-wing series is used from he
 constexpr double kFastYMax = 0.03;    // above: voigt_exact (error of the y^7 truncation < 3e-13 below)
 constexpr double kFastYMin = 1e-30;   // below (and > 0): voigt_exact (Gaussian cut-off would pass exp underflow)
 
-// Global-memory master copy of the G(x) table (raw 8-byte words: three doubles, then five floats and a
-// pad per interval); kernels stage it in shared memory and address it as doubles.
-__device__ __align__(16) const unsigned long long d_gtable_words[FSB_GTAB_SIZE] = FSB_GTAB_WORDS;
-#define d_gtable (reinterpret_cast<const double *>(d_gtable_words))
-
 // FP32 fast path: degree-3 pieces on the same intervals, {c0, c1, c2, c3} per interval.
 __device__ __align__(16) const float d_gtable32[4 * FSB_GTAB_NINT] = FSB_GTAB32_VALUES;
 
@@ -215,43 +210,56 @@ __device__ __forceinline__ void fast_coefs(double y, FastCoef &c)
     c.y = y;
 }
 
-// Table index and offset of |x| < 16: k = rint(8|x|), t = |x| - k/8.
-__device__ __forceinline__ void g_index(double ax, int &k, double &t)
+// ---- the G(x) table (second generation: fsb_voigt_tables.h) ---------------------------------------------
+// 1537 intervals of width 1/64 centred on k/64, degree 4 in t = |x| - k/64; per interval two 16-byte pieces,
+// A = {c0, c1} and B = {c2, (float c3, float c4)}, kept in two arrays.  Kernels stage both arrays in shared
+// memory with the interval index SWIZZLED (slot = k ^ ((k >> 3) & 7)): the lanes of a quarter-warp hold
+// adjacent pixels, i.e. equally spaced intervals, and with a plain layout a spacing that is a multiple of 2, 4 or
+// 8 intervals would put their 16-byte pieces 2-, 4- or 8-fold into the same banks.
+__device__ __align__(16) const unsigned long long d_g2a_words[2 * FSB_G2_NINT] = FSB_G2_WORDS_A;
+__device__ __align__(16) const unsigned long long d_g2b_words[2 * FSB_G2_NINT] = FSB_G2_WORDS_B;
+constexpr int kG2Slots = (FSB_G2_NINT + 7) & ~7;  // slots per array (the swizzle permutes inside groups of 64)
+
+__device__ __forceinline__ int g2_slot(int k) { return k ^ ((k >> 3) & 7); }
+
+// k = rint(64 |x|), t = |x| - k/64.
+__device__ __forceinline__ void g2_index(double ax, int &k, double &t)
 {
-    const double magic = 6755399441055744.0;  // 1.5 * 2^52: low mantissa bits = rint(8|x|)
-    const double m = fma(ax, FSB_GTAB_INV_DELTA, magic);
+    const double magic = 6755399441055744.0;  // 1.5 * 2^52: low mantissa bits = rint(64|x|)
+    const double m = fma(ax, FSB_G2_INV_DELTA, magic);
     k = __double2loint(m);
-    t = fma(m - magic, -1.0 / FSB_GTAB_INV_DELTA, ax);
+    t = fma(m - magic, -1.0 / FSB_G2_INV_DELTA, ax);
 }
 
-// Degree-7 polynomial of one interval at offset t from its three 16-byte pieces {c0, c1}, {c2, (c3, c4)},
-// {(c5, c6), (c7, -)}: the t^3..t^7 part runs in single precision (|t| <= 1/16 scales its rounding error by
-// 2^-12 or less), the rest in double.
-__device__ __forceinline__ double g_poly(double2 v0, double2 v1, double2 v2, double t)
+// c0 + t (c1 + t (c2 + t (c3 + t c4))): the (c3 + t c4) pair in single precision (|t| <= 1/128 scales its rounding
+// error by 2^-21: < 3e-14 |c3|), the rest in double.
+__device__ __forceinline__ double g2_poly(double2 a, double2 b, double t)
 {
-    const float tf = (float) t;
-    float hi = __int_as_float(__double2loint(v2.y));                 // c7
-    hi = fmaf(hi, tf, __int_as_float(__double2hiint(v2.x)));         // c6
-    hi = fmaf(hi, tf, __int_as_float(__double2loint(v2.x)));         // c5
-    hi = fmaf(hi, tf, __int_as_float(__double2hiint(v1.y)));         // c4
-    hi = fmaf(hi, tf, __int_as_float(__double2loint(v1.y)));         // c3
-    return fma(fma(fma((double) hi, t, v1.x), t, v0.y), t, v0.x);
+    const float r = fmaf(__int_as_float(__double2hiint(b.y)), (float) t, __int_as_float(__double2loint(b.y)));
+    return fma(fma(fma((double) r, t, b.x), t, a.y), t, a.x);
 }
 
-__device__ __forceinline__ double g_eval(const double *__restrict__ tab, int k, double t)
-{
-    const double2 *c = reinterpret_cast<const double2 *>(tab + k * FSB_GTAB_STRIDE);
-    return g_poly(c[0], c[1], c[2], t);
-}
-
-// G(|x|) for |x| < 16 from the staged table (tab may be shared or global memory).
-__device__ __forceinline__ double g_table(double ax, const double *__restrict__ tab)
+// G(|x|) for |x| < FSB_GTAB_XMAX.  SWZ: tabA/tabB are the swizzled shared-memory copies; otherwise the global masters.
+template <bool SWZ>
+__device__ __forceinline__ double g2_table(double ax, const double2 *__restrict__ tabA, const double2 *__restrict__ tabB)
 {
     int k;
     double t;
-    g_index(ax, k, t);
-    k = k > FSB_GTAB_NINT - 1 ? FSB_GTAB_NINT - 1 : k;
-    return g_eval(tab, k, t);
+    g2_index(ax, k, t);
+    k = (int) min((unsigned) k, (unsigned) (FSB_G2_NINT - 1));
+    const int slot = SWZ ? g2_slot(k) : k;
+    return g2_poly(tabA[slot], tabB[slot], t);
+}
+
+// Stage both arrays into shared memory (swizzled).  smem holds 2 * kG2Slots double2.
+__device__ __forceinline__ void g2_stage(double2 *smem_tab, int tid, int nthreads)
+{
+    const double2 *ga = reinterpret_cast<const double2 *>(d_g2a_words), *gb = reinterpret_cast<const double2 *>(d_g2b_words);
+    for (int k = tid; k < FSB_G2_NINT; k += nthreads) {
+        const int slot = g2_slot(k);
+        smem_tab[slot] = ga[k];
+        smem_tab[kG2Slots + slot] = gb[k];
+    }
 }
 
 // Damping wing for |x| >= 12, u = 1/x^2:  H = (y/sqrt(pi)) u [P1(u) - (y^2 u) P3(u) + (y^2 u)^2 P5(u)],
@@ -287,11 +295,12 @@ __device__ __forceinline__ double voigt_far(double s, double y)
 }
 
 // One profile value with a known U = exp(-x^2) (or 0 where it is negligible).
+template <bool SWZ>
 __device__ __forceinline__ double voigt_fast_with_u(double ax, double s, double U, const FastCoef &c,
-                                                    const double *__restrict__ tab)
+                                                    const double2 *__restrict__ tabA, const double2 *__restrict__ tabB)
 {
     if (ax >= kFarXMin) return voigt_far(s, c.y);
-    const double G = g_table(ax, tab);
+    const double G = g2_table<SWZ>(ax, tabA, tabB);
     const double Pe = fma(fma(fma(c.pe[3], s, c.pe[2]), s, c.pe[1]), s, c.pe[0]);
     const double A = fma(fma(fma(c.a[3], s, c.a[2]), s, c.a[1]), s, c.a[0]);
     const double B = fma(fma(c.b[2], s, c.b[1]), s, c.b[0]);
@@ -299,11 +308,13 @@ __device__ __forceinline__ double voigt_fast_with_u(double ax, double s, double 
 }
 
 // Stand-alone evaluation (tests, and any caller without a shared U recurrence).
-__device__ __forceinline__ double voigt_fast(double x, const FastCoef &c, const double *__restrict__ tab)
+template <bool SWZ>
+__device__ __forceinline__ double voigt_fast(double x, const FastCoef &c, const double2 *__restrict__ tabA,
+                                             const double2 *__restrict__ tabB)
 {
     const double ax = fabs(x), s = x * x;
     const double U = s < c.xU2 ? exp(-s) : 0.0;
-    return voigt_fast_with_u(ax, s, U, c, tab);
+    return voigt_fast_with_u<SWZ>(ax, s, U, c, tabA, tabB);
 }
 
 // y == 0 (gamma = 0, spectra.py:669-672) takes the exact path, whose y == 0 branch is exp(-x^2).

@@ -29,7 +29,9 @@ def _need(t, dtype, name):
 class CandidateIndex:
     """Per-sightline candidate particle lists (replaces IndexTable + get_near_particles)."""
 
-    def __init__(self, box, cofm, axis, pos, h):
+    def __init__(self, box, cofm, axis, pos, h, counts=None):
+        """counts: optional int32 CUDA tensor [nlos] of list sizes from :func:`count_pairs` for these sightlines and
+        these particles (skips the counting pass)."""
         self.lib = _lib.load()
         self.box = float(box)
         _need(cofm, torch.float64, "cofm"), _need(axis, torch.int32, "axis")
@@ -38,9 +40,13 @@ class CandidateIndex:
         self.npart = pos.shape[0]
         self.device = pos.device
         handle = C.c_void_p()
+        if counts is not None:
+            _need(counts, torch.int32, "counts")
+            if counts.shape[0] != self.nlos:
+                raise ValueError("counts must have one entry per sightline")
         with torch.cuda.device(self.device):
-            rc = self.lib.fsb_index_build(self.box, _dptr(cofm), _dptr(axis), self.nlos, _dptr(pos), _dptr(h),
-                                          self.npart, _stream(), C.byref(handle))
+            rc = self.lib.fsb_index_build_counted(self.box, _dptr(cofm), _dptr(axis), self.nlos, _dptr(pos), _dptr(h),
+                                                  self.npart, _dptr(counts), _stream(), C.byref(handle))
         _lib.check(rc, "fsb_index_build")
         self.handle = handle
         nlos, npairs, mx = C.c_int32(), C.c_int64(), C.c_int64()

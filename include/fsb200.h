@@ -102,6 +102,12 @@ typedef struct fsb_index fsb_index;
  * Synchronises `stream` once (the pair count sizes the lists).  Free with fsb_index_free. */
 FSB_API int fsb_index_build(double box, const double *cofm, const int32_t *axis, int32_t nlos,
                     const float *pos, const float *h, int64_t npart, void *stream, fsb_index **out);
+/* Same, with the list sizes handed in: counts[nlos] int32 (DEVICE) = the output of fsb_count_pairs for exactly
+ * these sightlines against exactly these particles (e.g. summed over the ranks that each counted a slice of the
+ * particles).  Skips the counting pass over the particles.  Wrong counts are undefined behaviour. */
+FSB_API int fsb_index_build_counted(double box, const double *cofm, const int32_t *axis, int32_t nlos,
+                            const float *pos, const float *h, int64_t npart, const int32_t *counts,
+                            void *stream, fsb_index **out);
 FSB_API int fsb_index_free(fsb_index *idx, void *stream);
 /* sizes: number of sightlines, total candidate pairs, longest single list */
 FSB_API int fsb_index_sizes(const fsb_index *idx, int32_t *nlos, int64_t *npairs, int64_t *max_list);
@@ -162,7 +168,8 @@ FSB_API int fsb_near_lines_host(double box, const float *pos, const float *h, in
 
 /* Candidate pairs per sightline (the sizes of the lists fsb_index_build would make) without building them:
  * the count pass that balances sightline blocks across GPUs.  counts[nlos] int32, overwritten; DEVICE
- * pointers + stream, or HOST pointers (synchronous).  No reference counterpart (the reference shards particles). */
+ * pointers + stream (synchronised once), or HOST pointers (synchronous).  Counts are additive over any split of
+ * the particles: ranks may each count a slice and sum.  No reference counterpart (the reference shards particles). */
 FSB_API int fsb_count_pairs(double box, const float *pos, const float *h, int64_t npart, const int32_t *axis,
                     const double *cofm, int32_t nlos, int32_t *counts, void *stream);
 FSB_API int fsb_count_pairs_host(double box, const float *pos, const float *h, int64_t npart, const int32_t *axis,

@@ -64,6 +64,49 @@ def words(coef):
     return ["0x%016xull" % w for w in d + pairs]
 
 
+# ---- second-generation FP64 table: 32 bytes per interval ----------------------------------------------------
+# Intervals of width 1/64 centred on k/64 (|t| <= 1/128), degree 4: c0, c1 as doubles (array A, 16 bytes per
+# interval); c2 as a double and c3, c4 as floats (array B, 16 bytes per interval).  The tau kernel's shared-memory
+# pipe moves 4 bytes per lane per wavefront, so a lookup costs its bytes: 32 instead of 48.  Two separate arrays:
+# a quarter-warp of adjacent pixels reads 16-byte pieces of consecutive intervals, which are contiguous
+# (conflict-free) in each array.  With |t| <= 1/128 the float pair perturbs G by < 3e-14 |c3|; the error is the
+# truncation of the t^5 term.
+DELTA2, DEG2 = 1.0 / 64, 4
+NINT2 = int(XMAX / DELTA2) + 1
+
+
+def device_eval2(c, t):
+    """Device order: r = c4 t + c3 in float32 on float(t), then c2, c1, c0 in float64."""
+    tf = t.astype(np.float32)
+    r = (np.float32(c[4]) * tf + np.float32(c[3])).astype(np.float32)
+    g = r.astype(np.float64)
+    for j in (2, 1, 0):
+        g = g * t + float(c[j])
+    return g
+
+
+def table2():
+    import struct
+    rows, worst, worst_abs, worst_wing = [], 0.0, 0.0, 0.0
+    for k in range(NINT2):
+        coef, mid = fit((k - 0.5) * DELTA2, (k + 0.5) * DELTA2, DEG2)
+        rows.append(coef)
+        xs = np.linspace((k - 0.5) * DELTA2, (k + 0.5) * DELTA2, 17)
+        p = device_eval2(coef, xs - mid)
+        ex = np.array([float(G_exact(x)) for x in xs])
+        rel = np.abs(p - ex) / np.maximum(np.abs(ex), 0.02)
+        worst = max(worst, float(np.max(rel)))
+        worst_abs = max(worst_abs, float(np.max(np.abs(p - ex))))
+        if mid >= 3.0:
+            worst_wing = max(worst_wing, float(np.max(np.abs(p - ex) / np.abs(ex))))
+    a_words, b_words = [], []
+    for coef in rows:
+        a_words += ["0x%016xull" % struct.unpack("<Q", struct.pack("<d", float(coef[j])))[0] for j in (0, 1)]
+        f = [struct.unpack("<I", struct.pack("<f", float(coef[j])))[0] for j in (3, 4)]
+        b_words += ["0x%016xull" % struct.unpack("<Q", struct.pack("<d", float(coef[2])))[0], "0x%016xull" % (f[0] | (f[1] << 32))]
+    return a_words, b_words, worst, worst_abs, worst_wing
+
+
 def main():
     rows, worst, worst_abs = [], 0.0, 0.0
     for k in range(NINT):
@@ -100,6 +143,22 @@ def main():
             coef, _ = fit((k - 0.5) * DELTA, (k + 0.5) * DELTA, 3)
             f.write("    " + ", ".join("%.9ef" % (float(c) if abs(float(c)) > 1e-30 else 0.0) for c in coef) + ", \\\n")
         f.write("}\n")
+        a_words, b_words, w2, w2abs, w2wing = table2()
+        f.write("// Second-generation FP64 table: %d intervals centred on k/%d (k = 0..%d), degree %d in t = |x| - k/%d;\n"
+                % (NINT2, int(1 / DELTA2), NINT2 - 1, DEG2, int(1 / DELTA2)))
+        f.write("// array A = {c0, c1} doubles, array B = {c2 double, (c3, c4) floats, low word first}, 16 bytes per interval each.\n")
+        f.write("// Mixed-precision evaluation: max abs. error %.2e, max rel. error %.2e with G floored at 0.02,\n" % (w2abs, w2))
+        f.write("// max rel. error %.2e for |x| >= 3 (the damping wing, where G carries the profile).\n" % w2wing)
+        f.write("#define FSB_G2_NINT %d\n#define FSB_G2_INV_DELTA %.1f\n" % (NINT2, 1.0 / DELTA2))
+        f.write("#define FSB_G2_WORDS_A { \\\n")
+        for k in range(0, len(a_words), 4):
+            f.write("    " + ", ".join(a_words[k:k + 4]) + ", \\\n")
+        f.write("}\n")
+        f.write("#define FSB_G2_WORDS_B { \\\n")
+        for k in range(0, len(b_words), 4):
+            f.write("    " + ", ".join(b_words[k:k + 4]) + ", \\\n")
+        f.write("}\n")
+        print("table 2: max rel err %.2e (floored), abs %.2e, wing rel %.2e" % (w2, w2abs, w2wing))
     print("wrote", out, "max rel err %.2e, max abs err %.2e" % (worst, worst_abs))
 
 

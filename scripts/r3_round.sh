@@ -33,6 +33,8 @@ ncu) echo "== ncu full k_tau (c2, the timed launch)"
 ncuidx) echo "== ncu full index + colden kernels (c2)"
   timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'k_pairs|k_sort|k_colden|k_bin|k_fill|k_cand' -s 0 -c 8 -o $OUT/prof_idx_c2 \
     $B --workload c2_grid256_lya_lyb --steps 1 --warmup 0 --no-cpu-baseline --no-e2e > $OUT/prof_idx_c2.log 2>&1; tail -2 $OUT/prof_idx_c2.log | cut -c1-300;;
+multi) NG=${NG:-2}; WL=${WL:-c2_grid256_lya_lyb}; echo "== bench $WL on $NG GPUs (strong scaling)"
+  timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $NG --workload $WL --steps 3 --warmup 2 > $OUT/bench_${WL}_${NG}gpu.json 2> $OUT/bench_${WL}_${NG}gpu.err; tail -c 2500 $OUT/bench_${WL}_${NG}gpu.json; tail -5 $OUT/bench_${WL}_${NG}gpu.err;;
 sanitizer) echo "== compute-sanitizer"
   timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "golden or tiny or edge or voronoi" > $OUT/sanitizer_memcheck.log 2>&1; echo "rc=$?" >> $OUT/sanitizer_memcheck.log; tail -4 $OUT/sanitizer_memcheck.log
   timeout 1500 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "golden or tiny" > $OUT/sanitizer_racecheck.log 2>&1; echo "rc=$?" >> $OUT/sanitizer_racecheck.log; tail -4 $OUT/sanitizer_racecheck.log;;
