@@ -57,13 +57,14 @@ enum SharedField {
     S_THR_N,     // int2 {up, down}: outward pixels o < N have all nodes inside the table (|x| < 24)
     S_THR_F,     // int2: outward pixels o >= F have all nodes on the wing series (|x| >= 12)
     S_THR_G,     // int2: outward pixels o >= G are out of reach of the Gaussian
-    S_RECOK,     // 1 when the march-step recurrence is safe (all factors within e^+-500)
+    S_RECOK,     // int2 {1 when the march-step recurrence is safe (all factors within e^+-500), degree class: 1 = the
+                 // cubic terms of A(s) and Pe(s) matter for this particle, 0 = they are below 5e-13 of the profile}
     S_Q,         // exp(-2 step^2): second-order ratio of the Gaussian recurrence across nodes
     S_K16,       // exp(-2 D^2), D = 16 pixels in units of btherm: march-step recurrence of the Gaussian
     S_LU16,      // exp(+2 D step): ratio update of the inter-node factor, upward march
     S_LD16,      // exp(-2 D step): downward march
     S_KW0,       // 7 kernel weights x deltav                           singleabs.h:152-163
-    S_MODE = S_KW0 + 7,  // 0 skip, 1 fast, 2 exact, 3 sub-sampled pixels
+    S_MODE = S_KW0 + 7,  // 0 skip, 1 fast, 2 exact, 3 sub-sampled pixels (per-pixel fallback), 4 sub-sampled pixels (fast sums)
     S_VEL,       // velfac*pos + pvel                                  absorption.cpp:234
     S_INVB,      // 1/btherm
     S_HALFB,     // btherm/2: sub-sampling threshold                    singleabs.h:110
@@ -72,16 +73,22 @@ enum SharedField {
     S_PAD,       // mode 4: number of inner points per pixel (singleabs.h:116)
     S_COUNT
 };
+// Per fused line.  The profile is H = U Pe(s) + G A(s) + B(s) (fsb_voigt.cuh); every coefficient set below is
+// already multiplied by the line's amplitude CD = amp dens / velfac, so node sums come out as optical depths.
 enum LineField {
-    L_A0 = 0,    // A(s): 4 coefficients
-    L_PE0 = 4,   // Pe(s): 4 coefficients (exact mode: L_PE0 holds erfcx(aa))
-    L_BQ0 = 8,   // sum_i kw_i B(s_i) as a quartic in xb: 5 coefficients
-    L_CD = 13,   // amp*dens/velfac
-    L_Y,         // aa = voigt_fac/btherm
-    L_B0,        // B(s): 3 raw coefficients (generic route)
-    L_COUNT = L_B0 + 3
+    L_AC0 = 0,   // CD x A(s): 4 coefficients
+    L_PC0 = 4,   // CD x Pe(s): 4 coefficients
+    L_BQ0 = 8,   // CD x sum_i kw_i B(s_i) as a quartic in xb: 5 coefficients
+    L_FAR = 13,  // CD y / sqrt(pi): amplitude of the damping-wing series
+    L_Y2,        // y^2
+    L_CD,        // amp*dens/velfac
+    L_BC0,       // CD x B(s): 3 raw coefficients (generic route)
+    L_Y = L_BC0 + 3,  // aa = voigt_fac/btherm
+    L_ERFCX,     // exact mode: erfcx(aa)
+    L_COUNT = L_ERFCX + 2
 };
-static_assert(L_CD == L_BQ0 + 5 && (L_BQ0 + 4) % 2 == 0 && S_COUNT % 2 == 0 && L_COUNT % 2 == 0 && S_KW0 % 2 == 0 && S_Q % 2 == 0 && S_LU16 % 2 == 0, "16-byte field pairs");
+static_assert(L_FAR == L_BQ0 + 5 && L_BQ0 % 2 == 0 && L_Y2 % 2 == 0 && L_BC0 % 2 == 0 && S_COUNT % 2 == 0 && L_COUNT % 2 == 0 &&
+              S_KW0 % 2 == 0 && S_Q % 2 == 0 && S_LU16 % 2 == 0, "16-byte field pairs");
 template <int NL> struct SlabSize {
     static constexpr int kFields = S_COUNT + NL * L_COUNT;
     // record stride in doubles: an odd number of 16-byte units, so the 16 setup lanes spread over the banks
@@ -105,161 +112,114 @@ template <int NL> struct FSlabSize {
 #define LF2(l, f) (*reinterpret_cast<const double2 *>(sl + S_COUNT + (l) * L_COUNT + (f)))
 
 // ---- node sums ------------------------------------------------------------------------------------
-// All return sum_i kw_i H(x_i, y_l) for x_i = xb + (i+1) step, per fused line l.
+// All return tau_l = CD_l sum_i kw_i H(x_i, y_l) for x_i = xb + (i+1) step, per fused line l.
+//
+// The sums are taken in MOMENT form: with H = U Pe_l(s) + G A_l(s) + B_l(s), s = x^2, and Pe_l, A_l polynomials
+// in s whose coefficients depend on the line only,
+//     sum_i kw_i H(x_i, y_l) = sum_k pe_lk MU_k + sum_k a_lk MG_k + BQ_l(xb),
+//     MU_k = sum_i kw_i U(x_i) s_i^k,   MG_k = sum_i kw_i G(x_i) s_i^k,
+// so the per-node work (table lookup, Gaussian recurrence, 2 (DEG + 1) accumulations) does not depend on the
+// number of fused lines, and a line costs 2 (DEG + 1) + 5 multiply-adds per PIXEL.  DEG = 3 keeps the cubic terms
+// of A and Pe; DEG = 2 drops them for particles whose damping parameter makes them < 5e-13 of the profile
+// (setup_particle decides; nearly all H I gas above 2000 K).
 
 // NEAR: every node inside the table (|x| < 24).  U0 = exp(-x_1^2), R = exp(-(2 x_1 + step) step), q = exp(-2 step^2)
-// (gauss = false when the Gaussian is negligible for the whole warp step).  Nodes are processed in groups
-// of FSB_TAU_NODE_GROUP, interleaved within a group for instruction-level parallelism (the table lookups of
-// a group are in flight together); the Gaussians come from the node recurrence, carried across groups.
-// Lanes with nodes beyond the table compute finite garbage that the caller discards.  Totals are scaled
-// by the line amplitude L_CD.
-#ifndef FSB_TAU_NODE_GROUP
-#define FSB_TAU_NODE_GROUP 7
-#endif
-// One group of N nodes starting at node I0: table lookups in flight together, then the kernel-weighted table
-// value g[] and Gaussian uw[], then each fused line in turn (its coefficient pairs are loaded inside the loop and
-// a compiler barrier keeps the next line's loads from being hoisted: registers, not latency, are short here).
-template <int NL, int I0, int N, bool GAUSS>
-__device__ __forceinline__ void near_group(double xb, double step, const double *__restrict__ sl, const double *__restrict__ tab,
-                                           double &u, double &r, double q, unsigned lmask, double (&acc)[NL])
+// (GAUSS = false when the Gaussian is negligible for the whole warp step).  Lanes with nodes beyond the table
+// compute finite garbage that the caller discards.
+template <int NL, int DEG, bool GAUSS>
+__device__ __forceinline__ void node_sum_near_m(double xb, double step, const double *__restrict__ sl, const double2 *__restrict__ tabA,
+                                                double U0, double R, double q, unsigned lmask, double (&tot)[NL])
 {
-    double t[N], g[N];
-    {
-        const double2 *base[N];
-        double2 v0[N], v1[N], v2[N];
-        #pragma unroll
-        for (int i = 0; i < N; ++i) {
-            int k;
-            g_index(fabs(fma((double) (I0 + i + 1), step, xb)), k, t[i]);
-            k = (int) min((unsigned) k, (unsigned) (FSB_GTAB_NINT - 1));
-            base[i] = reinterpret_cast<const double2 *>(tab + k * FSB_GTAB_STRIDE);
-        }
-        #pragma unroll
-        for (int i = 0; i < N; ++i) v2[i] = base[i][2];
-        #pragma unroll
-        for (int i = 0; i < N; ++i) v1[i] = base[i][1];
-        #pragma unroll
-        for (int i = 0; i < N; ++i) v0[i] = base[i][0];
-#ifdef FSB_EXP_DBLLOAD
-        {   // timing experiment only: repeat the table loads (results feed an impossible accumulate)
-            double dummy = 0;
-            #pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                #pragma unroll
-                for (int i = 0; i < N; ++i) {
-                    double a, b;
-                    asm volatile("ld.volatile.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"((unsigned) __cvta_generic_to_shared(base[i] + j)));
-                    dummy += a + b;
-                }
-            }
-            if (dummy == 1.2345e300) acc[0] = dummy;
-        }
-#endif
-        #pragma unroll
-        for (int i = 0; i < N; ++i) g[i] = g_poly(v0[i], v1[i], v2[i], t[i]);
-    }
-    // t[] is reused for s = x^2; g[] becomes the kernel-weighted table value, uw[] the kernel-weighted Gaussian
-    double uw[N];
+    double MG[DEG + 1], MU[DEG + 1];
     #pragma unroll
-    for (int i = 0; i < N; ++i) {
-        const double x = fma((double) (I0 + i + 1), step, xb);
-        t[i] = x * x;
-        const double kw = SF(S_KW0 + I0 + i);
-        g[i] *= kw;
+    for (int k = 0; k <= DEG; ++k) MG[k] = 0, MU[k] = 0;
+    double u = U0, r = R;
+    #pragma unroll
+    for (int i = 0; i < 7; ++i) {
+        const double x = fma((double) (i + 1), step, xb);
+        int k;
+        double t;
+        g2_index(fabs(x), k, t);
+        k = (int) min((unsigned) k, (unsigned) (FSB_G2_NINT - 1));
+        const double2 *e = tabA + g2_slot(k);
+        const double g = g2_poly(e[0], e[kG2Slots], t);
+        const double s = x * x;
+        double w[DEG + 1];
+        w[0] = SF(S_KW0 + i);
+        #pragma unroll
+        for (int k2 = 1; k2 <= DEG; ++k2) w[k2] = w[k2 - 1] * s;
+        #pragma unroll
+        for (int k2 = 0; k2 <= DEG; ++k2) MG[k2] = fma(g, w[k2], MG[k2]);
         if (GAUSS) {
-            uw[i] = u * kw;
+            #pragma unroll
+            for (int k2 = 0; k2 <= DEG; ++k2) MU[k2] = fma(u, w[k2], MU[k2]);
             u *= r;
             r *= q;
         }
     }
     #pragma unroll
     for (int l = 0; l < NL; ++l) {
-        if (NL > 1 && !((lmask >> l) & 1u)) continue;
-        const double2 a01 = LF2(l, L_A0), a23 = LF2(l, L_A0 + 2);
-        double a = acc[l], a2 = 0;
-        if (GAUSS) {
-            const double2 p01 = LF2(l, L_PE0), p23 = LF2(l, L_PE0 + 2);
-            #pragma unroll
-            for (int i = 0; i < N; ++i) {
-                const double A = fma(fma(fma(a23.y, t[i], a23.x), t[i], a01.y), t[i], a01.x);
-                const double Pe = fma(fma(fma(p23.y, t[i], p23.x), t[i], p01.y), t[i], p01.x);
-                a = fma(uw[i], Pe, a);
-                a2 = fma(g[i], A, a2);
-            }
-        } else {
-            #pragma unroll
-            for (int i = 0; i < N; ++i) {
-                const double A = fma(fma(fma(a23.y, t[i], a23.x), t[i], a01.y), t[i], a01.x);
-                a2 = fma(g[i], A, a2);
-            }
-        }
-        acc[l] = a + a2;
-        if (NL > 1) asm volatile("" ::: "memory");
-    }
-}
-
-template <int NL, bool GAUSS>
-__device__ __forceinline__ void node_sum_near_g(double xb, double step, const double *__restrict__ sl, const double *__restrict__ tab,
-                                                double U0, double R, double q, unsigned lmask, double (&tot)[NL])
-{
-    static_assert(FSB_GTAB_DEG == 7 && FSB_GTAB_STRIDE == 6, "written for the 48-byte degree-7 table");
-    constexpr int G = FSB_TAU_NODE_GROUP;
-    double acc[NL];
-    #pragma unroll
-    for (int l = 0; l < NL; ++l) acc[l] = 0;
-    double u = U0, r = R;
-    near_group<NL, 0, (G < 7 ? G : 7), GAUSS>(xb, step, sl, tab, u, r, q, lmask, acc);
-    if (G < 7) near_group<NL, (G < 7 ? G : 0), (G < 7 ? (7 - G < G ? 7 - G : G) : 1), GAUSS>(xb, step, sl, tab, u, r, q, lmask, acc);
-    if (2 * G < 7) near_group<NL, (2 * G < 7 ? 2 * G : 0), (2 * G < 7 ? 7 - 2 * G : 1), GAUSS>(xb, step, sl, tab, u, r, q, lmask, acc);
-    static_assert(3 * G >= 7, "FSB_TAU_NODE_GROUP must be at least 3");
-    #pragma unroll
-    for (int l = 0; l < NL; ++l) {
         if (NL > 1 && !((lmask >> l) & 1u)) {
             tot[l] = 0;
             continue;
         }
-        // sum_i kw_i B(s_i): a quartic in xb; then the line amplitude
-        const double2 b01 = LF2(l, L_BQ0), b23 = LF2(l, L_BQ0 + 2), b4c = LF2(l, L_BQ0 + 4);
-        const double bq = fma(fma(fma(fma(b4c.x, xb, b23.y), xb, b23.x), xb, b01.y), xb, b01.x);
-        tot[l] = b4c.y * (acc[l] + bq);
+        // sum_i kw_i B(s_i): a quartic in xb
+        const double2 b01 = LF2(l, L_BQ0), b23 = LF2(l, L_BQ0 + 2);
+        double acc = fma(fma(fma(fma(LF(l, L_BQ0 + 4), xb, b23.y), xb, b23.x), xb, b01.y), xb, b01.x);
+        const double2 a01 = LF2(l, L_AC0), a23 = LF2(l, L_AC0 + 2);
+        acc = fma(a01.x, MG[0], acc);
+        acc = fma(a01.y, MG[1], acc);
+        acc = fma(a23.x, MG[2], acc);
+        if (DEG > 2) acc = fma(a23.y, MG[3], acc);
+        if (GAUSS) {
+            const double2 p01 = LF2(l, L_PC0), p23 = LF2(l, L_PC0 + 2);
+            double acu = p01.x * MU[0];
+            acu = fma(p01.y, MU[1], acu);
+            acu = fma(p23.x, MU[2], acu);
+            if (DEG > 2) acu = fma(p23.y, MU[3], acu);
+            acc += acu;
+        }
+        tot[l] = acc;
     }
 }
 
 template <int NL>
 __device__ __forceinline__ void node_sum_near(double xb, double step, const double *__restrict__ sl,
-                                              const double *__restrict__ tab, double U0, double R, double q, bool gauss,
-                                              unsigned lmask, double (&tot)[NL])
+                                              const double2 *__restrict__ tabA, double U0, double R, double q, bool gauss,
+                                              bool cubic, unsigned lmask, double (&tot)[NL])
 {
-    if (gauss) node_sum_near_g<NL, true>(xb, step, sl, tab, U0, R, q, lmask, tot);
-    else node_sum_near_g<NL, false>(xb, step, sl, tab, U0, R, q, lmask, tot);
+    if (cubic) {
+        if (gauss) node_sum_near_m<NL, 3, true>(xb, step, sl, tabA, U0, R, q, lmask, tot);
+        else node_sum_near_m<NL, 3, false>(xb, step, sl, tabA, U0, R, q, lmask, tot);
+    } else {
+        if (gauss) node_sum_near_m<NL, 2, true>(xb, step, sl, tabA, U0, R, q, lmask, tot);
+        else node_sum_near_m<NL, 2, false>(xb, step, sl, tabA, U0, R, q, lmask, tot);
+    }
 }
 
 // FAR: every node at |x| >= 12 (the Gaussian is < e^-144).  Lanes with nodes inside compute garbage
-// (possibly inf/NaN) that the caller discards.
+// (possibly inf/NaN) that the caller discards.  Also in moment form:
+//   H = (y/sqrt(pi)) u [P1(u) - v (P3(u) - v P5(u))], u = 1/x^2, v = y^2 u <= 3.6e-6 (far_polys, fsb_voigt.cuh), hence
+//   sum_i kw_i H = (y/sqrt(pi)) [F1 - y^2 F3 + y^4 F5],  F1 = sum kw u P1, F3 = sum kw u^2 P3, F5 = sum kw u^3 P5.
+// With u <= 1/144: the u^3.. tail of P1 (<= 5e-6 of P1, ten terms in all) runs in FP32, P3 stops at u^4 and P5 = 1
+// (what is dropped is below 3e-12 of H at y = 0.03, |x| = 12, and falls with y^2 and 1/x^2).
 template <int NL>
 __device__ __forceinline__ void node_sum_far(double xb, double step, const double *__restrict__ sl, unsigned lmask,
                                              double (&tot)[NL])
 {
-    const double isp = 0.56418958354775628694807945156;
-    double u[7], p1[7], p3[7], kw[7];
-    {
-        const double2 k01 = SF2(S_KW0), k23 = SF2(S_KW0 + 2), k45 = SF2(S_KW0 + 4), k6m = SF2(S_KW0 + 6);
-        kw[0] = k01.x, kw[1] = k01.y, kw[2] = k23.x, kw[3] = k23.y, kw[4] = k45.x, kw[5] = k45.y, kw[6] = k6m.x;
-    }
+    double F1 = 0, F3 = 0, F5 = 0;
     #pragma unroll
     for (int i = 0; i < 7; ++i) {
         const double x = fma((double) (i + 1), step, xb);
-        u[i] = fast_rcp(x * x);
-    }
-    // H = (y/sqrt(pi)) u [P1(u) - v (P3(u) - v P5(u))], v = y^2 u <= 3.6e-6 (far_polys, fsb_voigt.cuh).  Here, with
-    // u <= 1/144: the u^3.. tail of P1 (<= 5e-6 of P1, ten terms in all) runs in FP32, P3 stops at u^4 and P5 = 1
-    // (what is dropped is below 3e-12 of H at y = 0.03, |x| = 12, and falls with y^2 and 1/x^2).
-    #pragma unroll
-    for (int i = 0; i < 7; ++i) {
-        const float uf = (float) u[i];
+        const double u = fast_rcp(x * x);
+        const float uf = (float) u;
         const float tail = fmaf(fmaf(fmaf(fmaf(fmaf(fmaf(1278767.75f, uf, 134607.125f), uf, 15836.1328125f), uf, 2111.484375f), uf, 324.84375f), uf, 59.0625f), uf, 13.125f);
-        p1[i] = fma(fma(fma((double) tail, u[i], 3.75), u[i], 1.5), u[i], 1.0);
-        p3[i] = fma(fma(fma(fma(1082.8125, u[i], 157.5), u[i], 26.25), u[i], 5.0), u[i], 1.0);
+        const double p1 = fma(fma(fma((double) tail, u, 3.75), u, 1.5), u, 1.0);
+        const double p3 = fma(fma(fma(fma(1082.8125, u, 157.5), u, 26.25), u, 5.0), u, 1.0);
+        const double w1 = SF(S_KW0 + i) * u, w2 = w1 * u;
+        F1 = fma(w1, p1, F1);
+        F3 = fma(w2, p3, F3);
+        F5 = fma(w2, u, F5);
     }
     #pragma unroll
     for (int l = 0; l < NL; ++l) {
@@ -267,14 +227,8 @@ __device__ __forceinline__ void node_sum_far(double xb, double step, const doubl
             tot[l] = 0;
             continue;
         }
-        const double y = LF(l, L_Y), y2 = y * y;
-        double acc = 0;
-        #pragma unroll
-        for (int i = 0; i < 7; ++i) {
-            const double v = y2 * u[i];
-            acc = fma(u[i] * fma(-v, p3[i] - v, p1[i]), kw[i], acc);
-        }
-        tot[l] = (LF(l, L_CD) * isp * y) * acc;
+        const double y2 = LF(l, L_Y2);
+        tot[l] = LF(l, L_FAR) * fma(-y2, fma(-y2, F5, F3), F1);
     }
 }
 
@@ -358,47 +312,55 @@ __device__ __forceinline__ void node_sum_far32(float xb, float step, const float
 }
 
 // Generic per-node evaluation at velocity offset vouter for ONE line (mixed near/far warp steps and
-// sub-sampled pixels).
+// sub-sampled pixels).  Returns the optical depth (amplitude included).
 __device__ __noinline__ double node_sum_generic(double vouter, const double *__restrict__ sl, int l,
-                                                const double *__restrict__ tab)
+                                                const double2 *__restrict__ tabA)
 {
-    FastCoef fc;
-    #pragma unroll
-    for (int i = 0; i < 4; ++i) fc.pe[i] = LF(l, L_PE0 + i);
-    #pragma unroll
-    for (int i = 0; i < 4; ++i) fc.a[i] = LF(l, L_A0 + i);
-    #pragma unroll
-    for (int i = 0; i < 3; ++i) fc.b[i] = LF(l, L_B0 + i);
-    fc.xU2 = SF(S_XU2);
-    fc.y = LF(l, L_Y);
+    const double2 a01 = LF2(l, L_AC0), a23 = LF2(l, L_AC0 + 2), p01 = LF2(l, L_PC0), p23 = LF2(l, L_PC0 + 2);
+    const double b0 = LF(l, L_BC0), b1 = LF(l, L_BC0 + 1), b2 = LF(l, L_BC0 + 2);
+    const double xu2 = SF(S_XU2), y = LF(l, L_Y), cd = LF(l, L_CD);
     const double xb = fma(-vouter, SF(S_INVB), SF(S_XOFF)), step = SF(S_STEP);
     double total = 0;
     #pragma unroll 1
-    for (int i = 0; i < 7; ++i) total = fma(voigt_fast(fma((double) (i + 1), step, xb), fc, tab), SF(S_KW0 + i), total);
+    for (int i = 0; i < 7; ++i) {
+        const double x = fma((double) (i + 1), step, xb), ax = fabs(x), s = x * x;
+        double hval;
+        if (ax >= kFarXMin) {
+            hval = cd * voigt_far(s, y);
+        } else {
+            const double U = s < xu2 ? exp(-s) : 0.0;
+            const double G = g2_table<true>(ax, tabA, tabA + kG2Slots);
+            const double Pe = fma(fma(fma(p23.y, s, p23.x), s, p01.y), s, p01.x);
+            const double A = fma(fma(fma(a23.y, s, a23.x), s, a01.y), s, a01.x);
+            const double B = fma(fma(b2, s, b1), s, b0);
+            hval = fma(U, Pe, fma(G, A, B));
+        }
+        total = fma(hval, SF(S_KW0 + i), total);
+    }
     return total;
 }
 
 __device__ __noinline__ double node_sum_exact(double vouter, const double *__restrict__ sl, int l)
 {
     const double xb = fma(-vouter, SF(S_INVB), SF(S_XOFF)), step = SF(S_STEP);
-    const double y = LF(l, L_Y), erfcx_y = LF(l, L_PE0);
+    const double y = LF(l, L_Y), erfcx_y = LF(l, L_ERFCX);
     double total = 0;
     #pragma unroll 1
     for (int i = 0; i < 7; ++i) total += voigt_exact(fma((double) (i + 1), step, xb), y, erfcx_y) * SF(S_KW0 + i);
-    return total;
+    return LF(l, L_CD) * total;
 }
 
 // Pixel average tau_kern_outer (singleabs.h:104-126) for one line through the generic / exact
-// evaluators; returns the node sum (callers multiply by the amplitude) and the number of inner sums.
+// evaluators; returns the optical depth of the pixel and the number of inner sums.
 template <bool EXACT>
 __device__ __noinline__ double pixel_sum_slow(double vlow, double vhigh_px, const double *__restrict__ sl, int l,
-                                              const double *__restrict__ tab, int &ninner)
+                                              const double2 *__restrict__ tabA, int &ninner)
 {
     const double width = vhigh_px - vlow;
     if (width < SF(S_HALFB)) {
         ninner = 1;
         const double vmid = (vhigh_px + vlow) / 2.;
-        return EXACT ? node_sum_exact(vmid, sl, l) : node_sum_generic(vmid, sl, l, tab);
+        return EXACT ? node_sum_exact(vmid, sl, l) : node_sum_generic(vmid, sl, l, tabA);
     }
     const int npoints = (int) (2 * ceil(width / SF(S_HALFB) / 2) + 1.);
     const double dv = width / (npoints - 1);
@@ -406,7 +368,7 @@ __device__ __noinline__ double pixel_sum_slow(double vlow, double vhigh_px, cons
     for (int i = 0; i < npoints; ++i) {
         const double v = (i == 0) ? vlow : ((i == npoints - 1) ? vhigh_px : i * dv + vlow);
         const double wgt = (i == 0 || i == npoints - 1) ? 0.5 : 1.0;
-        total += wgt * (EXACT ? node_sum_exact(v, sl, l) : node_sum_generic(v, sl, l, tab));
+        total += wgt * (EXACT ? node_sum_exact(v, sl, l) : node_sum_generic(v, sl, l, tabA));
     }
     ninner = npoints;
     return total / (npoints - 1);
@@ -481,7 +443,7 @@ __device__ __forceinline__ void store_if(double *p, double v, bool pred)
 }
 
 template <int NL, bool COUNT, bool F32>
-__device__ __forceinline__ void march_fast(const double *__restrict__ sl, const float *__restrict__ fl, const double *__restrict__ tab,
+__device__ __forceinline__ void march_fast(const double *__restrict__ sl, const float *__restrict__ fl, const double2 *__restrict__ tab,
                                            const float4 *__restrict__ tab32, double *__restrict__ row0, int64_t line_stride, int nbins,
                                            double tautail, int lane, Tally &tally)
 {
@@ -494,7 +456,7 @@ __device__ __forceinline__ void march_fast(const double *__restrict__ sl, const 
     const int2 thrN = make_int2(__double2loint(nf.x), __double2hiint(nf.x));
     const int2 thrF = make_int2(__double2loint(nf.y), __double2hiint(nf.y));
     const int2 thrG = make_int2(__double2loint(gr.x), __double2hiint(gr.x));
-    const bool rec_ok = gr.y != 0.0;
+    const bool rec_ok = __double2loint(gr.y) != 0, cubic = __double2hiint(gr.y) != 0;
     unsigned live = half > 0 ? (kUpBits | kDnBits) : 0u;
     int near_lim = min(thrN.x, thrN.y), far_beg = max(thrF.x, thrF.y), gauss_end = max(thrG.x, thrG.y);
     double U0 = 0, R = 0, rho = 0;  // Gaussian recurrence state of this lane
@@ -559,7 +521,7 @@ __device__ __forceinline__ void march_fast(const double *__restrict__ sl, const 
                 } else {
                     rec_valid = false;
                 }
-                node_sum_near<NL>(xb, step, sl, tab, U0, R, qk.x, gauss, lmask, tot);
+                node_sum_near<NL>(xb, step, sl, tab, U0, R, qk.x, gauss, cubic, lmask, tot);
             }
             if (COUNT) ++tally.route[gauss ? 0 : 1];
         } else {
@@ -581,7 +543,7 @@ __device__ __forceinline__ void march_fast(const double *__restrict__ sl, const 
                         U0 = exp(-x1 * x1);
                         R = exp(-fma(2.0, x1, step) * step);
                     }
-                    node_sum_near<NL>(xb, step, sl, tab, U0, R, SF(S_Q), gauss, lmask, tot);
+                    node_sum_near<NL>(xb, step, sl, tab, U0, R, SF(S_Q), gauss, cubic, lmask, tot);
                 }
             }
             if (cls & 2u) {
@@ -601,7 +563,7 @@ __device__ __forceinline__ void march_fast(const double *__restrict__ sl, const 
                 if (lc == 2) {
                     #pragma unroll
                     for (int l = 0; l < NL; ++l)
-                        if ((lmask >> l) & 1u) tot[l] = LF(l, L_CD) * node_sum_generic((SF(S_XOFF) - xb) / SF(S_INVB), sl, l, tab);
+                        if ((lmask >> l) & 1u) tot[l] = node_sum_generic((SF(S_XOFF) - xb) / SF(S_INVB), sl, l, tab);
                 }
             }
             if (COUNT) ++tally.route[3];
@@ -638,7 +600,7 @@ __device__ __forceinline__ void march_fast(const double *__restrict__ sl, const 
 // as march_fast; the Gaussians are started afresh at every inner position (no recurrence across positions).
 // The route thresholds of these particles carry a half-pixel margin (setup_particle).
 template <int NL, bool COUNT>
-__device__ __noinline__ void march_sub(const double *__restrict__ sl, const double *__restrict__ tab, double *__restrict__ row0,
+__device__ __noinline__ void march_sub(const double *__restrict__ sl, const double2 *__restrict__ tab, double *__restrict__ row0,
                                        int64_t line_stride, int nbins, double bintov, double tautail, int lane, Tally &tally)
 {
     constexpr unsigned kUpBits = NL == 2 ? 0x5u : 0x1u, kDnBits = NL == 2 ? 0xau : 0x2u;
@@ -700,7 +662,7 @@ __device__ __noinline__ void march_sub(const double *__restrict__ sl, const doub
                         U0 = exp(-x1 * x1);
                         R = exp(-fma(2.0, x1, step) * step);
                     }
-                    node_sum_near<NL>(xb, step, sl, tab, U0, R, q, gauss, lmask, tot);
+                    node_sum_near<NL>(xb, step, sl, tab, U0, R, q, gauss, true, lmask, tot);
                 }
                 if (cls & 2u) {
                     double tfar[NL];
@@ -711,7 +673,7 @@ __device__ __noinline__ void march_sub(const double *__restrict__ sl, const doub
                 if ((cls & 4u) && lc == 2) {
                     #pragma unroll
                     for (int l = 0; l < NL; ++l)
-                        if ((lmask >> l) & 1u) tot[l] = LF(l, L_CD) * node_sum_generic(v, sl, l, tab);
+                        if ((lmask >> l) & 1u) tot[l] = node_sum_generic(v, sl, l, tab);
                 }
             }
             #pragma unroll
@@ -747,7 +709,7 @@ __device__ __noinline__ void march_sub(const double *__restrict__ sl, const doub
 // Slow routes: the exact Faddeeva restatement, and pixels wider than btherm/2 (sub-sampling rule of
 // singleabs.h:110-125).  Same lane layout, per-pixel evaluation through pixel_sum_slow.
 template <int NL, bool EXACT, bool COUNT>
-__device__ __noinline__ void march_slow(const double *__restrict__ sl, const double *__restrict__ tab, double *__restrict__ row0,
+__device__ __noinline__ void march_slow(const double *__restrict__ sl, const double2 *__restrict__ tab, double *__restrict__ row0,
                                         int64_t line_stride, int nbins, double bintov, double tautail, int lane, Tally &tally)
 {
     const MarchGeom g = march_geom(lane, nbins, *reinterpret_cast<const int2 *>(&SF(S_ZMAX)));
@@ -774,7 +736,7 @@ __device__ __noinline__ void march_slow(const double *__restrict__ sl, const dou
         for (int l = 0; l < NL; ++l) {
             const bool on = mine && ((live[l] >> g.dir) & 1u);
             cur[l] = on ? row0[l * line_stride + j] : 0.0;
-            t[l] = on ? LF(l, L_CD) * pixel_sum_slow<EXACT>(vlow, vhigh_px, sl, l, tab, ninner) : 0.0;
+            t[l] = on ? pixel_sum_slow<EXACT>(vlow, vhigh_px, sl, l, tab, ninner) : 0.0;
         }
         if (COUNT) ++tally.route[4];
         march_commit<NL, COUNT>(g, t, cur, live, mine, base, j, ninner, row0, line_stride, tautail, tally);
@@ -784,7 +746,7 @@ __device__ __noinline__ void march_slow(const double *__restrict__ sl, const dou
 // Everything but the plain fast march behind ONE call site, so the register allocation of the kernel's main
 // loop sees a single cold call (measured: separate call sites cost the main path 1.4 %).
 template <int NL, bool COUNT>
-__device__ __noinline__ void march_other(int mode, const double *__restrict__ sl, const double *__restrict__ tab,
+__device__ __noinline__ void march_other(int mode, const double *__restrict__ sl, const double2 *__restrict__ tab,
                                          double *__restrict__ row0, int64_t line_stride, int nbins, double bintov,
                                          double tautail, int lane, Tally &tally)
 {
@@ -879,45 +841,66 @@ __device__ __noinline__ void setup_particle(const InterpConsts &C, double *__res
     SF(S_K16) = exp(-2.0 * D16 * D16);
     SF(S_LU16) = exp(2.0 * D16 * step);
     SF(S_LD16) = exp(-2.0 * D16 * step);
-    // every factor stays within e^+-500 while a lane is within reach of the Gaussian core
-    SF(S_RECOK) = (step <= 1.0 && D16 <= 10.0) ? 1.0 : 0.0;
-    double ymin = 1e300;
+    double ymin = 1e300, ymax = 0;
     #pragma unroll
     for (int l = 0; l < NL; ++l) {
         const double aa = C.line[l].voigt_fac * inv_b;
         const double amp = C.line[l].sigma_a / kSqrtPi * (kLight / 1e5 * inv_b);
         if (mode && (force_exact || !fast_domain(aa))) mode = 2;
         ymin = fmin(ymin, aa);
-        LF(l, L_CD) = amp * (double) pdens / C.velfac;
+        ymax = fmax(ymax, aa);
+        const double cd = amp * (double) pdens / C.velfac;
+        LF(l, L_CD) = cd;
         LF(l, L_Y) = aa;
+        LF(l, L_Y2) = aa * aa;
+        LF(l, L_FAR) = cd * (0.56418958354775628694807945156 * aa);
         FastCoef fc;
         fast_coefs(aa, fc);
         #pragma unroll
-        for (int i = 0; i < 4; ++i) LF(l, L_PE0 + i) = fc.pe[i];
+        for (int i = 0; i < 4; ++i) LF(l, L_PC0 + i) = cd * fc.pe[i];
         #pragma unroll
-        for (int i = 0; i < 4; ++i) LF(l, L_A0 + i) = fc.a[i];
+        for (int i = 0; i < 4; ++i) LF(l, L_AC0 + i) = cd * fc.a[i];
         #pragma unroll
-        for (int i = 0; i < 3; ++i) LF(l, L_B0 + i) = fc.b[i];
+        for (int i = 0; i < 3; ++i) LF(l, L_BC0 + i) = cd * fc.b[i];
         // sum_i kw_i B((xb + d_i)^2), B(s) = b0 + b1 s + b2 s^2, as a quartic in xb
-        LF(l, L_BQ0) = fma(fc.b[2], M[4], fma(fc.b[1], M[2], fc.b[0] * M[0]));
-        LF(l, L_BQ0 + 1) = fma(4.0 * fc.b[2], M[3], 2.0 * fc.b[1] * M[1]);
-        LF(l, L_BQ0 + 2) = fma(6.0 * fc.b[2], M[2], fc.b[1] * M[0]);
-        LF(l, L_BQ0 + 3) = 4.0 * fc.b[2] * M[1];
-        LF(l, L_BQ0 + 4) = fc.b[2] * M[0];
+        const double bq0 = fma(fc.b[2], M[4], fma(fc.b[1], M[2], fc.b[0] * M[0]));
+        const double bq1 = fma(4.0 * fc.b[2], M[3], 2.0 * fc.b[1] * M[1]);
+        const double bq2 = fma(6.0 * fc.b[2], M[2], fc.b[1] * M[0]);
+        const double bq3 = 4.0 * fc.b[2] * M[1];
+        const double bq4 = fc.b[2] * M[0];
+        LF(l, L_BQ0) = cd * bq0;
+        LF(l, L_BQ0 + 1) = cd * bq1;
+        LF(l, L_BQ0 + 2) = cd * bq2;
+        LF(l, L_BQ0 + 3) = cd * bq3;
+        LF(l, L_BQ0 + 4) = cd * bq4;
+        LF(l, L_ERFCX) = 0;
         if (F32) {
             #pragma unroll
             for (int i = 0; i < 3; ++i) FLF(l, FL_A0 + i) = (float) fc.a[i];
             #pragma unroll
             for (int i = 0; i < 3; ++i) FLF(l, FL_PE0 + i) = (float) fc.pe[i];
-            #pragma unroll
-            for (int i = 0; i < 5; ++i) FLF(l, FL_BQ0 + i) = (float) LF(l, L_BQ0 + i);
+            FLF(l, FL_BQ0) = (float) bq0;
+            FLF(l, FL_BQ0 + 1) = (float) bq1;
+            FLF(l, FL_BQ0 + 2) = (float) bq2;
+            FLF(l, FL_BQ0 + 3) = (float) bq3;
+            FLF(l, FL_BQ0 + 4) = (float) bq4;
             FLF(l, FL_Y2) = (float) (aa * aa);
             FLF(l, FL_YISP) = (float) (aa * 0.56418958354775628694807945156);
         }
     }
     if (mode == 2) {
         #pragma unroll
-        for (int l = 0; l < NL; ++l) LF(l, L_PE0) = erfcx(C.line[l].voigt_fac * inv_b);
+        for (int l = 0; l < NL; ++l) LF(l, L_ERFCX) = erfcx(C.line[l].voigt_fac * inv_b);
+    }
+    {
+        // every factor of the march-step recurrence stays within e^+-500 while a lane is within reach of the Gaussian core
+        int2 rc;
+        rc.x = (step <= 1.0 && D16 <= 10.0) ? 1 : 0;
+        // degree class: the s^3 terms of A(s) and Pe(s) relative to the profile are at most (4/315) y^6 s^3 on the table
+        // route, whose nodes stay below |x| = 12 + the reach of one warp step (and below the table's end)
+        const double xs = fmin(FSB_GTAB_XMAX, kFarXMin + D16 + 6.0 * step + 0.5 * pix), y2m = ymax * ymax, s3 = (xs * xs) * y2m;
+        rc.y = ((4.0 / 315.0) * s3 * s3 * s3 > 5e-13) ? 1 : 0;
+        *reinterpret_cast<int2 *>(&SF(S_RECOK)) = rc;
     }
     const double xu2 = ymin > 0 ? 37.0 - log(ymin) : 1e300;
     SF(S_XU2) = xu2;
@@ -963,9 +946,10 @@ __device__ __noinline__ void setup_particle(const InterpConsts &C, double *__res
 
 // The FP32 tables and float slabs exist only in the FP32 instantiation (they would cost the FP64 kernel a
 // resident CTA per SM).
+constexpr int kTabDoubles = 4 * kG2Slots;  // both arrays of the G(x) table: 2 x kG2Slots double2
 template <int NL, bool F32> constexpr size_t tau_smem_bytes()
 {
-    return sizeof(double) * (size_t) (FSB_GTAB_SIZE + kTauWarps * SlabSize<NL>::kDoubles) +
+    return sizeof(double) * (size_t) (kTabDoubles + kTauWarps * SlabSize<NL>::kDoubles) +
            (F32 ? sizeof(float) * (size_t) (4 * FSB_GTAB_NINT + kTauWarps * FSlabSize<NL>::kFloats) : 0);
 }
 
@@ -980,15 +964,15 @@ k_tau(InterpConsts C, Items items, int n_items, int *__restrict__ next_item, con
       unsigned long long *__restrict__ counters, int *__restrict__ chunk_done, int *host_flags, int chunk_lines)
 {
     extern __shared__ __align__(16) double smem[];
-    double *tab = smem;  // [FSB_GTAB_SIZE], 16-byte aligned
+    double2 *tab = reinterpret_cast<double2 *>(smem);  // [2 * kG2Slots]: array A then array B, swizzled slots
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double *slab = smem + FSB_GTAB_SIZE + warp * SlabSize<NL>::kDoubles;
+    double *slab = smem + kTabDoubles + warp * SlabSize<NL>::kDoubles;
     // floats follow the doubles: the degree-3 table of the FP32 path (16-byte aligned), then the float slabs
-    static_assert((FSB_GTAB_SIZE + kTauWarps * SlabSize<NL>::kDoubles) % 2 == 0, "float4 table must stay 16-byte aligned");
-    float *tab32f = reinterpret_cast<float *>(smem + FSB_GTAB_SIZE + kTauWarps * SlabSize<NL>::kDoubles);
+    static_assert((kTabDoubles + kTauWarps * SlabSize<NL>::kDoubles) % 2 == 0, "float4 table must stay 16-byte aligned");
+    float *tab32f = reinterpret_cast<float *>(smem + kTabDoubles + kTauWarps * SlabSize<NL>::kDoubles);
     const float4 *tab32 = reinterpret_cast<const float4 *>(tab32f);
     float *fslab = F32 ? tab32f + 4 * FSB_GTAB_NINT + warp * FSlabSize<NL>::kFloats : nullptr;
-    for (int i = threadIdx.x; i < FSB_GTAB_SIZE; i += kTauThreads) tab[i] = d_gtable[i];
+    g2_stage(tab, threadIdx.x, kTauThreads);
     if (F32)
         for (int i = threadIdx.x; i < 4 * FSB_GTAB_NINT; i += kTauThreads) tab32f[i] = d_gtable32[i];
     __syncthreads();
@@ -1090,7 +1074,7 @@ __global__ void k_voigt_profile(const double *__restrict__ x, const double *__re
     if (voigt == FSB_VOIGT_FAST && fast_domain(yy)) {
         FastCoef fc;
         fast_coefs(yy, fc);
-        out[i] = voigt_fast(x[i], fc, d_gtable);
+        out[i] = voigt_fast<false>(x[i], fc, reinterpret_cast<const double2 *>(d_g2a_words), reinterpret_cast<const double2 *>(d_g2b_words));
     } else {
         out[i] = voigt_exact(x[i], yy, erfcx(yy));
     }
