@@ -44,6 +44,9 @@ namespace {
 constexpr int kTauWarps = FSB_TAU_WARPS;
 constexpr int kTauThreads = 32 * kTauWarps;
 constexpr int kBatch = FSB_TAU_BATCH;  // particles per slab refill (one lane each), <= 32
+// A single line in FP64 has room for 32 records per warp: the per-particle setup then runs on full warps, which
+// halves its share of the instruction stream (weak lines spend a fifth of their instructions there).
+template <int NL, bool F32> struct BatchOf { static constexpr int value = (NL == 1 && !F32 && kBatch == 16) ? 32 : kBatch; };
 constexpr int kMaxTauLines = 2;
 
 // ---- slab layout: one record of doubles per particle, kBatch records per warp ------------------------
@@ -89,11 +92,11 @@ enum LineField {
 };
 static_assert(L_FAR == L_BQ0 + 5 && L_BQ0 % 2 == 0 && L_Y2 % 2 == 0 && L_BC0 % 2 == 0 && S_COUNT % 2 == 0 && L_COUNT % 2 == 0 &&
               S_KW0 % 2 == 0 && S_Q % 2 == 0 && S_LU16 % 2 == 0, "16-byte field pairs");
-template <int NL> struct SlabSize {
+template <int NL, bool F32 = false> struct SlabSize {
     static constexpr int kFields = S_COUNT + NL * L_COUNT;
-    // record stride in doubles: an odd number of 16-byte units, so the 16 setup lanes spread over the banks
+    // record stride in doubles: an odd number of 16-byte units, so the setup lanes spread over the banks
     static constexpr int kStride = (kFields / 2) % 2 ? kFields : kFields + 2;
-    static constexpr int kDoubles = kStride * kBatch;
+    static constexpr int kDoubles = kStride * BatchOf<NL, F32>::value;
 };
 
 // FP32 fast path: float copies of the node constants, one record of floats per particle after the doubles
@@ -101,7 +104,7 @@ enum FShared { F_STEP = 0, F_KW0, F_COUNT = F_KW0 + 7 };
 enum FLineField { FL_A0 = 0, FL_PE0 = 3, FL_BQ0 = 6, FL_Y2 = 11, FL_YISP, FL_COUNT };
 template <int NL> struct FSlabSize {
     static constexpr int kStride = F_COUNT + NL * FL_COUNT;
-    static constexpr int kFloats = kStride * kBatch;
+    static constexpr int kFloats = kStride * kBatch;  // (FP32 instantiations keep kBatch records)
 };
 #define FS(f) fl[(f)]
 #define FLF(l, f) fl[F_COUNT + (l) * FL_COUNT + (f)]
@@ -139,10 +142,10 @@ __device__ __forceinline__ void node_sum_near_m(double xb, double step, const do
         const double x = fma((double) (i + 1), step, xb);
         int k;
         double t;
-        g2_index(fabs(x), k, t);
-        k = (int) min((unsigned) k, (unsigned) (FSB_G2_NINT - 1));
-        const double2 *e = tabA + g2_slot(k);
-        const double g = g2_poly(e[0], e[kG2Slots], t);
+        g_index(fabs(x), k, t);
+        k = (int) min((unsigned) k, (unsigned) (FSB_GTAB_NINT - 1));
+        const double2 *e = tabA + 3 * k;
+        const double g = g_poly(e[0], e[1], e[2], t);
         const double s = x * x;
         double w[DEG + 1];
         w[0] = SF(S_KW0 + i);
@@ -229,6 +232,63 @@ __device__ __forceinline__ void node_sum_far(double xb, double step, const doubl
         }
         const double y2 = LF(l, L_Y2);
         tot[l] = LF(l, L_FAR) * fma(-y2, fma(-y2, F5, F3), F1);
+    }
+}
+
+// MIXED: the warp step straddles the table / series overlap (12 <= |x| < 24), or a pixel's own nodes do (kernels
+// much wider than the thermal width: metal lines).  Node by node, with a warp-uniform choice per node: the lanes
+// of the downward run take the nodes in mirror order (node 8 - n where the upward run takes node n), so that at
+// every loop index all 32 lanes sit at nearly the same |x| (the two runs are mirror images about the particle up
+// to a pixel): either every lane is inside the table (|x| < 24) or every lane is on the series (|x| >= 12), unless
+// 16 pixels are wider than the overlap, in which case both are evaluated with the weights masked.
+// Table nodes feed MG, MU (Gaussian by direct exp where some lane is within its reach) and MW_k = sum kw s^k
+// (for B(s), which the all-table route takes from the quartic in xb); series nodes feed F1, F3, F5.
+// `active`: lanes whose result is used (the others compute garbage that must not steer the uniform choices).
+template <int NL>
+__device__ __noinline__ void node_sum_mixed(double xb, double step, const double *__restrict__ sl, const double2 *__restrict__ tab,
+                                            bool down, bool active, unsigned lmask, double (&tot)[NL])
+{
+    double MG[4] = {0, 0, 0, 0}, MU[4] = {0, 0, 0, 0}, MW[3] = {0, 0, 0}, F1 = 0, F3 = 0, F5 = 0;
+    const double xu2 = SF(S_XU2);
+    #pragma unroll 1
+    for (int n = 0; n < 7; ++n) {
+        const int ni = down ? 6 - n : n;
+        const double x = fma((double) (ni + 1), step, xb), ax = fabs(x), s = x * x, kw = SF(S_KW0 + ni);
+        const bool lane_far = ax >= kFarXMin, lane_tab = ax < FSB_GTAB_XMAX - 0.005;
+        const bool all_far = __all_sync(kFull, lane_far || !active), all_tab = __all_sync(kFull, lane_tab || !active);
+        if (!all_far) {  // table (all lanes, or masked to the lanes below the series' start when not every lane is inside)
+            const double wt = (all_tab || !lane_far) ? kw : 0.0;
+            const double g = g_table(fmin(ax, FSB_GTAB_XMAX - 0.005), tab);
+            const double w1 = wt * s, w2 = w1 * s, w3 = w2 * s;
+            MG[0] = fma(g, wt, MG[0]), MG[1] = fma(g, w1, MG[1]), MG[2] = fma(g, w2, MG[2]), MG[3] = fma(g, w3, MG[3]);
+            MW[0] += wt, MW[1] += w1, MW[2] += w2;
+            if (__any_sync(kFull, active && s < xu2)) {
+                const double u = s < xu2 ? exp(-s) : 0.0;
+                MU[0] = fma(u, wt, MU[0]), MU[1] = fma(u, w1, MU[1]), MU[2] = fma(u, w2, MU[2]), MU[3] = fma(u, w3, MU[3]);
+            }
+        }
+        if (all_far || !all_tab) {  // series (all lanes, or masked to the lanes the table did not take)
+            const double wf = (all_far || lane_far) ? kw : 0.0;
+            const double u = fast_rcp(fmax(s, kFarXMin * kFarXMin));
+            double p1, p3, p5;
+            far_polys(u, p1, p3, p5);
+            const double w1 = wf * u, w2 = w1 * u;
+            F1 = fma(w1, p1, F1), F3 = fma(w2, p3, F3), F5 = fma(w2 * u, p5, F5);
+        }
+    }
+    #pragma unroll
+    for (int l = 0; l < NL; ++l) {
+        if (NL > 1 && !((lmask >> l) & 1u)) {
+            tot[l] = 0;
+            continue;
+        }
+        const double2 a01 = LF2(l, L_AC0), a23 = LF2(l, L_AC0 + 2), p01 = LF2(l, L_PC0), p23 = LF2(l, L_PC0 + 2);
+        const double y2 = LF(l, L_Y2);
+        double acc = LF(l, L_FAR) * fma(-y2, fma(-y2, F5, F3), F1);
+        acc = fma(LF(l, L_BC0), MW[0], acc), acc = fma(LF(l, L_BC0 + 1), MW[1], acc), acc = fma(LF(l, L_BC0 + 2), MW[2], acc);
+        acc = fma(a01.x, MG[0], acc), acc = fma(a01.y, MG[1], acc), acc = fma(a23.x, MG[2], acc), acc = fma(a23.y, MG[3], acc);
+        acc = fma(p01.x, MU[0], acc), acc = fma(p01.y, MU[1], acc), acc = fma(p23.x, MU[2], acc), acc = fma(p23.y, MU[3], acc);
+        tot[l] = acc;
     }
 }
 
@@ -329,7 +389,7 @@ __device__ __noinline__ double node_sum_generic(double vouter, const double *__r
             hval = cd * voigt_far(s, y);
         } else {
             const double U = s < xu2 ? exp(-s) : 0.0;
-            const double G = g2_table<true>(ax, tabA, tabA + kG2Slots);
+            const double G = g_table(ax, tabA);
             const double Pe = fma(fma(fma(p23.y, s, p23.x), s, p01.y), s, p01.x);
             const double A = fma(fma(fma(a23.y, s, a23.x), s, a01.y), s, a01.x);
             const double B = fma(fma(b2, s, b1), s, b0);
@@ -525,45 +585,51 @@ __device__ __forceinline__ void march_fast(const double *__restrict__ sl, const 
             }
             if (COUNT) ++tally.route[gauss ? 0 : 1];
         } else {
-            // transition step: lanes differ.  Lane class: 0 table, 1 series, 2 neither (own nodes on both
-            // sides of the overlap: node by node), 3 idle.
-            const int myN = dir ? thrN.y : thrN.x, myF = dir ? thrF.y : thrF.x;
-            const int lc = !mybits ? 3 : (o >= myF ? 1 : (o < myN ? 0 : 2));
-            const unsigned cls = __reduce_or_sync(kFull, 1u << lc);
             rec_valid = false;
-            if (cls & 1u) {
-                if (F32) {
-                    float tf[NL];
-                    node_sum_near32<NL>((float) xb, FS(F_STEP), fl, tab32, gauss, lmask, tf);
-                    #pragma unroll
-                    for (int l = 0; l < NL; ++l) tot[l] = LF(l, L_CD) * (double) tf[l];
-                } else {
-                    if (gauss) {
-                        const double x1 = xb + step;
-                        U0 = exp(-x1 * x1);
-                        R = exp(-fma(2.0, x1, step) * step);
+            if (!F32) {
+                // transition step, node by node with a warp-uniform route per node (node_sum_mixed)
+                node_sum_mixed<NL>(xb, step, sl, tab, dir != 0, mybits != 0, lmask, tot);
+            } else {
+                // transition step: lanes differ.  Lane class: 0 table, 1 series, 2 neither (own nodes on both
+                // sides of the overlap: node by node), 3 idle.
+                const int myN = dir ? thrN.y : thrN.x, myF = dir ? thrF.y : thrF.x;
+                const int lc = !mybits ? 3 : (o >= myF ? 1 : (o < myN ? 0 : 2));
+                const unsigned cls = __reduce_or_sync(kFull, 1u << lc);
+                rec_valid = false;
+                if (cls & 1u) {
+                    if (F32) {
+                        float tf[NL];
+                        node_sum_near32<NL>((float) xb, FS(F_STEP), fl, tab32, gauss, lmask, tf);
+                        #pragma unroll
+                        for (int l = 0; l < NL; ++l) tot[l] = LF(l, L_CD) * (double) tf[l];
+                    } else {
+                        if (gauss) {
+                            const double x1 = xb + step;
+                            U0 = exp(-x1 * x1);
+                            R = exp(-fma(2.0, x1, step) * step);
+                        }
+                        node_sum_near<NL>(xb, step, sl, tab, U0, R, SF(S_Q), gauss, cubic, lmask, tot);
                     }
-                    node_sum_near<NL>(xb, step, sl, tab, U0, R, SF(S_Q), gauss, cubic, lmask, tot);
                 }
-            }
-            if (cls & 2u) {
-                double tfar[NL];
-                if (F32) {
-                    float tf[NL];
-                    node_sum_far32<NL>((float) xb, FS(F_STEP), fl, lmask, tf);
+                if (cls & 2u) {
+                    double tfar[NL];
+                    if (F32) {
+                        float tf[NL];
+                        node_sum_far32<NL>((float) xb, FS(F_STEP), fl, lmask, tf);
+                        #pragma unroll
+                        for (int l = 0; l < NL; ++l) tfar[l] = LF(l, L_CD) * (double) tf[l];
+                    } else {
+                        node_sum_far<NL>(xb, step, sl, lmask, tfar);
+                    }
                     #pragma unroll
-                    for (int l = 0; l < NL; ++l) tfar[l] = LF(l, L_CD) * (double) tf[l];
-                } else {
-                    node_sum_far<NL>(xb, step, sl, lmask, tfar);
+                    for (int l = 0; l < NL; ++l) tot[l] = lc == 1 ? tfar[l] : tot[l];
                 }
-                #pragma unroll
-                for (int l = 0; l < NL; ++l) tot[l] = lc == 1 ? tfar[l] : tot[l];
-            }
-            if (cls & 4u) {
-                if (lc == 2) {
-                    #pragma unroll
-                    for (int l = 0; l < NL; ++l)
-                        if ((lmask >> l) & 1u) tot[l] = node_sum_generic((SF(S_XOFF) - xb) / SF(S_INVB), sl, l, tab);
+                if (cls & 4u) {
+                    if (lc == 2) {
+                        #pragma unroll
+                        for (int l = 0; l < NL; ++l)
+                            if ((lmask >> l) & 1u) tot[l] = node_sum_generic((SF(S_XOFF) - xb) / SF(S_INVB), sl, l, tab);
+                    }
                 }
             }
             if (COUNT) ++tally.route[3];
@@ -635,13 +701,6 @@ __device__ __noinline__ void march_sub(const double *__restrict__ sl, const doub
         const double dv = (vhigh_px - vlow) / (npts - 1);
         const bool gauss = base < gauss_end;
         const bool all_far = base >= far_beg, all_near = min(base + 16, half) <= near_lim;
-        int lc = 0;
-        unsigned cls = 0;
-        if (!all_far && !all_near) {  // transition step: lane class 0 table, 1 series, 2 node by node, 3 idle
-            const int myN = dir ? thrN.y : thrN.x, myF = dir ? thrF.y : thrF.x;
-            lc = !mybits ? 3 : (o >= myF ? 1 : (o < myN ? 0 : 2));
-            cls = __reduce_or_sync(kFull, 1u << lc);
-        }
         double acc[NL];
         #pragma unroll
         for (int l = 0; l < NL; ++l) acc[l] = 0;
@@ -654,27 +713,16 @@ __device__ __noinline__ void march_sub(const double *__restrict__ sl, const doub
             for (int l = 0; l < NL; ++l) tot[l] = 0;
             if (all_far) {
                 node_sum_far<NL>(xb, step, sl, lmask, tot);
+            } else if (all_near) {
+                double U0 = 0, R = 0;
+                if (gauss) {
+                    const double x1 = xb + step;
+                    U0 = exp(-x1 * x1);
+                    R = exp(-fma(2.0, x1, step) * step);
+                }
+                node_sum_near<NL>(xb, step, sl, tab, U0, R, q, gauss, true, lmask, tot);
             } else {
-                if (all_near || (cls & 1u)) {
-                    double U0 = 0, R = 0;
-                    if (gauss) {
-                        const double x1 = xb + step;
-                        U0 = exp(-x1 * x1);
-                        R = exp(-fma(2.0, x1, step) * step);
-                    }
-                    node_sum_near<NL>(xb, step, sl, tab, U0, R, q, gauss, true, lmask, tot);
-                }
-                if (cls & 2u) {
-                    double tfar[NL];
-                    node_sum_far<NL>(xb, step, sl, lmask, tfar);
-                    #pragma unroll
-                    for (int l = 0; l < NL; ++l) tot[l] = lc == 1 ? tfar[l] : tot[l];
-                }
-                if ((cls & 4u) && lc == 2) {
-                    #pragma unroll
-                    for (int l = 0; l < NL; ++l)
-                        if ((lmask >> l) & 1u) tot[l] = node_sum_generic(v, sl, l, tab);
-                }
+                node_sum_mixed<NL>(xb, step, sl, tab, dir != 0, mybits != 0, lmask, tot);
             }
             #pragma unroll
             for (int l = 0; l < NL; ++l) acc[l] = fma(wgt, tot[l], acc[l]);
@@ -804,27 +852,25 @@ __device__ __noinline__ void setup_particle(const InterpConsts &C, double *__res
     SF(S_STEP) = step;
     SF(S_XOFF) = -vhigh * inv_b;
     SF(S_Q) = exp(-2.0 * step * step);
-    double kw[7];
-    #pragma unroll
+    // kernel weights and their moments about xb, in units of btherm: M_n = sum kw_i (i step)^n.  A rolled loop on
+    // purpose: this function runs once per batch of particles and its length is paid in instruction fetches.
+    double M[5] = {0, 0, 0, 0, 0};
+    const double inv_vs = 1.0 / vsmooth;
+    #pragma unroll 1
     for (int i = 1; i < kNGrid; ++i) {
         const double vv = i * deltav - vhigh;
-        kw[i - 1] = sph_kernel<KERNEL>(sqrt(vdr2 + vv * vv) / vsmooth) * deltav;
-        SF(S_KW0 + i - 1) = kw[i - 1];
-        if (F32) FS(F_KW0 + i - 1) = (float) kw[i - 1];
-    }
-    if (F32) FS(F_STEP) = (float) step;
-    // moments of the node weights about xb, in units of btherm: M_n = sum kw_i (i step)^n
-    double M[5] = {0, 0, 0, 0, 0};
-    #pragma unroll
-    for (int i = 0; i < 7; ++i) {
-        const double d = (i + 1) * step;
-        double p = kw[i];
+        const double kwi = sph_kernel<KERNEL>(sqrt(vdr2 + vv * vv) * inv_vs) * deltav;
+        SF(S_KW0 + i - 1) = kwi;
+        if (F32) FS(F_KW0 + i - 1) = (float) kwi;
+        const double d = i * step;
+        double p = kwi;
         #pragma unroll
         for (int n = 0; n < 5; ++n) {
             M[n] += p;
             p *= d;
         }
     }
+    if (F32) FS(F_STEP) = (float) step;
     const double zmaxd = floor(velp / C.bintov);
     {
         int2 zj;
@@ -838,9 +884,12 @@ __device__ __noinline__ void setup_particle(const InterpConsts &C, double *__res
     SF(S_PIX) = pix;
     // march-step recurrence factors: D = 16 pixels in units of btherm
     const double D16 = 16.0 * pix;
-    SF(S_K16) = exp(-2.0 * D16 * D16);
-    SF(S_LU16) = exp(2.0 * D16 * step);
-    SF(S_LD16) = exp(-2.0 * D16 * step);
+    const bool rec_usable = step <= 1.0 && D16 <= 10.0;
+    if (rec_usable) {
+        SF(S_K16) = exp(-2.0 * D16 * D16);
+        SF(S_LU16) = exp(2.0 * D16 * step);
+        SF(S_LD16) = exp(-2.0 * D16 * step);
+    }
     double ymin = 1e300, ymax = 0;
     #pragma unroll
     for (int l = 0; l < NL; ++l) {
@@ -895,7 +944,7 @@ __device__ __noinline__ void setup_particle(const InterpConsts &C, double *__res
     {
         // every factor of the march-step recurrence stays within e^+-500 while a lane is within reach of the Gaussian core
         int2 rc;
-        rc.x = (step <= 1.0 && D16 <= 10.0) ? 1 : 0;
+        rc.x = rec_usable ? 1 : 0;
         // degree class: the s^3 terms of A(s) and Pe(s) relative to the profile are at most (4/315) y^6 s^3 on the table
         // route, whose nodes stay below |x| = 12 + the reach of one warp step (and below the table's end)
         const double xs = fmin(FSB_GTAB_XMAX, kFarXMin + D16 + 6.0 * step + 0.5 * pix), y2m = ymax * ymax, s3 = (xs * xs) * y2m;
@@ -946,10 +995,10 @@ __device__ __noinline__ void setup_particle(const InterpConsts &C, double *__res
 
 // The FP32 tables and float slabs exist only in the FP32 instantiation (they would cost the FP64 kernel a
 // resident CTA per SM).
-constexpr int kTabDoubles = 4 * kG2Slots;  // both arrays of the G(x) table: 2 x kG2Slots double2
+constexpr int kTabDoubles = FSB_GTAB_SIZE;  // the staged G(x) table
 template <int NL, bool F32> constexpr size_t tau_smem_bytes()
 {
-    return sizeof(double) * (size_t) (kTabDoubles + kTauWarps * SlabSize<NL>::kDoubles) +
+    return sizeof(double) * (size_t) (kTabDoubles + kTauWarps * SlabSize<NL, F32>::kDoubles) +
            (F32 ? sizeof(float) * (size_t) (4 * FSB_GTAB_NINT + kTauWarps * FSlabSize<NL>::kFloats) : 0);
 }
 
@@ -964,15 +1013,15 @@ k_tau(InterpConsts C, Items items, int n_items, int *__restrict__ next_item, con
       unsigned long long *__restrict__ counters, int *__restrict__ chunk_done, int *host_flags, int chunk_lines)
 {
     extern __shared__ __align__(16) double smem[];
-    double2 *tab = reinterpret_cast<double2 *>(smem);  // [2 * kG2Slots]: array A then array B, swizzled slots
+    double2 *tab = reinterpret_cast<double2 *>(smem);  // [kGtabPieces]: three 16-byte pieces per interval
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double *slab = smem + kTabDoubles + warp * SlabSize<NL>::kDoubles;
+    double *slab = smem + kTabDoubles + warp * SlabSize<NL, F32>::kDoubles;
     // floats follow the doubles: the degree-3 table of the FP32 path (16-byte aligned), then the float slabs
-    static_assert((kTabDoubles + kTauWarps * SlabSize<NL>::kDoubles) % 2 == 0, "float4 table must stay 16-byte aligned");
-    float *tab32f = reinterpret_cast<float *>(smem + kTabDoubles + kTauWarps * SlabSize<NL>::kDoubles);
+    static_assert((kTabDoubles + kTauWarps * SlabSize<NL, F32>::kDoubles) % 2 == 0, "float4 table must stay 16-byte aligned");
+    float *tab32f = reinterpret_cast<float *>(smem + kTabDoubles + kTauWarps * SlabSize<NL, F32>::kDoubles);
     const float4 *tab32 = reinterpret_cast<const float4 *>(tab32f);
     float *fslab = F32 ? tab32f + 4 * FSB_GTAB_NINT + warp * FSlabSize<NL>::kFloats : nullptr;
-    g2_stage(tab, threadIdx.x, kTauThreads);
+    for (int i = threadIdx.x; i < kGtabPieces; i += kTauThreads) tab[i] = d_gtable[i];
     if (F32)
         for (int i = threadIdx.x; i < 4 * FSB_GTAB_NINT; i += kTauThreads) tab32f[i] = d_gtable32[i];
     __syncthreads();
@@ -1012,8 +1061,9 @@ k_tau(InterpConsts C, Items items, int n_items, int *__restrict__ next_item, con
         const int ax = axis[line] - 1;
         n_pairs += (unsigned long long) (kend - kbeg);
 
-        for (int64_t k0 = kbeg; k0 < kend; k0 += kBatch) {
-            const int nb = (int) min((int64_t) kBatch, kend - k0);
+        constexpr int kB = BatchOf<NL, F32>::value;
+        for (int64_t k0 = kbeg; k0 < kend; k0 += kB) {
+            const int nb = (int) min((int64_t) kB, kend - k0);
             __syncwarp();
             if (lane < nb) setup_particle<KERNEL, NL, F32>(C, slab + lane * SlabSize<NL>::kStride, fslab + lane * FSlabSize<NL>::kStride, k0 + lane, ax, zorder, particle, dr2s, pos, vel, dens, temp, hsml, cells);
             __syncwarp();
@@ -1074,7 +1124,7 @@ __global__ void k_voigt_profile(const double *__restrict__ x, const double *__re
     if (voigt == FSB_VOIGT_FAST && fast_domain(yy)) {
         FastCoef fc;
         fast_coefs(yy, fc);
-        out[i] = voigt_fast<false>(x[i], fc, reinterpret_cast<const double2 *>(d_g2a_words), reinterpret_cast<const double2 *>(d_g2b_words));
+        out[i] = voigt_fast(x[i], fc, d_gtable);
     } else {
         out[i] = voigt_exact(x[i], yy, erfcx(yy));
     }

@@ -210,56 +210,49 @@ __device__ __forceinline__ void fast_coefs(double y, FastCoef &c)
     c.y = y;
 }
 
-// ---- the G(x) table (second generation: fsb_voigt_tables.h) ---------------------------------------------
-// 1537 intervals of width 1/64 centred on k/64, degree 4 in t = |x| - k/64; per interval two 16-byte pieces,
-// A = {c0, c1} and B = {c2, (float c3, float c4)}, kept in two arrays.  Kernels stage both arrays in shared
-// memory with the interval index SWIZZLED (slot = k ^ ((k >> 3) & 7)): the lanes of a quarter-warp hold
-// adjacent pixels, i.e. equally spaced intervals, and with a plain layout a spacing that is a multiple of 2, 4 or
-// 8 intervals would put their 16-byte pieces 2-, 4- or 8-fold into the same banks.
-__device__ __align__(16) const unsigned long long d_g2a_words[2 * FSB_G2_NINT] = FSB_G2_WORDS_A;
-__device__ __align__(16) const unsigned long long d_g2b_words[2 * FSB_G2_NINT] = FSB_G2_WORDS_B;
-constexpr int kG2Slots = (FSB_G2_NINT + 7) & ~7;  // slots per array (the swizzle permutes inside groups of 64)
+// ---- the G(x) table (fsb_voigt_tables.h) ------------------------------------------------------------------
+// 193 intervals of width 1/8 centred on k/8, degree 7 in t = |x| - k/8, 48 bytes per interval: three 16-byte
+// pieces {c0, c1}, {c2, (c3, c4)}, {(c5, c6), (c7, -)} with c3..c7 as floats.  The intervals are deliberately
+// COARSE: the lanes of a quarter-warp hold adjacent pixels, a fraction of an interval apart, so their 16-byte
+// loads hit the same or consecutive intervals, which the 48-byte stride (an odd multiple of 16 bytes) spreads
+// over distinct banks.  A finer table of lower degree (32 bytes per interval at h = 1/64, tried) makes the lanes
+// hit intervals several entries apart at an irregular stride: 2.5 wavefronts per quarter-warp instead of 1, whatever
+// the slot permutation (profiles/README.md).
+__device__ __align__(16) const unsigned long long d_gtable_words[FSB_GTAB_SIZE] = FSB_GTAB_WORDS;
+#define d_gtable (reinterpret_cast<const double2 *>(d_gtable_words))
+constexpr int kGtabPieces = FSB_GTAB_SIZE / 2;  // double2 pieces of the staged table
 
-__device__ __forceinline__ int g2_slot(int k) { return k ^ ((k >> 3) & 7); }
-
-// k = rint(64 |x|), t = |x| - k/64.
-__device__ __forceinline__ void g2_index(double ax, int &k, double &t)
+// Table index and offset of |x| < 24: k = rint(8|x|), t = |x| - k/8.
+__device__ __forceinline__ void g_index(double ax, int &k, double &t)
 {
-    const double magic = 6755399441055744.0;  // 1.5 * 2^52: low mantissa bits = rint(64|x|)
-    const double m = fma(ax, FSB_G2_INV_DELTA, magic);
+    const double magic = 6755399441055744.0;  // 1.5 * 2^52: low mantissa bits = rint(8|x|)
+    const double m = fma(ax, FSB_GTAB_INV_DELTA, magic);
     k = __double2loint(m);
-    t = fma(m - magic, -1.0 / FSB_G2_INV_DELTA, ax);
+    t = fma(m - magic, -1.0 / FSB_GTAB_INV_DELTA, ax);
 }
 
-// c0 + t (c1 + t (c2 + t (c3 + t c4))): the (c3 + t c4) pair in single precision (|t| <= 1/128 scales its rounding
-// error by 2^-21: < 3e-14 |c3|), the rest in double.
-__device__ __forceinline__ double g2_poly(double2 a, double2 b, double t)
+// Degree-7 polynomial of one interval at offset t from its three 16-byte pieces: the t^3..t^7 part runs in single
+// precision (|t| <= 1/16 scales its rounding error by 2^-12 or less), the rest in double.
+__device__ __forceinline__ double g_poly(double2 v0, double2 v1, double2 v2, double t)
 {
-    const float r = fmaf(__int_as_float(__double2hiint(b.y)), (float) t, __int_as_float(__double2loint(b.y)));
-    return fma(fma(fma((double) r, t, b.x), t, a.y), t, a.x);
+    const float tf = (float) t;
+    float hi = __int_as_float(__double2loint(v2.y));                 // c7
+    hi = fmaf(hi, tf, __int_as_float(__double2hiint(v2.x)));         // c6
+    hi = fmaf(hi, tf, __int_as_float(__double2loint(v2.x)));         // c5
+    hi = fmaf(hi, tf, __int_as_float(__double2hiint(v1.y)));         // c4
+    hi = fmaf(hi, tf, __int_as_float(__double2loint(v1.y)));         // c3
+    return fma(fma(fma((double) hi, t, v1.x), t, v0.y), t, v0.x);
 }
 
-// G(|x|) for |x| < FSB_GTAB_XMAX.  SWZ: tabA/tabB are the swizzled shared-memory copies; otherwise the global masters.
-template <bool SWZ>
-__device__ __forceinline__ double g2_table(double ax, const double2 *__restrict__ tabA, const double2 *__restrict__ tabB)
+// G(|x|) for |x| < FSB_GTAB_XMAX from the table (tab may be the shared-memory copy or the global master).
+__device__ __forceinline__ double g_table(double ax, const double2 *__restrict__ tab)
 {
     int k;
     double t;
-    g2_index(ax, k, t);
-    k = (int) min((unsigned) k, (unsigned) (FSB_G2_NINT - 1));
-    const int slot = SWZ ? g2_slot(k) : k;
-    return g2_poly(tabA[slot], tabB[slot], t);
-}
-
-// Stage both arrays into shared memory (swizzled).  smem holds 2 * kG2Slots double2.
-__device__ __forceinline__ void g2_stage(double2 *smem_tab, int tid, int nthreads)
-{
-    const double2 *ga = reinterpret_cast<const double2 *>(d_g2a_words), *gb = reinterpret_cast<const double2 *>(d_g2b_words);
-    for (int k = tid; k < FSB_G2_NINT; k += nthreads) {
-        const int slot = g2_slot(k);
-        smem_tab[slot] = ga[k];
-        smem_tab[kG2Slots + slot] = gb[k];
-    }
+    g_index(ax, k, t);
+    k = (int) min((unsigned) k, (unsigned) (FSB_GTAB_NINT - 1));
+    const double2 *c = tab + 3 * k;
+    return g_poly(c[0], c[1], c[2], t);
 }
 
 // Damping wing for |x| >= 12, u = 1/x^2:  H = (y/sqrt(pi)) u [P1(u) - (y^2 u) P3(u) + (y^2 u)^2 P5(u)],
@@ -295,12 +288,11 @@ __device__ __forceinline__ double voigt_far(double s, double y)
 }
 
 // One profile value with a known U = exp(-x^2) (or 0 where it is negligible).
-template <bool SWZ>
 __device__ __forceinline__ double voigt_fast_with_u(double ax, double s, double U, const FastCoef &c,
-                                                    const double2 *__restrict__ tabA, const double2 *__restrict__ tabB)
+                                                    const double2 *__restrict__ tab)
 {
     if (ax >= kFarXMin) return voigt_far(s, c.y);
-    const double G = g2_table<SWZ>(ax, tabA, tabB);
+    const double G = g_table(ax, tab);
     const double Pe = fma(fma(fma(c.pe[3], s, c.pe[2]), s, c.pe[1]), s, c.pe[0]);
     const double A = fma(fma(fma(c.a[3], s, c.a[2]), s, c.a[1]), s, c.a[0]);
     const double B = fma(fma(c.b[2], s, c.b[1]), s, c.b[0]);
@@ -308,13 +300,11 @@ __device__ __forceinline__ double voigt_fast_with_u(double ax, double s, double 
 }
 
 // Stand-alone evaluation (tests, and any caller without a shared U recurrence).
-template <bool SWZ>
-__device__ __forceinline__ double voigt_fast(double x, const FastCoef &c, const double2 *__restrict__ tabA,
-                                             const double2 *__restrict__ tabB)
+__device__ __forceinline__ double voigt_fast(double x, const FastCoef &c, const double2 *__restrict__ tab)
 {
     const double ax = fabs(x), s = x * x;
     const double U = s < c.xU2 ? exp(-s) : 0.0;
-    return voigt_fast_with_u<SWZ>(ax, s, U, c, tabA, tabB);
+    return voigt_fast_with_u(ax, s, U, c, tab);
 }
 
 // y == 0 (gamma = 0, spectra.py:669-672) takes the exact path, whose y == 0 branch is exp(-x^2).

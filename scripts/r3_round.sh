@@ -28,8 +28,11 @@ launches3) echo "== ncu launch list (c3)"
   timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/launches_c3.csv \
     $B --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --no-extras > $OUT/launches_c3.log 2>&1; tail -3 $OUT/launches_c3.log | cut -c1-300;;
 ncu) echo "== ncu full k_tau (c2, the timed launch)"
-  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:k_tau -s 4 -c 1 -o $OUT/prof_tau_c2 \
+  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:k_tau -s 3 -c 1 -o $OUT/prof_tau_c2 \
     $B --workload c2_grid256_lya_lyb --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --no-extras > $OUT/prof_tau_c2.log 2>&1; tail -2 $OUT/prof_tau_c2.log | cut -c1-300;;
+ncumetal) echo "== ncu full k_tau NL=1 (metal lines, mini3 workload)"
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_tau -s 8 -c 2 -o $OUT/prof_tau_metal \
+    $B --workload mini3_rand6k_3axes_4lines --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --no-extras > $OUT/prof_tau_metal.log 2>&1; tail -2 $OUT/prof_tau_metal.log | cut -c1-300;;
 ncuidx) echo "== ncu full index + colden kernels (c2)"
   timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'k_pairs|k_sort|k_colden|k_bin|k_fill|k_cand' -s 0 -c 8 -o $OUT/prof_idx_c2 \
     $B --workload c2_grid256_lya_lyb --steps 1 --warmup 0 --no-cpu-baseline --no-e2e > $OUT/prof_idx_c2.log 2>&1; tail -2 $OUT/prof_idx_c2.log | cut -c1-300;;
