@@ -40,10 +40,14 @@ int plan_items(const fsb_index *idx, int seg_pairs_req, int nbins, int nrows_per
     if (seg <= 0 || seg >= idx->max_list) {
         plan.items.item_start = nullptr;
         plan.items.seg_pairs = 0;
+        plan.items.ticket_pairs = 0;
+        plan.items.line_done = nullptr;
         plan.n_items = idx->nlos;
         plan.segmented = false;
         return FSB_OK;
     }
+    plan.items.ticket_pairs = 0;
+    plan.items.line_done = nullptr;
     plan.segmented = true;
     plan.items.seg_pairs = seg;
     plan.n_items = (int64_t) idx->nlos + idx->npairs / seg;

@@ -76,8 +76,15 @@ __device__ __forceinline__ double kern_frac(double zlow, double zhigh, double sm
 
 // ---- work items ---------------------------------------------------------------------------------
 struct Items {
-    const int32_t *item_start;  // [nlos+1] first item of each line (NULL: one item per line)
+    const int32_t *item_start;  // [nlos+1] first item of each line (NULL: one output row per line, no scratch rows)
     int32_t seg_pairs;
+    // Ticketed segments (tau only, item_start == NULL): a line's list is cut into runs of ticket_pairs candidates that
+    // are handed out as separate items, run-major (run 0 of every line, then run 1, ...); run s of a line waits until
+    // line_done[line] == s, adds into the line's own row, then publishes s + 1.  The row therefore receives its
+    // particles in exactly the order of an unsegmented pass (results are bit-identical whatever the number of
+    // sightlines, warps or GPUs), while the scheduling granularity is a run instead of a whole sightline.
+    int32_t ticket_pairs;       // 0: one item per line
+    int32_t *line_done;         // [nlos] zero-initialised
 };
 
 // item -> (line, [kbeg, kend) in the pair arrays).  Returns false for items past the end.

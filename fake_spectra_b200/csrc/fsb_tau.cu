@@ -532,7 +532,7 @@ __device__ __forceinline__ void march_fast(const double *__restrict__ sl, const 
         double *const pj = row0 + j;
         double cur[NL];
         #pragma unroll
-        for (int l = 0; l < NL; ++l) cur[l] = (mybits >> (2 * l)) & 1u ? pj[l * line_stride] : 0.0;
+        for (int l = 0; l < NL; ++l) cur[l] = (mybits >> (2 * l)) & 1u ? __ldcg(pj + l * line_stride) : 0.0;
         unsigned lmask = 0;  // lines with a live run
         #pragma unroll
         for (int l = 0; l < NL; ++l) lmask |= (live >> (2 * l)) & 3u ? (1u << l) : 0u;
@@ -691,7 +691,7 @@ __device__ __noinline__ void march_sub(const double *__restrict__ sl, const doub
         double *const pj = row0 + j;
         double cur[NL];
         #pragma unroll
-        for (int l = 0; l < NL; ++l) cur[l] = (mybits >> (2 * l)) & 1u ? pj[l * line_stride] : 0.0;
+        for (int l = 0; l < NL; ++l) cur[l] = (mybits >> (2 * l)) & 1u ? __ldcg(pj + l * line_stride) : 0.0;
         unsigned lmask = 0;
         #pragma unroll
         for (int l = 0; l < NL; ++l) lmask |= (live >> (2 * l)) & 3u ? (1u << l) : 0u;
@@ -783,7 +783,7 @@ __device__ __noinline__ void march_slow(const double *__restrict__ sl, const dou
         #pragma unroll
         for (int l = 0; l < NL; ++l) {
             const bool on = mine && ((live[l] >> g.dir) & 1u);
-            cur[l] = on ? row0[l * line_stride + j] : 0.0;
+            cur[l] = on ? __ldcg(row0 + l * line_stride + j) : 0.0;
             t[l] = on ? pixel_sum_slow<EXACT>(vlow, vhigh_px, sl, l, tab, ninner) : 0.0;
         }
         if (COUNT) ++tally.route[4];
@@ -1052,7 +1052,29 @@ k_tau(InterpConsts C, Items items, int n_items, int *__restrict__ next_item, con
                 }
             }
         };
-        if (!locate_item(items, offsets, C.nlos, item, line, kbeg, kend)) {
+        int run = 0;
+        bool last_run = true;
+        if (items.item_start == nullptr && items.ticket_pairs > 0) {
+            // ticketed run of a line's list: item = run * nlos + line
+            run = item / C.nlos;
+            line = item - run * C.nlos;
+            const int64_t b0 = offsets[line], b1 = offsets[line + 1];
+            kbeg = b0 + (int64_t) run * items.ticket_pairs;
+            kend = min(kbeg + (int64_t) items.ticket_pairs, b1);
+            last_run = kend >= b1;
+            if (kbeg >= b1) {  // the line has fewer runs (or no candidates at all)
+                if (STREAM && run == 0) row_done(line);
+                continue;
+            }
+            if (run > 0) {  // the previous run of this line must have finished adding to the row
+                if (lane == 0) {
+                    const volatile int *flag = items.line_done + line;
+                    while (*flag != run) __nanosleep(64);
+                }
+                __syncwarp();
+                __threadfence();
+            }
+        } else if (!locate_item(items, offsets, C.nlos, item, line, kbeg, kend)) {
             if (STREAM && item < C.nlos) row_done(item);
             continue;
         }
@@ -1090,7 +1112,12 @@ k_tau(InterpConsts C, Items items, int n_items, int *__restrict__ next_item, con
                 __syncwarp();
             }
         }
-        if (STREAM) row_done(line);
+        if (items.item_start == nullptr && items.ticket_pairs > 0 && !last_run) {
+            __threadfence();  // this run's additions are visible before the next run is released
+            __syncwarp();
+            if (lane == 0) atomicExch(items.line_done + line, run + 1);
+        }
+        if (STREAM && last_run) row_done(line);
     }
     if (COUNT) {
         unsigned long long pix = tally.pix, vg = 7ull * tally.inner;
@@ -1212,6 +1239,23 @@ int launch_tau(const fsb_index *idx, const InterpConsts &c, const float *pos, co
     }
     ItemPlan plan;
     FSB_TRY(plan_items(idx, c.seg_pairs, c.nbins, c.nlines, stream, plan));
+    // One output row per line: hand the lists out in ticketed runs (fsb_items.cuh).  The run length is a multiple
+    // of the particle batch, so the batches, and with them the order of every addition, are those of a whole-list pass.
+    Scratch line_done;
+    if (!plan.segmented) {
+        int64_t ticket = 256;
+        if (const char *env = getenv("FSB200_TICKET_PAIRS")) ticket = std::max(0ll, atoll(env)) / 32 * 32;  // tuning hook; 0 = whole lists
+        if (ticket > 0 && idx->max_list > ticket) {
+            const int64_t nruns = (idx->max_list + ticket - 1) / ticket;
+            if (nruns * (int64_t) idx->nlos <= (int64_t) INT32_MAX) {
+                FSB_TRY(line_done.alloc(sizeof(int32_t) * (size_t) idx->nlos, stream));
+                FSB_CUDA_TRY(cudaMemsetAsync(line_done.ptr, 0, sizeof(int32_t) * (size_t) idx->nlos, stream));
+                plan.items.ticket_pairs = (int32_t) ticket;
+                plan.items.line_done = line_done.as<int32_t>();
+                plan.n_items = nruns * (int64_t) idx->nlos;
+            }
+        }
+    }
     Scratch next_item;
     FSB_TRY(next_item.alloc(sizeof(int), stream));
     FSB_CUDA_TRY(cudaMemsetAsync(next_item.ptr, 0, sizeof(int), stream));
