@@ -87,6 +87,9 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the colden / flux statistics / weak-replica legs")
     ap.add_argument("--ref-lines", type=int, default=0, help="sightlines of the reference sample (0 = choose)")
+    ap.add_argument("--gather", default="push", choices=["push", "nccl"],
+                    help="N > 1, sightline-sharded: how the rows reach every rank: stored into the peers' arrays from inside "
+                         "the tau kernel (push), or gathered afterwards with NCCL (sharding.Sharder.combine)")
     return ap.parse_args()
 
 
@@ -295,6 +298,10 @@ def run_b200(args):
         out.zero_()
         idx = timed("index", lambda: native.CandidateIndex(w["box"], cofm, axis, t["pos"], t["h"], counts=my_counts), time_parts)
 
+        use_push = world > 1 and not pshard and args.gather == "push" and counters is None
+        if use_push and "peer" not in state:
+            state["peer"] = native.PeerRows(nlines, L, nbins)  # full array on every rank, mapped into all the others
+
         def all_tau():
             r0 = 0
             marks = [torch.cuda.Event(enable_timing=True) for _ in range(len(groups) + 1)] if time_parts else None
@@ -302,7 +309,8 @@ def run_b200(args):
                 if marks:
                     marks[gi].record()
                 idx.compute_tau(params[ion], t["pos"], t["vel"], dens[ion], t["temp"], t["h"], out=out[r0:r0 + len(lns)],
-                                counters=None if counters is None else counters[gi])
+                                counters=None if counters is None else counters[gi],
+                                push=state["peer"].push_spec(r0, sl.start) if use_push else None)
                 r0 += len(lns)
             if marks:
                 marks[-1].record()
@@ -310,7 +318,11 @@ def run_b200(args):
         timed("tau", all_tau, time_parts)
         state["npairs"], state["sl"] = idx.npairs, sl
         idx.free()
-        if world > 1:
+        if use_push:
+            # the rows are already in every rank's array: wait until every rank's kernels have finished
+            timed("gather", state["peer"].barrier, time_parts)
+            state["full"] = state["peer"].full
+        elif world > 1:
             # sightlines: gather the row blocks into the full array on every rank; particles: FP64 sum over NCCL
             state["full"] = timed("gather", lambda: sharder.combine(out, L, dim=1), time_parts)
         else:
@@ -503,7 +515,9 @@ def run_b200(args):
                        "parallelism": ("particle-sharded x%d (%d cells per rank, box grows with N), FP64 NCCL sum of the tau array each step"
                                        % (world, w["npart"])) if pshard else
                                       ("sightline-sharded x%d through sharding.Sharder: pair-balanced contiguous blocks of ONE fixed "
-                                       "sightline set, particles replicated, rows gathered to every rank" % world),
+                                       "sightline set, particles replicated, rows delivered to every rank (%s)" % (
+                                           world, "stored into the peers' arrays over NVLink from inside the tau kernel" if args.gather == "push"
+                                           else "NCCL gather after the kernels")),
                        "l2": ("inputs and outputs larger than L2 (particles %.2f GB, tau %.2f GB on this rank)" if flush is None else
                               "working set fits the L2 (particles %.3f GB, tau %.3f GB): a 256 MB buffer is overwritten "
                               "between timed steps, outside the timed intervals") % (
@@ -541,6 +555,9 @@ def run_b200(args):
         }
         line.update(extras)
         print(json.dumps(line))
+    if "peer" in state:
+        state["full"] = None
+        state["peer"].close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -24,6 +24,14 @@ class Params(C.Structure):
                 ("seg_pairs", C.c_int32), ("reserved", C.c_int32)]
 
 
+MAX_PEERS = 16
+
+
+class Push(C.Structure):
+    """struct fsb_push."""
+    _fields_ = [("npeers", C.c_int32), ("reserved", C.c_int32), ("line_stride", C.c_int64), ("dest", C.c_void_p * MAX_PEERS)]
+
+
 class FsbError(RuntimeError):
     def __init__(self, code, what, detail):
         super().__init__("libfsb200: %s (%d): %s" % (what, code, detail))
@@ -45,6 +53,11 @@ SIGNATURES = {
     "fsb_index_export": (C.c_int, [_P, _P, _P, _P, _P]),
     "fsb_compute_tau": (C.c_int, [_P, C.POINTER(Params), _P, _P, _P, _P, _P, _P, _P, _P]),
     "fsb_compute_tau_multi": (C.c_int, [_P, C.POINTER(Params), C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "fsb_compute_tau_multi_push": (C.c_int, [_P, C.POINTER(Params), C.c_int32, _P, _P, _P, _P, _P, _P, C.POINTER(Push), _P]),
+    "fsb_peer_alloc": (C.c_int, [C.c_int64, C.POINTER(_P), _P]),
+    "fsb_peer_free": (C.c_int, [_P]),
+    "fsb_peer_open": (C.c_int, [_P, C.POINTER(_P)]),
+    "fsb_peer_close": (C.c_int, [_P]),
     "fsb_compute_colden": (C.c_int, [_P, C.POINTER(Params), _P, _P, C.c_int32, _P, _P, _P, _P]),
     "fsb_particle_interpolate": (C.c_int, [C.c_int32, C.POINTER(Params), _P, _P, _P, _P, _P, C.c_int64, _P, _P,
                                            C.c_int32, _P, _P]),

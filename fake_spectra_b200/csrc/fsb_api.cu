@@ -137,7 +137,7 @@ namespace {
 // host[line][nlos][nbins]: streamed out while its kernel runs when the launch supports it, copied after it otherwise.
 int compute_tau_multi_impl(const fsb_index *idx, const fsb_params *p, int32_t nlines, const float *pos, const float *vel,
                            const float *dens, const float *temp, const float *h, double *tau, fsb_counters *counters,
-                           cudaStream_t stream, double *host, cudaStream_t copy_stream)
+                           cudaStream_t stream, double *host, cudaStream_t copy_stream, const fsb_push *push = nullptr)
 {
     FSB_REQUIRE(nlines >= 1, "nlines must be >= 1");
     FSB_REQUIRE(idx != nullptr && p != nullptr, "NULL index or params");
@@ -160,8 +160,13 @@ int compute_tau_multi_impl(const fsb_index *idx, const fsb_params *p, int32_t nl
         HostSink sink;
         sink.host = host ? host + off : nullptr;
         sink.copy_stream = copy_stream;
+        fsb_push gpush;
+        if (push) {  // this group's lines start i0 lines into the destination arrays
+            gpush = *push;
+            for (int q = 0; q < gpush.npeers; ++q) gpush.dest[q] += (int64_t) i0 * gpush.line_stride;
+        }
         FSB_TRY(launch_tau(idx, c, pos, vel, dens, temp, h, nullptr, tau + off, counters, p[i0].precision, stream,
-                           host ? &sink : nullptr));
+                           host ? &sink : nullptr, push ? &gpush : nullptr));
         if (host && !sink.streamed) {
             const size_t bytes = sizeof(double) * (size_t) n * (size_t) idx->nlos * (size_t) c.nbins;
             cudaEvent_t done;
@@ -183,6 +188,64 @@ extern "C" int fsb_compute_tau_multi(const fsb_index *idx, const fsb_params *p, 
 {
     return compute_tau_multi_impl(idx, p, nlines, pos, vel, dens, temp, h, tau, counters, static_cast<cudaStream_t>(stream_v),
                                   nullptr, nullptr);
+}
+
+extern "C" int fsb_compute_tau_multi_push(const fsb_index *idx, const fsb_params *p, int32_t nlines, const float *pos,
+                                          const float *vel, const float *dens, const float *temp, const float *h, double *tau,
+                                          const fsb_push *push, void *stream_v)
+{
+    FSB_REQUIRE(push != nullptr && push->npeers >= 1 && push->npeers <= FSB_MAX_PEERS, "push: between 1 and 16 destination arrays");
+    FSB_REQUIRE(nlines >= 1 && p != nullptr, "nlines must be >= 1");
+    for (int q = 0; q < push->npeers; ++q) FSB_REQUIRE(push->dest[q] != nullptr, "push: NULL destination");
+    // one work row per sightline, whatever the caller's seg_pairs: the rows that are pushed are the final rows
+    fsb_params local[kMaxFused];
+    FSB_REQUIRE(nlines <= kMaxFused, "at most 4 lines per call");
+    for (int32_t i = 0; i < nlines; ++i) {
+        local[i] = p[i];
+        local[i].seg_pairs = 1 << 30;
+    }
+    return compute_tau_multi_impl(idx, local, nlines, pos, vel, dens, temp, h, tau, nullptr, static_cast<cudaStream_t>(stream_v),
+                                  nullptr, nullptr, push);
+}
+
+extern "C" int fsb_peer_alloc(int64_t bytes, void **dev_ptr, unsigned char *handle64)
+{
+    FSB_REQUIRE(dev_ptr != nullptr && handle64 != nullptr && bytes > 0, "bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    *dev_ptr = nullptr;
+    FSB_CUDA_TRY(cudaMalloc(dev_ptr, (size_t) bytes));
+    cudaIpcMemHandle_t hnd;
+    const cudaError_t e = cudaIpcGetMemHandle(&hnd, *dev_ptr);
+    if (e != cudaSuccess) {
+        cudaFree(*dev_ptr);
+        *dev_ptr = nullptr;
+        set_error("cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
+        return FSB_ECUDA;
+    }
+    memcpy(handle64, &hnd, sizeof(hnd));
+    return FSB_OK;
+}
+
+extern "C" int fsb_peer_free(void *dev_ptr)
+{
+    if (dev_ptr) FSB_CUDA_TRY(cudaFree(dev_ptr));
+    return FSB_OK;
+}
+
+extern "C" int fsb_peer_open(const unsigned char *handle64, void **dev_ptr)
+{
+    FSB_REQUIRE(dev_ptr != nullptr && handle64 != nullptr, "bad arguments");
+    cudaIpcMemHandle_t hnd;
+    memcpy(&hnd, handle64, sizeof(hnd));
+    *dev_ptr = nullptr;
+    FSB_CUDA_TRY(cudaIpcOpenMemHandle(dev_ptr, hnd, cudaIpcMemLazyEnablePeerAccess));
+    return FSB_OK;
+}
+
+extern "C" int fsb_peer_close(void *dev_ptr)
+{
+    if (dev_ptr) FSB_CUDA_TRY(cudaIpcCloseMemHandle(dev_ptr));
+    return FSB_OK;
 }
 
 extern "C" int fsb_compute_tau(const fsb_index *idx, const fsb_params *p, const float *pos, const float *vel,

@@ -107,7 +107,7 @@ struct HostSink {
 // launches implemented in the .cu files
 int launch_tau(const fsb_index *idx, const InterpConsts &c, const float *pos, const float *vel, const float *dens,
                const float *temp, const float *h, const float *cells, double *out, fsb_counters *counters,
-               int precision, cudaStream_t stream, HostSink *sink = nullptr);
+               int precision, cudaStream_t stream, HostSink *sink = nullptr, const fsb_push *push = nullptr);
 int launch_colden(const fsb_index *idx, const InterpConsts &c, const float *pos, const float *dens, int64_t dens_stride,
                   const float *h, const float *cells, double *out, fsb_counters *counters, cudaStream_t stream);
 int tau_max_fused_lines();

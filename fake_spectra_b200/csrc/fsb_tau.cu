@@ -23,6 +23,7 @@
 //          (sub-sampling rule of singleabs.h:110-125): generic per-node evaluation
 //   EXACT  FSB_VOIGT_EXACT or y outside (1e-30, 0.03]: restatement of the reference's Faddeeva::w
 #include <stdlib.h>
+#include <string.h>
 
 #include "fsb_items.cuh"
 #include "fsb_voigt.cuh"
@@ -1010,7 +1011,7 @@ k_tau(InterpConsts C, Items items, int n_items, int *__restrict__ next_item, con
       const float *__restrict__ pos, const float *__restrict__ vel, const float *__restrict__ dens,
       const float *__restrict__ temp, const float *__restrict__ hsml, const float *__restrict__ cells,
       double *__restrict__ out, double *__restrict__ scratch, int64_t scratch_stride,
-      unsigned long long *__restrict__ counters, int *__restrict__ chunk_done, int *host_flags, int chunk_lines)
+      unsigned long long *__restrict__ counters, int *__restrict__ chunk_done, int *host_flags, int chunk_lines, fsb_push push)
 {
     extern __shared__ __align__(16) double smem[];
     double2 *tab = reinterpret_cast<double2 *>(smem);  // [kGtabPieces]: three 16-byte pieces per interval
@@ -1043,6 +1044,20 @@ k_tau(InterpConsts C, Items items, int n_items, int *__restrict__ next_item, con
         auto row_done = [&](int finished_line) {
             __threadfence();
             __syncwarp();
+            if (push.npeers > 0) {
+                // the finished rows of this sightline (one per fused line) go to every destination array: peers' memory
+                // over NVLink, stores only; 8-byte pieces (rows of an odd number of pixels are not 16-byte aligned)
+                for (int l = 0; l < NL; ++l) {
+                    const double *src = out + (int64_t) l * ((int64_t) C.nlos * C.nbins) + (int64_t) finished_line * C.nbins;
+                    const int64_t doff = (int64_t) l * push.line_stride + (int64_t) finished_line * C.nbins;
+                    for (int j = lane; j < C.nbins; j += 32) {
+                        const double v = __ldcg(src + j);
+                        for (int q = 0; q < push.npeers; ++q) push.dest[q][doff + j] = v;
+                    }
+                }
+                __threadfence_system();
+                if (chunk_done == nullptr) return;
+            }
             if (lane == 0) {
                 const int c = finished_line / chunk_lines;
                 const int in_chunk = min(chunk_lines, C.nlos - c * chunk_lines);
@@ -1160,7 +1175,8 @@ __global__ void k_voigt_profile(const double *__restrict__ x, const double *__re
 template <int KERNEL, int NL>
 int launch_tau_k(const fsb_index *idx, const InterpConsts &c, const ItemPlan &plan, int *next_item, const float *pos,
                  const float *vel, const float *dens, const float *temp, const float *h, const float *cells, double *out,
-                 unsigned long long *ctr, int precision, cudaStream_t stream, int *chunk_done, int *host_flags, int chunk_lines)
+                 unsigned long long *ctr, int precision, cudaStream_t stream, int *chunk_done, int *host_flags, int chunk_lines,
+                 const fsb_push &push)
 {
     int dev = 0, sms = 0, per_sm = 0;
     FSB_CUDA_TRY(cudaGetDevice(&dev));
@@ -1173,16 +1189,16 @@ int launch_tau_k(const fsb_index *idx, const InterpConsts &c, const ItemPlan &pl
         count_launch();
         kern<<<grid, kTauThreads, smem, stream>>>(c, plan.items, n_items, next_item, idx->offsets, idx->zorder, idx->particle, idx->dr2, idx->axis,
                                                   pos, vel, dens, temp, h, cells, out, plan.scratch_rows.as<double>(),
-                                                  plan.n_items * (int64_t) c.nbins, ctr, chunk_done, host_flags, chunk_lines);
+                                                  plan.n_items * (int64_t) c.nbins, ctr, chunk_done, host_flags, chunk_lines, push);
         FSB_CUDA_TRY(cudaGetLastError());
         return FSB_OK;
     };
     constexpr size_t smem64 = tau_smem_bytes<NL, false>(), smem32 = tau_smem_bytes<NL, true>();
     // the row-streaming variant exists without counters only (the host one-shot entry never asks for them)
-    if (chunk_done && !ctr)
+    if ((chunk_done || push.npeers > 0) && !ctr)
         return precision == FSB_PRECISION_FP32 ? go(k_tau<KERNEL, NL, false, true, true>, smem32)
                                                : go(k_tau<KERNEL, NL, false, false, true>, smem64);
-    if (chunk_done) {
+    if (chunk_done || push.npeers > 0) {
         set_error("launch_tau: row streaming and counters are exclusive");
         return FSB_EINVAL;
     }
@@ -1194,13 +1210,14 @@ int launch_tau_k(const fsb_index *idx, const InterpConsts &c, const ItemPlan &pl
 template <int NL>
 int launch_tau_nl(const fsb_index *idx, const InterpConsts &c, const ItemPlan &plan, int *next_item, const float *pos,
                   const float *vel, const float *dens, const float *temp, const float *h, const float *cells, double *out,
-                  unsigned long long *ctr, int precision, cudaStream_t stream, int *chunk_done, int *host_flags, int chunk_lines)
+                  unsigned long long *ctr, int precision, cudaStream_t stream, int *chunk_done, int *host_flags, int chunk_lines,
+                  const fsb_push &push)
 {
     switch (c.kernel) {
-    case FSB_KERNEL_TOPHAT: return launch_tau_k<FSB_KERNEL_TOPHAT, NL>(idx, c, plan, next_item, pos, vel, dens, temp, h, cells, out, ctr, precision, stream, chunk_done, host_flags, chunk_lines);
-    case FSB_KERNEL_CUBIC: return launch_tau_k<FSB_KERNEL_CUBIC, NL>(idx, c, plan, next_item, pos, vel, dens, temp, h, cells, out, ctr, precision, stream, chunk_done, host_flags, chunk_lines);
-    case FSB_KERNEL_VORONOI: return launch_tau_k<FSB_KERNEL_VORONOI, NL>(idx, c, plan, next_item, pos, vel, dens, temp, h, cells, out, ctr, precision, stream, chunk_done, host_flags, chunk_lines);
-    case FSB_KERNEL_QUINTIC: return launch_tau_k<FSB_KERNEL_QUINTIC, NL>(idx, c, plan, next_item, pos, vel, dens, temp, h, cells, out, ctr, precision, stream, chunk_done, host_flags, chunk_lines);
+    case FSB_KERNEL_TOPHAT: return launch_tau_k<FSB_KERNEL_TOPHAT, NL>(idx, c, plan, next_item, pos, vel, dens, temp, h, cells, out, ctr, precision, stream, chunk_done, host_flags, chunk_lines, push);
+    case FSB_KERNEL_CUBIC: return launch_tau_k<FSB_KERNEL_CUBIC, NL>(idx, c, plan, next_item, pos, vel, dens, temp, h, cells, out, ctr, precision, stream, chunk_done, host_flags, chunk_lines, push);
+    case FSB_KERNEL_VORONOI: return launch_tau_k<FSB_KERNEL_VORONOI, NL>(idx, c, plan, next_item, pos, vel, dens, temp, h, cells, out, ctr, precision, stream, chunk_done, host_flags, chunk_lines, push);
+    case FSB_KERNEL_QUINTIC: return launch_tau_k<FSB_KERNEL_QUINTIC, NL>(idx, c, plan, next_item, pos, vel, dens, temp, h, cells, out, ctr, precision, stream, chunk_done, host_flags, chunk_lines, push);
     default: set_error("unknown kernel id %d", c.kernel); return FSB_EINVAL;
     }
 }
@@ -1225,8 +1242,11 @@ struct PinnedFlags {  // zero-initialised ints in pinned, device-visible host me
 // c.nlines (1..kMaxTauLines) lines of one ion in one pass; out[l][nlos][nbins].
 int launch_tau(const fsb_index *idx, const InterpConsts &c, const float *pos, const float *vel, const float *dens,
                const float *temp, const float *h, const float *cells, double *out, fsb_counters *counters, int precision,
-               cudaStream_t stream, HostSink *sink)
+               cudaStream_t stream, HostSink *sink, const fsb_push *push_in)
 {
+    fsb_push push;
+    memset(&push, 0, sizeof(push));
+    if (push_in) push = *push_in;
     if (sink) sink->streamed = false;
     if (idx->nlos == 0 || idx->npairs == 0) return FSB_OK;
     if (precision != FSB_PRECISION_FP64 && precision != FSB_PRECISION_FP32) {
@@ -1278,8 +1298,12 @@ int launch_tau(const fsb_index *idx, const InterpConsts &c, const float *pos, co
         FSB_TRY(flags.alloc((size_t) nchunks));
     }
     int *cd = stream_out ? chunk_done.as<int>() : nullptr;
-    if (c.nlines == 1) FSB_TRY(launch_tau_nl<1>(idx, c, plan, next_item.as<int>(), pos, vel, dens, temp, h, cells, out, ctr, precision, stream, cd, flags.ptr, chunk_lines));
-    else FSB_TRY(launch_tau_nl<2>(idx, c, plan, next_item.as<int>(), pos, vel, dens, temp, h, cells, out, ctr, precision, stream, cd, flags.ptr, chunk_lines));
+    if (push.npeers > 0 && (plan.segmented || ctr || (sink && sink->host))) {
+        set_error("launch_tau: pushing rows to peers needs one work row per sightline, no counters and no host sink");
+        return FSB_EINVAL;
+    }
+    if (c.nlines == 1) FSB_TRY(launch_tau_nl<1>(idx, c, plan, next_item.as<int>(), pos, vel, dens, temp, h, cells, out, ctr, precision, stream, cd, flags.ptr, chunk_lines, push));
+    else FSB_TRY(launch_tau_nl<2>(idx, c, plan, next_item.as<int>(), pos, vel, dens, temp, h, cells, out, ctr, precision, stream, cd, flags.ptr, chunk_lines, push));
     FSB_TRY(reduce_items(plan, idx, c.nbins, c.nlines, out, stream));
     if (stream_out) {
         // follow the kernel: copy each chunk as soon as its flag is up; if the kernel ends first (or fails), the

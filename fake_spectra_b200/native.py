@@ -76,9 +76,11 @@ class CandidateIndex:
             pass
 
     # -- accumulation --------------------------------------------------------------------------
-    def compute_tau(self, params, pos, vel, dens, temp, h, out=None, counters=None):
+    def compute_tau(self, params, pos, vel, dens, temp, h, out=None, counters=None, push=None):
         """params: one _lib.Params or a list of them (fused lines of one ion).
-        Returns float64 [nlos, nbins] (or [nlines, nlos, nbins]); accumulates into ``out`` if given."""
+        Returns float64 [nlos, nbins] (or [nlines, nlos, nbins]); accumulates into ``out`` if given.
+        push: a _lib.Push (see PeerRows.push_spec): finished rows are also stored into the listed full arrays
+        (this rank's and its peers') from inside the kernel."""
         plist = params if isinstance(params, (list, tuple)) else [params]
         nbins = plist[0].nbins
         shape = (len(plist), self.nlos, nbins)
@@ -86,8 +88,14 @@ class CandidateIndex:
             out = torch.zeros(shape, dtype=torch.float64, device=self.device)
         arr = (_lib.Params * len(plist))(*plist)
         with torch.cuda.device(self.device):
-            rc = self.lib.fsb_compute_tau_multi(self.handle, arr, len(plist), _dptr(pos), _dptr(vel), _dptr(dens),
-                                                _dptr(temp), _dptr(h), _dptr(out), _dptr(counters), _stream())
+            if push is not None:
+                if counters is not None:
+                    raise ValueError("counters and push are exclusive")
+                rc = self.lib.fsb_compute_tau_multi_push(self.handle, arr, len(plist), _dptr(pos), _dptr(vel), _dptr(dens),
+                                                         _dptr(temp), _dptr(h), _dptr(out), C.byref(push), _stream())
+            else:
+                rc = self.lib.fsb_compute_tau_multi(self.handle, arr, len(plist), _dptr(pos), _dptr(vel), _dptr(dens),
+                                                    _dptr(temp), _dptr(h), _dptr(out), _dptr(counters), _stream())
         _lib.check(rc, "fsb_compute_tau")
         return out.view(shape) if isinstance(params, (list, tuple)) else out.view(self.nlos, nbins)
 
@@ -112,6 +120,78 @@ class CandidateIndex:
                                            _stream())
         _lib.check(rc, "fsb_assign_cells")
         return cells[:self.npairs]
+
+
+class _RawCuda:
+    """Minimal __cuda_array_interface__ carrier: lets torch wrap device memory this library allocated."""
+
+    def __init__(self, ptr, shape, typestr="<f8"):
+        self.__cuda_array_interface__ = {"shape": tuple(int(x) for x in shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+class PeerRows:
+    """A full result array [K, numlos, nbins] (float64) on every rank of a sightline-sharded job, each rank's copy
+    mapped into all the others (CUDA IPC over NVLink / NVSwitch).  The tau kernel of a rank stores every row it
+    finishes into all copies (fsb_compute_tau_multi_push), so after a barrier every rank holds the complete array
+    without a gather.  One process per GPU on ONE node; `group` as in torch.distributed."""
+
+    def __init__(self, K, numlos, nbins, group=None):
+        import torch.distributed as dist
+        self.lib = _lib.load()
+        self.K, self.numlos, self.nbins = int(K), int(numlos), int(nbins)
+        self.group = group
+        self.rank, self.size = dist.get_rank(group), dist.get_world_size(group)
+        if self.size > _lib.MAX_PEERS:
+            raise ValueError("at most %d ranks" % _lib.MAX_PEERS)
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        nbytes = 8 * self.K * self.numlos * self.nbins
+        ptr, handle = C.c_void_p(), (C.c_ubyte * 64)()
+        _lib.check(self.lib.fsb_peer_alloc(nbytes, C.byref(ptr), handle), "fsb_peer_alloc")
+        self.ptr = ptr.value
+        handles = [None] * self.size
+        dist.all_gather_object(handles, bytes(handle), group=group)
+        self.peer_ptr = []
+        for r, hb in enumerate(handles):
+            if r == self.rank:
+                self.peer_ptr.append(self.ptr)
+                continue
+            q = C.c_void_p()
+            buf = (C.c_ubyte * 64).from_buffer_copy(hb)
+            _lib.check(self.lib.fsb_peer_open(buf, C.byref(q)), "fsb_peer_open")
+            self.peer_ptr.append(q.value)
+        self._carrier = _RawCuda(self.ptr, (self.K, self.numlos, self.nbins))
+        self.full = torch.as_tensor(self._carrier, device=self.device)
+
+    def push_spec(self, first_line, first_sightline):
+        """Destinations for a compute_tau call whose first line is `first_line` of K and whose sightline block starts
+        at `first_sightline` of numlos."""
+        sp = _lib.Push()
+        sp.npeers = self.size
+        sp.line_stride = self.numlos * self.nbins
+        off = 8 * ((int(first_line) * self.numlos + int(first_sightline)) * self.nbins)
+        for r in range(self.size):
+            sp.dest[r] = self.peer_ptr[r] + off
+        return sp
+
+    def barrier(self):
+        """All ranks' kernels have finished (stream-ordered on each rank) => every copy is complete."""
+        import torch.distributed as dist
+        dist.barrier(group=self.group)
+
+    def close(self):
+        if getattr(self, "ptr", None) is None:
+            return
+        import torch.distributed as dist
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)  # nobody is still writing into anybody's array
+        for r, q in enumerate(self.peer_ptr):
+            if r != self.rank:
+                self.lib.fsb_peer_close(C.c_void_p(q))
+        dist.barrier(group=self.group)
+        self.full = None
+        self.lib.fsb_peer_free(C.c_void_p(self.ptr))
+        self.ptr = None
 
 
 def particle_interpolate(compute_tau, params, pos, vel, dens, temp, h, axis, cofm, out=None):

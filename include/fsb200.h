@@ -128,6 +128,32 @@ FSB_API int fsb_compute_tau(const fsb_index *idx, const fsb_params *p, const flo
 FSB_API int fsb_compute_tau_multi(const fsb_index *idx, const fsb_params *p, int32_t nlines, const float *pos,
                           const float *vel, const float *dens, const float *temp, const float *h,
                           double *tau, fsb_counters *counters, void *stream);
+/* ---- sightline-sharded multi-GPU: rows pushed to the peers while the kernel runs -------------------------
+ * One process per GPU, every rank interpolates a block of the sightlines (no reference counterpart: the reference
+ * shards particles and Allreduces, spectra.py:825-831).  Every rank owns a FULL result array [nlines_total][numlos]
+ * [nbins] in memory obtained from fsb_peer_alloc, and maps the other ranks' arrays with fsb_peer_open (CUDA IPC over
+ * NVLink / NVSwitch).  fsb_compute_tau_multi_push is fsb_compute_tau_multi plus: the warp that completes a sightline's
+ * row stores that row into every array listed in `push`, from inside the tau kernel, so the gather of the result rows
+ * overlaps the computation and needs no collective (a barrier across the ranks afterwards makes the arrays complete). */
+#define FSB_MAX_PEERS 16
+typedef struct fsb_push {
+    int32_t npeers;           /* number of destination arrays (the rank's own array may be one of them)            */
+    int32_t reserved;
+    int64_t line_stride;      /* elements between consecutive LINES in the destination arrays: numlos * nbins         */
+    double *dest[FSB_MAX_PEERS]; /* per destination: address of [first line of this call][first sightline of this
+                                 rank's block][0] in that array, valid in THIS process (own or fsb_peer_open'ed)     */
+} fsb_push;
+/* cudaMalloc'ed device memory that other processes of this node can map: handle[64] = cudaIpcMemHandle_t. */
+FSB_API int fsb_peer_alloc(int64_t bytes, void **dev_ptr, unsigned char *handle64);
+FSB_API int fsb_peer_free(void *dev_ptr);
+/* Maps another process's fsb_peer_alloc memory into this process (peer access is enabled as needed). */
+FSB_API int fsb_peer_open(const unsigned char *handle64, void **dev_ptr);
+FSB_API int fsb_peer_close(void *dev_ptr);
+/* tau[nlines][nlos*nbins] as fsb_compute_tau_multi (the rank's working rows); one work row per sightline is forced. */
+FSB_API int fsb_compute_tau_multi_push(const fsb_index *idx, const fsb_params *p, int32_t nlines, const float *pos,
+                               const float *vel, const float *dens, const float *temp, const float *h,
+                               double *tau, const fsb_push *push, void *stream);
+
 /* part_int.cpp:53-84, with nweights density-like columns sharing one geometry pass
  * (spectra.py:945-1024 issues one colden call per weight).  dens[nweights][npart] f32,
  * colden[nweights][nlos*nbins] f64, accumulated into. */
