@@ -160,8 +160,14 @@ class PeerRows:
             buf = (C.c_ubyte * 64).from_buffer_copy(hb)
             _lib.check(self.lib.fsb_peer_open(buf, C.byref(q)), "fsb_peer_open")
             self.peer_ptr.append(q.value)
-        self._carrier = _RawCuda(self.ptr, (self.K, self.numlos, self.nbins))
-        self.full = torch.as_tensor(self._carrier, device=self.device)
+        self._carriers = [_RawCuda(q, (self.K, self.numlos, self.nbins)) for q in self.peer_ptr]
+        self.views = [torch.as_tensor(c, device=self.device) for c in self._carriers]  # every rank's array, as seen from here
+        self.full = self.views[self.rank]
+
+    def zero_block(self, first_sightline, nrows):
+        """Zero this rank's block of rows in every copy (a rank that launches no kernel for its block)."""
+        for v in self.views:
+            v[:, first_sightline:first_sightline + nrows].zero_()
 
     def push_spec(self, first_line, first_sightline):
         """Destinations for a compute_tau call whose first line is `first_line` of K and whose sightline block starts
@@ -190,6 +196,7 @@ class PeerRows:
                 self.lib.fsb_peer_close(C.c_void_p(q))
         dist.barrier(group=self.group)
         self.full = None
+        self.views = []
         self.lib.fsb_peer_free(C.c_void_p(self.ptr))
         self.ptr = None
 

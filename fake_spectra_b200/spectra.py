@@ -48,12 +48,17 @@ class _SegmentEngine:
         self.index = native.CandidateIndex(spec.box, self.cofm, self.axis, self.pos, self.h)
         self.cells = None
 
-    def tau(self, params_list):
-        """float64 CUDA tensor [nlines, nlos_local, nbins]."""
+    def tau(self, params_list, out=None, push=None):
+        """float64 CUDA tensor [nlines, nlos_local, nbins]; accumulated into ``out`` when given.  ``push``: see
+        native.PeerRows (rows finished by this call are also stored into every rank's full array)."""
         if params_list[0].kernel == 2:
-            return self.torch.stack([self.native.particle_interpolate(1, p, self.pos, self.vel, self.dens, self.temp, self.h,
-                                                                      self.axis, self.cofm) for p in params_list])
-        return self.index.compute_tau(list(params_list), self.pos, self.vel, self.dens, self.temp, self.h)
+            res = self.torch.stack([self.native.particle_interpolate(1, p, self.pos, self.vel, self.dens, self.temp, self.h,
+                                                                     self.axis, self.cofm) for p in params_list])
+            if out is not None:
+                out += res
+                return out
+            return res
+        return self.index.compute_tau(list(params_list), self.pos, self.vel, self.dens, self.temp, self.h, out=out, push=push)
 
     def colden(self, params, weights=None):
         """Column density of the ion density (weights None) or of K weight columns
@@ -79,13 +84,17 @@ class Spectra:
     resident   keep particles + candidate index in HBM between calls (default: on when CUDA is there)
     backend    object providing _Particle_Interpolate / _near_lines (default: the CUDA boundary
                module; the CPU tests of the host logic pass a checker here)
+    seg_pairs  candidate pairs per work item of the kernels (fsb_params.seg_pairs).  None = one work row per
+               sightline when sharded (every row is then bit-identical whatever the number of GPUs), automatic
+               otherwise (few sightlines are cut into segments with private rows, summed in list order: faster on one
+               GPU, same values to rounding); 1 << 30 forces one work row per sightline.
     """
 
     def __init__(self, num, base, cofm, axis, MPI=None, nbins=None, res=1., cdir=None, savefile="spectra.hdf5",
                  savedir=None, reload_file=False, spec_res=0, load_halo=False, units=None, sf_neutral=True,
                  turn_off_selfshield=False, quiet=False, load_snapshot=True, gasprop=None, gasprop_args=None,
                  kernel=None, use_external_Hz=None, precision="fp64", voigt="fast", shard=None, group=None,
-                 resident=None, backend=None):
+                 resident=None, backend=None, seg_pairs=None):
         _ = (load_halo, load_snapshot)
         self.num = num
         self.base = base
@@ -112,6 +121,7 @@ class Spectra:
         self.cdir = cdir
         self.minwidth = 500.
         self.tautail = 1e-7  # spectra.py:135
+        self.seg_pairs = seg_pairs
         self.precision = _PRECISION[precision]
         self.voigt = _VOIGT[voigt]
         self._backend = backend if backend is not None else _spectra_priv
@@ -393,11 +403,35 @@ class Spectra:
             raise KeyError((elem, ion, ll))
         return self.lines[(elem, ion)][ll]
 
-    def _params(self, line, amumass):
+    def _params(self, line, amumass, unsegmented=False):
         from . import _lib
         gamma_X = 0 if self.turn_off_selfshield else line.gamma_X
+        # sharded runs keep one work row per sightline: rows are then bit-identical whatever the partition
+        seg = (1 << 30) if (unsegmented or self._sharder.size > 1) else 0
+        if self.seg_pairs is not None:
+            seg = int(self.seg_pairs)
         return _lib.make_params(self.nbins, self.kernel_int, self.box, self.velfac, self.atime, line.lambda_X * 1e-8, gamma_X,
-                                line.fosc_X, amumass, self.tautail, precision=self.precision, voigt=self.voigt)
+                                line.fosc_X, amumass, self.tautail, precision=self.precision, voigt=self.voigt, seg_pairs=seg)
+
+    def _push_rows(self):
+        """True when the ranks exchange result rows through peer-mapped arrays: sightline-sharded, several ranks,
+        NCCL process group (one process per GPU of one node), every rank with at least one engine decides alike."""
+        if self._sharder.mode != "sightlines" or self._sharder.size == 1 or self._backend is not _spectra_priv:
+            return False
+        import torch.distributed as dist
+        return dist.is_initialized() and dist.get_backend(self._sharder.group) == "nccl"
+
+    def _peer_rows(self, nl):
+        """The full [nl, NumLos, nbins] array of this rank, mapped into every other rank (cached per shape)."""
+        from . import native
+        key = (nl, self.NumLos, self.nbins)
+        cache = self.__dict__.setdefault("_peer_cache", {})
+        if key not in cache:
+            for old in cache.values():
+                old.close()
+            cache.clear()
+            cache[key] = native.PeerRows(nl, self.NumLos, self.nbins, group=self._sharder.group)
+        return cache[key]
 
     def _do_interpolation_work(self, pos, vel, elem_den, temp, hh, amumass, line, get_tau):
         """Run the interpolation on pre-determined host arrays (spectra.py:666-673): the drop-in
@@ -468,14 +502,23 @@ class Spectra:
         if self.resident:
             import torch
             acc = torch.zeros((nl, nlocal, self.nbins), dtype=torch.float64, device="cuda")
-            for seg in self._segments():
-                eng = self._engine(seg, elem, ion)
-                if eng is None:
-                    continue
+            engines = [e for e in (self._engine(seg, elem, ion) for seg in self._segments()) if e is not None]
+            # sightline-sharded optical depths on several GPUs: the kernel of the LAST segment stores every finished row
+            # (all segments summed) into every rank's full array over NVLink; no gather afterwards (native.PeerRows)
+            peer = self._peer_rows(nl) if (get_tau and self.kernel_int != 2 and self._push_rows()) else None
+            for n, eng in enumerate(engines):
                 if get_tau:
-                    acc += eng.tau([self._params(self._line(elem, ion, ll), eng.amumass) for ll in lls])
+                    push = peer.push_spec(0, self._my_slice.start) if (peer is not None and n == len(engines) - 1) else None
+                    eng.tau([self._params(self._line(elem, ion, ll), eng.amumass, unsegmented=peer is not None) for ll in lls],
+                            out=acc, push=push)
                 else:
                     acc += eng.colden(self._params(self.lines[("H", 1)][1215], eng.amumass))
+            if peer is not None:
+                if not engines:  # no particle of the snapshot reaches this rank's sightlines: its rows are zero
+                    peer.zero_block(self._my_slice.start, nlocal)
+                torch.cuda.synchronize()
+                peer.barrier()
+                return peer.full.cpu().numpy()
             local = acc
         else:
             arepo = self.kernel_int == 2
