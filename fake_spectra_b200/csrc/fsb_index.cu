@@ -108,45 +108,88 @@ __global__ void k_line_scatter(const double *__restrict__ cofm, const int32_t *_
 // sees), taken modulo the grid: a superset of the cells that hold a line passing the predicate, whatever
 // side of the periodic box the particle's reach falls on (lines outside [0, box] sit in the edge cells,
 // where cell_of clamps them, and those are the cells a wrapped reach lands in).
+// Exact predicate of one (particle, axis group): every constant the comparisons of index_table.cpp:22-113 need,
+// derived once per particle and group, and only when the cell walk found a sightline to test.
+struct PairTest {
+    double box, first, second, dffm, dffp, dsfm, dsfp, wrap_hi, wrap_lo, h2;
+    bool wrapped, hi_wrap, lo_wrap;
+    __device__ __forceinline__ void init(double box_, float first_f, float second_f, float h, double h2_)
+    {
+        box = box_;
+        h2 = h2_;
+        first = (double) first_f;
+        second = (double) second_f;
+        // B1, index_table.cpp:89-113: float add, wrap in double then round to float.
+        float ffp = __fadd_rn(first_f, h);
+        if ((double) ffp > box) ffp = __double2float_rn(__dsub_rn((double) ffp, box));
+        float ffm = __fsub_rn(first_f, h);
+        if (ffm < 0) ffm = __double2float_rn(__dadd_rn((double) ffm, box));
+        wrapped = !(ffm <= ffp);
+        dffm = (double) ffm;
+        dffp = (double) ffp;
+        // B2, index_table.cpp:52-68: wrap arithmetic stays in double here.
+        const float sfp = __fadd_rn(second_f, h);
+        const float sfm = __fsub_rn(second_f, h);
+        dsfp = (double) sfp;
+        dsfm = (double) sfm;
+        hi_wrap = dsfp > box;
+        lo_wrap = sfm < 0;
+        wrap_hi = __dsub_rn(dsfp, box);  // lproj2 < sfp - box
+        wrap_lo = __dadd_rn(dsfm, box);  // lproj2 > sfm + box
+    }
+    __device__ __forceinline__ bool operator()(double key, double lp2) const
+    {
+        // B1: lower_bound on both ends -> [ffm, ffp)
+        const bool in1 = !wrapped ? (key >= dffm && key < dffp) : (key < dffp || key >= dffm);
+        if (!in1) return false;
+        bool in2 = false;
+        if (hi_wrap && lp2 < wrap_hi) in2 = true;
+        else if (lo_wrap && lp2 > wrap_lo) in2 = true;
+        else in2 = (lp2 > dsfm && lp2 < dsfp);
+        if (!in2) return false;
+        // B3, index_table.cpp:70-87: separately rounded products and sum
+        double d1 = fabs(__dsub_rn(first, key));
+        if (d1 > 0.5 * box) d1 = __dsub_rn(box, d1);
+        double d2 = fabs(__dsub_rn(second, lp2));
+        if (d2 > 0.5 * box) d2 = __dsub_rn(box, d2);
+        const double dr2 = __dadd_rn(__dmul_rn(d1, d1), __dmul_rn(d2, d2));
+        return dr2 <= h2;
+    }
+};
+
+// One axis group of one particle: walks the grid cells its kernel square can reach and applies the exact
+// predicate to the sightlines binned there.
+//
+// Cells are enumerated from the UNWRAPPED square [first - h, first + h] x [second - h, second + h] widened by
+// 1e-3 of a cell (far above the float rounding of first +- h that the exact predicate sees, and above the rounding of
+// this single-precision cell arithmetic), taken modulo the grid: a superset of the cells that hold a line passing
+// the predicate, whatever side of the periodic box the particle's reach falls on (lines outside [0, box] sit in the
+// edge cells, where cell_of clamps them, and those are the cells a wrapped reach lands in).  With few sightlines
+// most reached cells are empty and the particle costs two loads per grid row.
 template <int MODE, int GRP>
 __device__ __forceinline__ void pairs_in_group(const LineTable &T, const AxisGrid g, float px, float py, float pz, float h,
-                                               double h2, int64_t p, int32_t *__restrict__ count,
+                                               int64_t p, int32_t *__restrict__ count,
                                                const int64_t *__restrict__ offsets, int32_t *__restrict__ particle, bool &any)
 {
-    if (g.G == 0) return;
-    const double box = T.box;
+    const int G = g.G;
+    if (G == 0) return;
     // axis 1: (y,z); axis 2: (x,z); axis 3: (x,y)   (index_table.cpp:29-40,120-125)
     const float first = GRP == 0 ? py : px;
     const float second = GRP == 2 ? py : pz;
-
-    // B1, index_table.cpp:89-113: float add, wrap in double then round to float.
-    float ffp = __fadd_rn(first, h);
-    if ((double) ffp > box) ffp = __double2float_rn(__dsub_rn((double) ffp, box));
-    float ffm = __fsub_rn(first, h);
-    if (ffm < 0) ffm = __double2float_rn(__dadd_rn((double) ffm, box));
-    const bool wrapped = !(ffm <= ffp);
-    const double dffm = (double) ffm, dffp = (double) ffp;
-    // B2, index_table.cpp:52-68: wrap arithmetic stays in double here.
-    const float sfp = __fadd_rn(second, h);
-    const float sfm = __fsub_rn(second, h);
-    const double dsfp = (double) sfp, dsfm = (double) sfm;
-    const bool hi_wrap = dsfp > box;
-    const bool lo_wrap = sfm < 0;
-    const double wrap_hi = __dsub_rn(dsfp, box);  // lproj2 < sfp - box
-    const double wrap_lo = __dadd_rn(dsfm, box);  // lproj2 > sfm + box
-
-    const double eps = 1e-6 * box, reach = (double) h + eps;
-    const double fr0 = floor(((double) first - reach) * g.inv_cs), fr1 = floor(((double) first + reach) * g.inv_cs);
-    const double fc0 = floor(((double) second - reach) * g.inv_cs), fc1 = floor(((double) second + reach) * g.inv_cs);
+    const float inv = (float) g.inv_cs, fG = (float) G;
+    const float fr0 = floorf(fmaf(first - h, inv, -1e-3f)), fr1 = floorf(fmaf(first + h, inv, 1e-3f));
+    const float fc0 = floorf(fmaf(second - h, inv, -1e-3f)), fc1 = floorf(fmaf(second + h, inv, 1e-3f));
     if (!(fr1 >= fr0) || !(fc1 >= fc0)) return;  // NaN coordinates reach nothing
-    const int G = g.G;
-    const int nrow = (int) fmin(fr1 - fr0 + 1.0, (double) G), ncol = (int) fmin(fc1 - fc0 + 1.0, (double) G);
-    int row = (int) fmod(fr0, (double) G);
-    row += row < 0 ? G : 0;
-    int col0 = (int) fmod(fc0, (double) G);
-    col0 += col0 < 0 ? G : 0;
+    const int nrow = (int) fminf(fr1 - fr0 + 1.0f, fG), ncol = (int) fminf(fc1 - fc0 + 1.0f, fG);
+    // first row / column modulo G (the common case needs one correction; anything farther out takes the division)
+    int row = (int) fmaxf(fminf(fr0, 3.0e8f), -3.0e8f);
+    row = (row >= -G && row < 2 * G) ? (row < 0 ? row + G : (row >= G ? row - G : row)) : ((row % G) + G) % G;
+    int col0 = (int) fmaxf(fminf(fc0, 3.0e8f), -3.0e8f);
+    col0 = (col0 >= -G && col0 < 2 * G) ? (col0 < 0 ? col0 + G : (col0 >= G ? col0 - G : col0)) : ((col0 % G) + G) % G;
     // the reach in columns: [col0, col0 + ncol) modulo G = one span, or two when it crosses the edge
     const int span1_hi = min(col0 + ncol, G) - 1, span2_hi = col0 + ncol - G - 1;  // span 2 = [0, span2_hi] when >= 0
+    PairTest test;
+    bool have_test = false;
     for (int rr = 0; rr < nrow; ++rr) {
         const int32_t *cs = T.cell_start + g.cell_base + row * G;
         row = row + 1 == G ? 0 : row + 1;
@@ -155,24 +198,12 @@ __device__ __forceinline__ void pairs_in_group(const LineTable &T, const AxisGri
             if (sp == 1 && span2_hi < 0) break;
             const int beg = cs[sp == 0 ? col0 : 0];
             const int end = cs[(sp == 0 ? span1_hi : span2_hi) + 1];
+            if (end > beg && !have_test) {
+                test.init(T.box, first, second, h, (double) __fmul_rn(h, h));  // float product: index_table.cpp:45
+                have_test = true;
+            }
             for (int s = beg; s < end; ++s) {
-                const double key = T.key[s];
-                // B1: lower_bound on both ends -> [ffm, ffp)
-                const bool in1 = !wrapped ? (key >= dffm && key < dffp) : (key < dffp || key >= dffm);
-                if (!in1) continue;
-                const double lp2 = T.proj2[s];
-                bool in2 = false;
-                if (hi_wrap && lp2 < wrap_hi) in2 = true;
-                else if (lo_wrap && lp2 > wrap_lo) in2 = true;
-                else in2 = (lp2 > dsfm && lp2 < dsfp);
-                if (!in2) continue;
-                // B3, index_table.cpp:70-87: separately rounded products and sum
-                double d1 = fabs(__dsub_rn((double) first, key));
-                if (d1 > 0.5 * box) d1 = __dsub_rn(box, d1);
-                double d2 = fabs(__dsub_rn((double) second, lp2));
-                if (d2 > 0.5 * box) d2 = __dsub_rn(box, d2);
-                const double dr2 = __dadd_rn(__dmul_rn(d1, d1), __dmul_rn(d2, d2));
-                if (!(dr2 <= h2)) continue;
+                if (!test(T.key[s], T.proj2[s])) continue;
                 if (MODE == 0) {
                     atomicAdd(&count[T.line_id[s]], 1);
                 } else if (MODE == 1) {
@@ -206,11 +237,10 @@ __global__ void __launch_bounds__(256) k_pairs(LineTable T, const float *__restr
     const int64_t p = p0 + threadIdx.x;
     const float px = s_pos[3 * threadIdx.x], py = s_pos[3 * threadIdx.x + 1], pz = s_pos[3 * threadIdx.x + 2];
     const float h = hh[p];
-    const double h2 = (double) __fmul_rn(h, h);  // float product: index_table.cpp:45
     bool any = false;
-    pairs_in_group<MODE, 0>(T, T.grid[0], px, py, pz, h, h2, p, count, offsets, particle, any);
-    if (!(MODE == 2 && any)) pairs_in_group<MODE, 1>(T, T.grid[1], px, py, pz, h, h2, p, count, offsets, particle, any);
-    if (!(MODE == 2 && any)) pairs_in_group<MODE, 2>(T, T.grid[2], px, py, pz, h, h2, p, count, offsets, particle, any);
+    pairs_in_group<MODE, 0>(T, T.grid[0], px, py, pz, h, p, count, offsets, particle, any);
+    if (!(MODE == 2 && any)) pairs_in_group<MODE, 1>(T, T.grid[1], px, py, pz, h, p, count, offsets, particle, any);
+    if (!(MODE == 2 && any)) pairs_in_group<MODE, 2>(T, T.grid[2], px, py, pz, h, p, count, offsets, particle, any);
     if (MODE == 2) flag[p] = any ? 1 : 0;
 }
 
