@@ -83,8 +83,16 @@ struct Items {
     // line_done[line] == s, adds into the line's own row, then publishes s + 1.  The row therefore receives its
     // particles in exactly the order of an unsegmented pass (results are bit-identical whatever the number of
     // sightlines, warps or GPUs), while the scheduling granularity is a run instead of a whole sightline.
+    //
+    // Dispatch order: phases by REMAINING runs, most first.  Phase k (k = 0 .. max_runs - 1) holds, for every line with at
+    // least r = max_runs - k runs, its run number nruns(line) - r; inside a phase the lines that start with this run
+    // come first.  A line's runs keep their order (remaining runs fall from phase to phase), lines with long lists start
+    // early, and the last phase is the last run of EVERY line: no thinly populated tail of phases at the end.
     int32_t ticket_pairs;       // 0: one item per line
+    int32_t max_runs;           // runs of the longest list
     int32_t *line_done;         // [nlos] zero-initialised
+    const int32_t *phase_start; // [max_runs + 1] first item of each phase; [max_runs] = total number of items
+    const int32_t *order;       // [nlos] lines sorted by number of runs, descending
 };
 
 // item -> (line, [kbeg, kend) in the pair arrays).  Returns false for items past the end.
@@ -121,7 +129,7 @@ __device__ __forceinline__ int wrap_bin(int z, int nbins)
 
 // Work-item table for one launch.
 struct ItemPlan {
-    Scratch item_start, nitems, scratch_rows;
+    Scratch item_start, nitems, scratch_rows, line_done, phase_start, order;
     Items items;
     int64_t n_items = 0;  // upper bound on the number of items (= grid size)
     bool segmented = false;
@@ -130,6 +138,9 @@ struct ItemPlan {
 // Chooses the segment length (0 = one item per sightline) and, when segmenting, builds the item
 // table and the zeroed scratch rows ([nrows_per_item][n_items][nbins] doubles).
 int plan_items(const fsb_index *idx, int seg_pairs_req, int nbins, int nrows_per_item, cudaStream_t stream, ItemPlan &plan);
+
+// Switches an unsegmented plan to ticketed runs of `ticket` candidates (a multiple of the kernels' particle batch).
+int plan_tickets(const fsb_index *idx, int ticket, cudaStream_t stream, ItemPlan &plan);
 
 // out[w][line][j] += sum over the line's items (in list order) of scratch[w][item][j]
 int reduce_items(const ItemPlan &plan, const fsb_index *idx, int nbins, int nrows_per_item, double *out, cudaStream_t stream);

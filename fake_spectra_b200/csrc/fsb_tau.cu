@@ -1032,6 +1032,39 @@ k_tau(InterpConsts C, Items items, int n_items, int *__restrict__ next_item, con
     Tally tally;
     unsigned long long n_pairs = 0;
 
+    // one item per sightline and a host sink: the last row of a chunk of sightlines to finish raises the
+    // chunk's flag in pinned host memory; the host copies that chunk out while the kernel carries on
+    auto row_done = [&](int finished_line) {
+        __threadfence();
+        __syncwarp();
+        if (push.npeers > 0) {
+            // the finished rows of this sightline (one per fused line) go to every destination array: peers' memory
+            // over NVLink, stores only; 8-byte pieces (rows of an odd number of pixels are not 16-byte aligned)
+            for (int l = 0; l < NL; ++l) {
+                const double *src = out + (int64_t) l * ((int64_t) C.nlos * C.nbins) + (int64_t) finished_line * C.nbins;
+                const int64_t doff = (int64_t) l * push.line_stride + (int64_t) finished_line * C.nbins;
+                for (int j = lane; j < C.nbins; j += 32) {
+                    const double v = __ldcg(src + j);
+                    for (int q = 0; q < push.npeers; ++q) push.dest[q][doff + j] = v;
+                }
+            }
+            __threadfence_system();
+            if (chunk_done == nullptr) return;
+        }
+        if (lane == 0) {
+            const int c = finished_line / chunk_lines;
+            const int in_chunk = min(chunk_lines, C.nlos - c * chunk_lines);
+            if (atomicAdd(&chunk_done[c], 1) + 1 == in_chunk) {
+                __threadfence_system();
+                *reinterpret_cast<volatile int *>(host_flags + c) = 1;
+            }
+        }
+    };
+    if (STREAM && items.item_start == nullptr && items.ticket_pairs > 0) {
+        // ticketed runs only list sightlines that have candidates: the empty ones are finished here, spread over the warps
+        for (int l = blockIdx.x * kTauWarps + warp; l < C.nlos; l += gridDim.x * kTauWarps)
+            if (offsets[l + 1] == offsets[l]) row_done(l);
+    }
     for (;;) {
         int item = 0;
         if (lane == 0) item = atomicAdd(next_item, 1);
@@ -1039,41 +1072,22 @@ k_tau(InterpConsts C, Items items, int n_items, int *__restrict__ next_item, con
         if (item >= n_items) break;
         int line;
         int64_t kbeg, kend;
-        // one item per sightline and a host sink: the last row of a chunk of sightlines to finish raises the
-        // chunk's flag in pinned host memory; the host copies that chunk out while the kernel carries on
-        auto row_done = [&](int finished_line) {
-            __threadfence();
-            __syncwarp();
-            if (push.npeers > 0) {
-                // the finished rows of this sightline (one per fused line) go to every destination array: peers' memory
-                // over NVLink, stores only; 8-byte pieces (rows of an odd number of pixels are not 16-byte aligned)
-                for (int l = 0; l < NL; ++l) {
-                    const double *src = out + (int64_t) l * ((int64_t) C.nlos * C.nbins) + (int64_t) finished_line * C.nbins;
-                    const int64_t doff = (int64_t) l * push.line_stride + (int64_t) finished_line * C.nbins;
-                    for (int j = lane; j < C.nbins; j += 32) {
-                        const double v = __ldcg(src + j);
-                        for (int q = 0; q < push.npeers; ++q) push.dest[q][doff + j] = v;
-                    }
-                }
-                __threadfence_system();
-                if (chunk_done == nullptr) return;
-            }
-            if (lane == 0) {
-                const int c = finished_line / chunk_lines;
-                const int in_chunk = min(chunk_lines, C.nlos - c * chunk_lines);
-                if (atomicAdd(&chunk_done[c], 1) + 1 == in_chunk) {
-                    __threadfence_system();
-                    *reinterpret_cast<volatile int *>(host_flags + c) = 1;
-                }
-            }
-        };
         int run = 0;
         bool last_run = true;
         if (items.item_start == nullptr && items.ticket_pairs > 0) {
-            // ticketed run of a line's list: item = run * nlos + line
-            run = item / C.nlos;
-            line = item - run * C.nlos;
+            // ticketed run of a line's list: phases by remaining runs (fsb_items.cuh)
+            const int nph = items.max_runs;
+            if (item >= items.phase_start[nph]) break;
+            int lo = 0, hi = nph;  // last phase with phase_start <= item
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (items.phase_start[mid] <= item) lo = mid;
+                else hi = mid;
+            }
+            const int in_phase = items.phase_start[lo + 1] - items.phase_start[lo];
+            line = items.order[in_phase - 1 - (item - items.phase_start[lo])];  // lines that start in this phase first
             const int64_t b0 = offsets[line], b1 = offsets[line + 1];
+            run = (int) ((b1 - b0 + items.ticket_pairs - 1) / items.ticket_pairs) - (nph - lo);
             kbeg = b0 + (int64_t) run * items.ticket_pairs;
             kend = min(kbeg + (int64_t) items.ticket_pairs, b1);
             last_run = kend >= b1;
@@ -1261,20 +1275,10 @@ int launch_tau(const fsb_index *idx, const InterpConsts &c, const float *pos, co
     FSB_TRY(plan_items(idx, c.seg_pairs, c.nbins, c.nlines, stream, plan));
     // One output row per line: hand the lists out in ticketed runs (fsb_items.cuh).  The run length is a multiple
     // of the particle batch, so the batches, and with them the order of every addition, are those of a whole-list pass.
-    Scratch line_done;
     if (!plan.segmented) {
         int64_t ticket = 256;
         if (const char *env = getenv("FSB200_TICKET_PAIRS")) ticket = std::max(0ll, atoll(env)) / 32 * 32;  // tuning hook; 0 = whole lists
-        if (ticket > 0 && idx->max_list > ticket) {
-            const int64_t nruns = (idx->max_list + ticket - 1) / ticket;
-            if (nruns * (int64_t) idx->nlos <= (int64_t) INT32_MAX) {
-                FSB_TRY(line_done.alloc(sizeof(int32_t) * (size_t) idx->nlos, stream));
-                FSB_CUDA_TRY(cudaMemsetAsync(line_done.ptr, 0, sizeof(int32_t) * (size_t) idx->nlos, stream));
-                plan.items.ticket_pairs = (int32_t) ticket;
-                plan.items.line_done = line_done.as<int32_t>();
-                plan.n_items = nruns * (int64_t) idx->nlos;
-            }
-        }
+        if (ticket > 0 && idx->max_list > ticket) FSB_TRY(plan_tickets(idx, (int) ticket, stream, plan));
     }
     Scratch next_item;
     FSB_TRY(next_item.alloc(sizeof(int), stream));
