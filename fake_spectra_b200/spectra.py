@@ -60,6 +60,12 @@ class _SegmentEngine:
             return res
         return self.index.compute_tau(list(params_list), self.pos, self.vel, self.dens, self.temp, self.h, out=out, push=push)
 
+    def release(self):
+        """Free the candidate index now (the tensors go back to torch's allocator with the object)."""
+        if self.index is not None:
+            self.index.free()
+            self.index = None
+
     def colden(self, params, weights=None):
         """Column density of the ion density (weights None) or of K weight columns
         [K, npart] float32 CUDA in one geometry pass: float64 [K, nlos_local, nbins]."""
@@ -276,8 +282,23 @@ class Spectra:
         sf.load(self, savefile)
 
     def save_file(self):
+        """Writes every result this object holds, including arrays of a reopened savefile that were never touched
+        (they are loaded first, like the reference's _load_all_multihash, spectra.py:275-282: the old file becomes
+        the .backup and must not be the only copy of anything).  Only one process writes: rank 0 of the sharding group,
+        of MPI, and of torch.distributed when a process group exists without sharding."""
         from . import savefile as sf
-        if self._sharder.rank == 0 and self.rank == 0:
+        for cache, name in ((self.tau_obs, "tau_obs"), (self.tau, "tau"), (self.colden, "colden"), (self.velocity, "velocity"),
+                            (self.temp, "temperature"), (self.dens_weight_dens, "density_weight_density")):
+            for key in list(cache.keys()):
+                self._really_load_array(key, cache, name)
+        global_rank = 0
+        try:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                global_rank = dist.get_rank()
+        except ImportError:
+            pass
+        if self._sharder.rank == 0 and self.rank == 0 and global_rank == 0:
             sf.save(self, self.savefile)
 
     def _really_load_array(self, key, array, array_name):
@@ -447,30 +468,41 @@ class Spectra:
                                                    vel, elem_den, temp, hh, self._my_axis, self._my_cofm, **kw)
 
     def _engine(self, fn, elem, ion):
-        """Device-resident particles + candidate index of a segment (None when it has no particles
-        near this rank's sightlines).  Cached once the sightlines are final."""
+        """Device-resident particles + candidate index of a segment (None when it has no particles near this rank's
+        sightlines).  Cached per (segment, element, ion) for the current sightline set (set_sightlines /
+        _set_my_sightlines drop the cache), so that further lines of the ion, its column density and its weighted
+        fields reuse the upload and the index.  Least-recently-used engines are released beyond ``max_engines``
+        (device memory of multi-segment snapshots stays bounded)."""
         key = (fn, elem, ion)
         if key in self._engines:
-            return self._engines[key]
+            eng = self._engines.pop(key)
+            self._engines[key] = eng  # most recently used last
+            return eng
         (pos, vel, elem_den, temp, hh, amumass) = self._read_particle_data(fn, elem, ion, True)
         eng = None
         if amumass is not False and np.size(self._my_axis) > 0:
             eng = _SegmentEngine(self, pos, vel, elem_den, temp, hh)
             eng.amumass = amumass
-        if self.cofm_final:
-            self._engines[key] = eng
+        self._engines[key] = eng
+        limit = getattr(self, "max_engines", 4)
+        while len(self._engines) > limit:
+            old_key = next(iter(self._engines))
+            old = self._engines.pop(old_key)
+            if old is not None:
+                old.release()
         return eng
 
     def _segments(self):
         """Segments this call loops over (the Voronoi kernel needs all particles at once:
         spectra.py:811-815)."""
         if self.kernel_int == 2:
-            return [None] if self.snapshot_set.get_n_segments(part_type=0) > 1 else [0]
+            # "all segments" is a negative segment number in the reference's snapshot API (abstractsnapshot.py:214,364)
+            return [-1] if self.snapshot_set.get_n_segments(part_type=0) > 1 else [0]
         return list(range(self.snapshot_set.get_n_segments(part_type=0)))
 
     def _interpolate_single_file(self, nsegment, elem, ion, ll, get_tau, load_all_data_first=False):
         """Read arrays and interpolate one segment through the drop-in boundary (spectra.py:501-548)."""
-        seg = None if load_all_data_first else nsegment
+        seg = -1 if load_all_data_first else nsegment
         (pos, vel, elem_den, temp, hh, amumass) = self._read_particle_data(seg, elem, ion, get_tau)
         if amumass is False:
             return np.zeros([np.shape(self._my_cofm)[0], self.nbins], dtype=np.float32)
@@ -767,6 +799,7 @@ class Spectra:
             if found >= wanted:
                 break
             self.set_sightlines(self.get_cofm(), self.axis)
+        self.discarded = int(self.discarded * 1. * wanted / max(found, 1))  # spectra.py:748
         self.set_sightlines(cofm_DLA, np.ones(ndla) if np.size(self.axis) < ndla else self.axis[:ndla])
         self.colden[(elem, ion)] = col_den_DLA
         self.cofm_final = True

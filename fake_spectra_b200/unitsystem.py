@@ -7,6 +7,8 @@ they enter results that the parity tests compare.
 """
 import math
 
+import numpy as np
+
 # cgs constants, as used by the reference
 _CONSTANTS = {
     "light": 2.99e10,             # cm/s
@@ -41,7 +43,7 @@ class UnitSystem:
 
     def hubble(self, z, omegam0):
         """H(z) in h/s for a flat universe with matter density omegam0."""
-        return self.h100 * math.sqrt(omegam0 * (1 + z) ** 3 + (1 - omegam0))
+        return self.h100 * np.sqrt(omegam0 * (1 + z) ** 3 + (1 - omegam0))
 
     def absorption_distance(self, speclen, red):
         """Absorption distance X of one sightline of comoving length speclen: (1+z)^2 H0 dL / c."""

@@ -31,7 +31,6 @@ def want(oracle):
 @pytest.mark.parametrize("nseg", [1, 3])
 def test_spectra_routes_match_oracle(want, resident, nseg):
     rs = rand(nseg, resident=resident)
-    rs.cofm_final = True
     for got, ref in ((rs.get_tau("H", 1, 1215), want["tau"]), (rs.get_col_density("H", 1), want["col"])):
         rel, same_zero = cases.rel_err(got, ref)
         assert same_zero and rel < 1e-10, rel
@@ -43,6 +42,32 @@ def test_spectra_routes_match_oracle(want, resident, nseg):
     assert np.allclose(rs.get_dens_weighted_density("H", 1), want["dwd"], rtol=1e-6)
     if resident:
         assert len(rs._engines) == nseg  # particles and index stayed in HBM across the calls
+
+
+def test_engine_cache_reuses_the_index(monkeypatch):
+    """Plain Spectra use (no replace_not_DLA): one upload and one candidate index per (segment, ion) serve every
+    quantity; changing the sightlines drops them; the LRU bound releases the oldest engine."""
+    from fake_spectra_b200 import native
+    built = []
+    orig = native.CandidateIndex.__init__
+
+    def counting(self, *a, **k):
+        built.append(1)
+        return orig(self, *a, **k)
+    monkeypatch.setattr(native.CandidateIndex, "__init__", counting)
+    rs = rand(2, resident=True)
+    rs.get_tau("H", 1, 1215)
+    n0 = len(built)
+    assert n0 == 2  # one per segment
+    rs.get_tau("H", 1, 1025), rs.get_col_density("H", 1), rs.get_temp("H", 1), rs.get_velocity("H", 1)
+    assert len(built) == n0
+    rs.set_sightlines(rs.cofm[:7], rs.axis[:7])
+    rs.get_tau("H", 1, 1215)
+    assert len(built) == 2 * n0
+    rs.max_engines = 1
+    rs.set_sightlines(rs.cofm, rs.axis)
+    rs.get_tau("H", 1, 1215)
+    assert len(rs._engines) == 1
 
 
 def test_gridded_all_axes_and_kernels(oracle):

@@ -137,6 +137,31 @@ def test_savefile_roundtrip(backend, tmp_path):
         spectra.Spectra(0, snap, None, None, savefile="missing.npz", savedir=str(tmp_path), quiet=True, backend=backend)
 
 
+def test_savefile_keeps_untouched_arrays(backend, tmp_path):
+    """Reopen a savefile, touch one array only, save again: the untouched arrays must survive (the first file becomes
+    the .backup, a second save overwrites that)."""
+    rs = make_rand(backend, savefile="spectra.npz", savedir=str(tmp_path))
+    tau, col = rs.get_tau("H", 1, 1215), rs.get_col_density("H", 1)
+    rs.save_file()
+    for _ in range(2):
+        back = spectra.Spectra(0, rs.snapshot_set, None, None, savefile="spectra.npz", savedir=str(tmp_path), res=None,
+                               quiet=True, backend=backend)
+        assert np.array_equal(back.get_col_density("H", 1), col)  # tau stays a lazy placeholder
+        back.save_file()
+    last = spectra.Spectra(0, rs.snapshot_set, None, None, savefile="spectra.npz", savedir=str(tmp_path), res=None, quiet=True,
+                           backend=backend)
+    assert np.array_equal(last.get_tau("H", 1, 1215), tau) and np.array_equal(last.get_col_density("H", 1), col)
+
+
+def test_unitsystem_hubble_takes_arrays():
+    from fake_spectra_b200 import unitsystem
+    u = unitsystem.UnitSystem()
+    z = np.array([0., 1., 3.])
+    h = u.hubble(z, 0.3) if u.hubble.__code__.co_argcount >= 3 else None
+    if h is not None:
+        assert h.shape == (3,) and np.all(np.diff(h) > 0)
+
+
 def test_balanced_blocks():
     from fake_spectra_b200 import sharding
     w = np.array([1, 1, 1, 1, 10, 1, 1, 1, 1, 10])
@@ -195,3 +220,14 @@ def test_two_rank_sharding_gloo(backend, tmp_path, mode):
             assert np.allclose(o["vel"], vel, rtol=1e-5, atol=1e-4)
             assert set(o["lines"]) == {13}            # every rank did all sightlines for its particles
     assert np.array_equal(outs[0]["tau"], outs[1]["tau"])
+
+
+def test_res_corr_is_the_reference_filter():
+    """spec_utils.res_corr == scipy.ndimage.gaussian_filter1d(mode='wrap') (what the reference calls, spec_utils.py:24),
+    also for sigma around one pixel where a continuous Gaussian would differ by tens of per cent."""
+    ndimage = pytest.importorskip("scipy.ndimage")
+    from fake_spectra_b200.spec_utils import res_corr
+    f = np.random.default_rng(0).random((4, 3, 160))
+    for fwhm, dv in ((8, 1.0), (8, 5.0), (2, 1.0), (30, 1.0)):
+        sig = (fwhm / dv) / (2 * np.sqrt(2 * np.log(2)))
+        assert np.allclose(res_corr(f, dv, fwhm), ndimage.gaussian_filter1d(f, sig, axis=-1, mode="wrap"), rtol=0, atol=1e-14)
