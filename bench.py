@@ -87,6 +87,8 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the colden / flux statistics / weak-replica legs")
     ap.add_argument("--ref-lines", type=int, default=0, help="sightlines of the reference sample (0 = choose)")
+    ap.add_argument("--reduce-blocks", type=int, default=4,
+                    help="particle-sharded workloads: sightline blocks whose NCCL sums overlap the next block's kernel (1 = one sum at the end)")
     ap.add_argument("--gather", default="push", choices=["push", "nccl"],
                     help="N > 1, sightline-sharded: how the rows reach every rank: stored into the peers' arrays from inside "
                          "the tau kernel (push), or gathered afterwards with NCCL (sharding.Sharder.combine)")
@@ -315,9 +317,24 @@ def run_b200(args):
             if marks:
                 marks[-1].record()
                 ev["ion"].append(marks)
-        timed("tau", all_tau, time_parts)
+        def all_tau_blocks():
+            # particle-sharded: sightline blocks; the FP64 sum of a finished block over the ranks (NCCL, its own stream)
+            # runs while the next block is computed
+            ion, lns = groups[0]
+            works = []
+            for (b0, b1) in sharder.reduce_blocks(L, args.reduce_blocks):
+                idx.compute_tau(params[ion], t["pos"], t["vel"], dens[ion], t["temp"], t["h"], out=out, lines=(b0, b1))
+                works.append(sharder.sum_block_async(out, b0, b1))
+            for wk in works:
+                if wk is not None:
+                    wk.wait()
+        blocked = pshard and world > 1 and counters is None and len(groups) == 1 and len(groups[0][1]) == 1 and args.reduce_blocks > 1
+        timed("tau", all_tau_blocks if blocked else all_tau, time_parts)
         state["npairs"], state["sl"] = idx.npairs, sl
         idx.free()
+        if blocked:
+            state["full"] = out
+            return out
         if use_push:
             # the rows are already in every rank's array: wait until every rank's kernels have finished
             timed("gather", state["peer"].barrier, time_parts)
@@ -512,8 +529,8 @@ def run_b200(args):
             "config": {"workload": args.workload, "particles": int(w["npart"]), "sightlines": int(L),
                        "precision": args.precision, "pixels": int(nbins), "pixel_kms": w["res"], "lines": list(w["lines"]),
                        "ion_passes": [[ion, lns] for ion, lns in groups], "sph_kernel": KERNEL_NAMES[w["kernel"]], "voigt": args.voigt,
-                       "parallelism": ("particle-sharded x%d (%d cells per rank, box grows with N), FP64 NCCL sum of the tau array each step"
-                                       % (world, w["npart"])) if pshard else
+                       "parallelism": ("particle-sharded x%d (%d cells per rank, box grows with N), FP64 NCCL sum of the tau array each step, "
+                                       "in %d sightline blocks overlapped with the kernel of the next block" % (world, w["npart"], args.reduce_blocks)) if pshard else
                                       ("sightline-sharded x%d through sharding.Sharder: pair-balanced contiguous blocks of ONE fixed "
                                        "sightline set, particles replicated, rows delivered to every rank (%s)" % (
                                            world, "stored into the peers' arrays over NVLink from inside the tau kernel" if args.gather == "push"

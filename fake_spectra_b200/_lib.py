@@ -54,6 +54,7 @@ SIGNATURES = {
     "fsb_compute_tau": (C.c_int, [_P, C.POINTER(Params), _P, _P, _P, _P, _P, _P, _P, _P]),
     "fsb_compute_tau_multi": (C.c_int, [_P, C.POINTER(Params), C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P]),
     "fsb_compute_tau_multi_push": (C.c_int, [_P, C.POINTER(Params), C.c_int32, _P, _P, _P, _P, _P, _P, C.POINTER(Push), _P]),
+    "fsb_compute_tau_multi_range": (C.c_int, [_P, C.POINTER(Params), C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, _P]),
     "fsb_peer_alloc": (C.c_int, [C.c_int64, C.POINTER(_P), _P]),
     "fsb_peer_free": (C.c_int, [_P]),
     "fsb_peer_open": (C.c_int, [_P, C.POINTER(_P)]),

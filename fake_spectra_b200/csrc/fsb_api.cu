@@ -84,6 +84,8 @@ static int make_consts(const fsb_index *idx, const fsb_params *p, int nlines, In
     c.boxtokpc = c.vbox / p->nbins / p->velfac;   // absorption.cpp:188
     c.voigt = p->voigt;
     c.seg_pairs = p->seg_pairs;
+    c.line0 = 0;
+    c.nrange = idx->nlos;
     return FSB_OK;
 }
 
@@ -137,7 +139,8 @@ namespace {
 // host[line][nlos][nbins]: streamed out while its kernel runs when the launch supports it, copied after it otherwise.
 int compute_tau_multi_impl(const fsb_index *idx, const fsb_params *p, int32_t nlines, const float *pos, const float *vel,
                            const float *dens, const float *temp, const float *h, double *tau, fsb_counters *counters,
-                           cudaStream_t stream, double *host, cudaStream_t copy_stream, const fsb_push *push = nullptr)
+                           cudaStream_t stream, double *host, cudaStream_t copy_stream, const fsb_push *push = nullptr,
+                           int32_t line_begin = 0, int32_t line_end = -1)
 {
     FSB_REQUIRE(nlines >= 1, "nlines must be >= 1");
     FSB_REQUIRE(idx != nullptr && p != nullptr, "NULL index or params");
@@ -156,6 +159,12 @@ int compute_tau_multi_impl(const fsb_index *idx, const fsb_params *p, int32_t nl
         InterpConsts c;
         FSB_TRY(make_consts(idx, &p[i0], n, c));
         for (int32_t k = 0; k < n; ++k) line_consts(p[i0 + k], c.line[k]);
+        if (line_end >= 0) {
+            FSB_REQUIRE(line_begin >= 0 && line_begin <= line_end && line_end <= idx->nlos, "sightline range outside the index");
+            c.line0 = line_begin;
+            c.nrange = line_end - line_begin;
+            if (c.nrange == 0) continue;
+        }
         const size_t off = (size_t) i0 * (size_t) idx->nlos * (size_t) c.nbins;
         HostSink sink;
         sink.host = host ? host + off : nullptr;
@@ -206,6 +215,20 @@ extern "C" int fsb_compute_tau_multi_push(const fsb_index *idx, const fsb_params
     }
     return compute_tau_multi_impl(idx, local, nlines, pos, vel, dens, temp, h, tau, nullptr, static_cast<cudaStream_t>(stream_v),
                                   nullptr, nullptr, push);
+}
+
+extern "C" int fsb_compute_tau_multi_range(const fsb_index *idx, const fsb_params *p, int32_t nlines, int32_t line_begin,
+                                           int32_t line_end, const float *pos, const float *vel, const float *dens,
+                                           const float *temp, const float *h, double *tau, void *stream_v)
+{
+    FSB_REQUIRE(nlines >= 1 && nlines <= kMaxFused && p != nullptr, "between 1 and 4 lines per call");
+    fsb_params local[kMaxFused];
+    for (int32_t i = 0; i < nlines; ++i) {
+        local[i] = p[i];
+        local[i].seg_pairs = 1 << 30;  // one work row per sightline
+    }
+    return compute_tau_multi_impl(idx, local, nlines, pos, vel, dens, temp, h, tau, nullptr, static_cast<cudaStream_t>(stream_v),
+                                  nullptr, nullptr, nullptr, line_begin, line_end);
 }
 
 extern "C" int fsb_peer_alloc(int64_t bytes, void **dev_ptr, unsigned char *handle64)

@@ -92,6 +92,7 @@ struct InterpConsts {
     LineConsts line[4];
     int32_t voigt;
     int32_t seg_pairs;
+    int32_t line0, nrange;  // sightlines [line0, line0 + nrange) of the index are processed (tau; default: all)
 };
 
 constexpr int kMaxFused = 4;

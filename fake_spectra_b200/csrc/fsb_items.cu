@@ -73,10 +73,10 @@ int plan_items(const fsb_index *idx, int seg_pairs_req, int nbins, int nrows_per
 namespace {
 
 // hist[r] = number of lines with exactly r runs (r = 0 .. max_runs)
-__global__ void k_runs_hist(const int64_t *__restrict__ offsets, int nlos, int ticket, int32_t *__restrict__ hist)
+__global__ void k_runs_hist(const int64_t *__restrict__ offsets, int line0, int nrange, int ticket, int32_t *__restrict__ hist)
 {
-    const int l = blockIdx.x * blockDim.x + threadIdx.x;
-    if (l >= nlos) return;
+    const int l = line0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= line0 + nrange) return;
     const int64_t n = offsets[l + 1] - offsets[l];
     atomicAdd(&hist[(int) ((n + ticket - 1) / ticket)], 1);
 }
@@ -100,11 +100,11 @@ __global__ void k_runs_plan(const int32_t *__restrict__ hist, int max_runs, int3
     bin_start[0] = slot;
 }
 
-__global__ void k_runs_order(const int64_t *__restrict__ offsets, int nlos, int ticket, int32_t *__restrict__ bin_start,
+__global__ void k_runs_order(const int64_t *__restrict__ offsets, int line0, int nrange, int ticket, int32_t *__restrict__ bin_start,
                              int32_t *__restrict__ order)
 {
-    const int l = blockIdx.x * blockDim.x + threadIdx.x;
-    if (l >= nlos) return;
+    const int l = line0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= line0 + nrange) return;
     const int64_t n = offsets[l + 1] - offsets[l];
     const int r = (int) ((n + ticket - 1) / ticket);
     order[atomicAdd(&bin_start[r], 1)] = l;  // any order inside a bin: every line's own additions stay sequential
@@ -113,10 +113,10 @@ __global__ void k_runs_order(const int64_t *__restrict__ offsets, int nlos, int 
 }  // namespace
 
 // Ticketed runs (fsb_items.cuh): builds the dispatch order on the device, no host synchronisation.
-int plan_tickets(const fsb_index *idx, int ticket, cudaStream_t stream, ItemPlan &plan)
+int plan_tickets(const fsb_index *idx, int ticket, int line0, int nrange, cudaStream_t stream, ItemPlan &plan)
 {
-    const int64_t max_runs = (idx->max_list + ticket - 1) / ticket;
-    if (max_runs < 2 || max_runs > (1 << 20) || max_runs * (int64_t) idx->nlos > (int64_t) INT32_MAX) return FSB_OK;  // whole lists
+    const int64_t max_runs = (idx->max_list + ticket - 1) / ticket;  // of the whole index: an upper bound for the range
+    if (max_runs < 2 || max_runs > (1 << 20) || max_runs * (int64_t) nrange > (int64_t) INT32_MAX || nrange <= 0) return FSB_OK;  // whole lists
     const int nlos = idx->nlos;
     FSB_TRY(plan.line_done.alloc(sizeof(int32_t) * (size_t) nlos, stream));
     FSB_TRY(plan.phase_start.alloc(sizeof(int32_t) * (size_t) (max_runs + 1), stream));
@@ -126,17 +126,17 @@ int plan_tickets(const fsb_index *idx, int ticket, cudaStream_t stream, ItemPlan
     FSB_TRY(bin_start.alloc(sizeof(int32_t) * (size_t) (max_runs + 1), stream));
     FSB_CUDA_TRY(cudaMemsetAsync(plan.line_done.ptr, 0, sizeof(int32_t) * (size_t) nlos, stream));
     FSB_CUDA_TRY(cudaMemsetAsync(hist.ptr, 0, sizeof(int32_t) * (size_t) (max_runs + 1), stream));
-    const int blocks = (nlos + 255) / 256;
-    count_launch(); k_runs_hist<<<blocks, 256, 0, stream>>>(idx->offsets, nlos, ticket, hist.as<int32_t>());
+    const int blocks = (nrange + 255) / 256;
+    count_launch(); k_runs_hist<<<blocks, 256, 0, stream>>>(idx->offsets, line0, nrange, ticket, hist.as<int32_t>());
     count_launch(); k_runs_plan<<<1, 32, 0, stream>>>(hist.as<int32_t>(), (int) max_runs, plan.phase_start.as<int32_t>(), bin_start.as<int32_t>());
-    count_launch(); k_runs_order<<<blocks, 256, 0, stream>>>(idx->offsets, nlos, ticket, bin_start.as<int32_t>(), plan.order.as<int32_t>());
+    count_launch(); k_runs_order<<<blocks, 256, 0, stream>>>(idx->offsets, line0, nrange, ticket, bin_start.as<int32_t>(), plan.order.as<int32_t>());
     FSB_CUDA_TRY(cudaGetLastError());
     plan.items.ticket_pairs = ticket;
     plan.items.max_runs = (int32_t) max_runs;
     plan.items.line_done = plan.line_done.as<int32_t>();
     plan.items.phase_start = plan.phase_start.as<int32_t>();
     plan.items.order = plan.order.as<int32_t>();
-    plan.n_items = max_runs * (int64_t) nlos;  // upper bound; the kernel stops at phase_start[max_runs]
+    plan.n_items = max_runs * (int64_t) nrange;  // upper bound; the kernel stops at phase_start[max_runs]
     return FSB_OK;
 }
 

@@ -140,7 +140,7 @@ struct ItemPlan {
 int plan_items(const fsb_index *idx, int seg_pairs_req, int nbins, int nrows_per_item, cudaStream_t stream, ItemPlan &plan);
 
 // Switches an unsegmented plan to ticketed runs of `ticket` candidates (a multiple of the kernels' particle batch).
-int plan_tickets(const fsb_index *idx, int ticket, cudaStream_t stream, ItemPlan &plan);
+int plan_tickets(const fsb_index *idx, int ticket, int line0, int nrange, cudaStream_t stream, ItemPlan &plan);
 
 // out[w][line][j] += sum over the line's items (in list order) of scratch[w][item][j]
 int reduce_items(const ItemPlan &plan, const fsb_index *idx, int nbins, int nrows_per_item, double *out, cudaStream_t stream);

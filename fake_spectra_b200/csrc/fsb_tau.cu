@@ -1062,7 +1062,7 @@ k_tau(InterpConsts C, Items items, int n_items, int *__restrict__ next_item, con
     };
     if (STREAM && items.item_start == nullptr && items.ticket_pairs > 0) {
         // ticketed runs only list sightlines that have candidates: the empty ones are finished here, spread over the warps
-        for (int l = blockIdx.x * kTauWarps + warp; l < C.nlos; l += gridDim.x * kTauWarps)
+        for (int l = C.line0 + blockIdx.x * kTauWarps + warp; l < C.line0 + C.nrange; l += gridDim.x * kTauWarps)
             if (offsets[l + 1] == offsets[l]) row_done(l);
     }
     for (;;) {
@@ -1103,8 +1103,16 @@ k_tau(InterpConsts C, Items items, int n_items, int *__restrict__ next_item, con
                 __syncwarp();
                 __threadfence();
             }
+        } else if (items.item_start == nullptr) {  // one item per sightline of the range
+            if (item >= C.nrange) continue;
+            line = C.line0 + item;
+            kbeg = offsets[line];
+            kend = offsets[line + 1];
+            if (kend <= kbeg) {
+                if (STREAM) row_done(line);
+                continue;
+            }
         } else if (!locate_item(items, offsets, C.nlos, item, line, kbeg, kend)) {
-            if (STREAM && item < C.nlos) row_done(item);
             continue;
         }
         double *row0 = items.item_start ? scratch + (int64_t) item * nbins : out + (int64_t) line * nbins;
@@ -1278,7 +1286,8 @@ int launch_tau(const fsb_index *idx, const InterpConsts &c, const float *pos, co
     if (!plan.segmented) {
         int64_t ticket = 256;
         if (const char *env = getenv("FSB200_TICKET_PAIRS")) ticket = std::max(0ll, atoll(env)) / 32 * 32;  // tuning hook; 0 = whole lists
-        if (ticket > 0 && idx->max_list > ticket) FSB_TRY(plan_tickets(idx, (int) ticket, stream, plan));
+        if (ticket > 0 && idx->max_list > ticket) FSB_TRY(plan_tickets(idx, (int) ticket, c.line0, c.nrange, stream, plan));
+        if (plan.items.ticket_pairs == 0) plan.n_items = c.nrange;
     }
     Scratch next_item;
     FSB_TRY(next_item.alloc(sizeof(int), stream));
@@ -1293,7 +1302,7 @@ int launch_tau(const fsb_index *idx, const InterpConsts &c, const float *pos, co
     }
     const int chunk_lines = (int) std::min<size_t>((size_t) idx->nlos, std::max<size_t>(min_lines, chunk_bytes / row_bytes));
     const int nchunks = (idx->nlos + chunk_lines - 1) / chunk_lines;
-    const bool stream_out = sink && sink->host && !ctr && !plan.segmented && nchunks >= 4;
+    const bool stream_out = sink && sink->host && !ctr && !plan.segmented && nchunks >= 4 && c.nrange == idx->nlos;
     Scratch chunk_done;
     PinnedFlags flags;
     if (stream_out) {
@@ -1302,6 +1311,10 @@ int launch_tau(const fsb_index *idx, const InterpConsts &c, const float *pos, co
         FSB_TRY(flags.alloc((size_t) nchunks));
     }
     int *cd = stream_out ? chunk_done.as<int>() : nullptr;
+    if (c.nrange != idx->nlos && plan.segmented) {
+        set_error("launch_tau: a sightline range needs one work row per sightline");
+        return FSB_EINVAL;
+    }
     if (push.npeers > 0 && (plan.segmented || ctr || (sink && sink->host))) {
         set_error("launch_tau: pushing rows to peers needs one work row per sightline, no counters and no host sink");
         return FSB_EINVAL;

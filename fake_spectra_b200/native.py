@@ -76,11 +76,12 @@ class CandidateIndex:
             pass
 
     # -- accumulation --------------------------------------------------------------------------
-    def compute_tau(self, params, pos, vel, dens, temp, h, out=None, counters=None, push=None):
+    def compute_tau(self, params, pos, vel, dens, temp, h, out=None, counters=None, push=None, lines=None):
         """params: one _lib.Params or a list of them (fused lines of one ion).
         Returns float64 [nlos, nbins] (or [nlines, nlos, nbins]); accumulates into ``out`` if given.
         push: a _lib.Push (see PeerRows.push_spec): finished rows are also stored into the listed full arrays
-        (this rank's and its peers') from inside the kernel."""
+        (this rank's and its peers') from inside the kernel.
+        lines: (begin, end): only these sightlines of the index are processed (rows outside stay untouched)."""
         plist = params if isinstance(params, (list, tuple)) else [params]
         nbins = plist[0].nbins
         shape = (len(plist), self.nlos, nbins)
@@ -88,7 +89,12 @@ class CandidateIndex:
             out = torch.zeros(shape, dtype=torch.float64, device=self.device)
         arr = (_lib.Params * len(plist))(*plist)
         with torch.cuda.device(self.device):
-            if push is not None:
+            if lines is not None:
+                if counters is not None or push is not None:
+                    raise ValueError("a sightline range excludes counters and push")
+                rc = self.lib.fsb_compute_tau_multi_range(self.handle, arr, len(plist), int(lines[0]), int(lines[1]), _dptr(pos),
+                                                          _dptr(vel), _dptr(dens), _dptr(temp), _dptr(h), _dptr(out), _stream())
+            elif push is not None:
                 if counters is not None:
                     raise ValueError("counters and push are exclusive")
                 rc = self.lib.fsb_compute_tau_multi_push(self.handle, arr, len(plist), _dptr(pos), _dptr(vel), _dptr(dens),

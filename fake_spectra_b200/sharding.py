@@ -81,6 +81,23 @@ class Sharder:
         e = even_blocks(npart, self.size)
         return slice(int(e[self.rank]), int(e[self.rank + 1]))
 
+    def reduce_blocks(self, numlos, nblocks=4):
+        """Particle-sharded mode: sightline blocks [(begin, end), ...] for computing and summing block by block: the
+        all-reduce of one block's rows runs while the next block is being computed ("issued as blocks
+        complete")."""
+        e = even_blocks(numlos, max(1, min(int(nblocks), max(numlos, 1))))
+        return [(int(e[i]), int(e[i + 1])) for i in range(len(e) - 1) if e[i + 1] > e[i]]
+
+    def sum_block_async(self, full, begin, end):
+        """Starts the FP64 sum over the ranks of rows [begin, end) of ``full`` ([K, numlos, ...] or [numlos, ...], K == 1
+        for an in-place contiguous block) on the collective's own stream; returns a handle to wait() on."""
+        if self.size == 1:
+            return None
+        blk = full[:, begin:end] if full.dim() == 3 else full[begin:end]
+        if not blk.is_contiguous():
+            raise ValueError("block sums need one line per array (rows of a block must be contiguous)")
+        return dist.all_reduce(blk, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
     # -- recombination -------------------------------------------------------------------------------
     def combine(self, local, numlos, dim=0):
         """local: this rank's result (torch tensor, any device); dimension ``dim`` (0 or 1) runs over its

@@ -128,6 +128,14 @@ FSB_API int fsb_compute_tau(const fsb_index *idx, const fsb_params *p, const flo
 FSB_API int fsb_compute_tau_multi(const fsb_index *idx, const fsb_params *p, int32_t nlines, const float *pos,
                           const float *vel, const float *dens, const float *temp, const float *h,
                           double *tau, fsb_counters *counters, void *stream);
+/* fsb_compute_tau_multi restricted to the sightlines [line_begin, line_end) of the index; tau is still the full
+ * [nlines][nlos*nbins] array (only the rows of the range are touched).  Lets a caller overlap a collective on the
+ * finished rows of one block with the computation of the next (particle-sharded mode: spectra.py:825-831 sums the
+ * whole array after the fact).  One work row per sightline. */
+FSB_API int fsb_compute_tau_multi_range(const fsb_index *idx, const fsb_params *p, int32_t nlines, int32_t line_begin,
+                                int32_t line_end, const float *pos, const float *vel, const float *dens,
+                                const float *temp, const float *h, double *tau, void *stream);
+
 /* ---- sightline-sharded multi-GPU: rows pushed to the peers while the kernel runs -------------------------
  * One process per GPU, every rank interpolates a block of the sightlines (no reference counterpart: the reference
  * shards particles and Allreduces, spectra.py:825-831).  Every rank owns a FULL result array [nlines_total][numlos]

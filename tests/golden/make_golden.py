@@ -115,6 +115,42 @@ def voronoi_case(ref):
     np.savez_compressed(os.path.join(HERE, "case_voronoi8.npz"), **z)
 
 
+def lattice_case():
+    """Cells on a regular lattice, sightlines through points equidistant from 4, 2 and 1 cell columns, on all three
+    axes: at every march point of assign_cells several candidates are at EXACTLY the same distance, and the reference
+    gives the point to the first of them (strict <, index_table.cpp:181-190).  All coordinates are exactly
+    representable, so the distances tie bit for bit."""
+    box, n, a = 64.0, 4, 16.0
+    g = (np.arange(n) + 0.5) * a
+    pos = np.array([[x, y, z] for x in g for y in g for z in g], dtype=np.float32)
+    npart = pos.shape[0]
+    rng = np.random.default_rng(21)
+    perp = [(16.0, 16.0), (16.0, 24.0), (24.0, 24.0), (32.0, 48.0), (8.0, 40.0), (17.5, 30.25)]
+    cofm, axis = [], []
+    for ax in (1, 2, 3):
+        for (u, v) in perp:
+            c = [0.0, 0.0, 0.0]
+            others = [i for i in range(3) if i != ax - 1]
+            c[others[0]], c[others[1]] = u, v
+            cofm.append(c)
+            axis.append(ax)
+    return {"box": box, "cofm": np.array(cofm, dtype=np.float64), "axis": np.array(axis, dtype=np.int32), "pos": pos,
+            "h": np.full(npart, 14.0, dtype=np.float32),
+            "vel": (30 * rng.standard_normal((npart, 3))).astype(np.float32),
+            "dens": (1e11 * (1 + rng.random(npart))).astype(np.float32),
+            "temp": (1e4 * (0.5 + rng.random(npart))).astype(np.float32)}
+
+
+def voronoi_lattice_case(ref):
+    d = lattice_case()
+    run_case(ref, d, "case_voronoi_lattice.npz", VORONOI_CONFIGS)
+    z = dict(np.load(os.path.join(HERE, "case_voronoi_lattice.npz")))
+    for line in range(d["cofm"].shape[0]):
+        _, arr = ref.assign_cells(d["cofm"], d["axis"], d["box"], line, d["pos"], d["h"])
+        z["cells_%d" % line] = arr
+    np.savez_compressed(os.path.join(HERE, "case_voronoi_lattice.npz"), **z)
+
+
 def main():
     ref = Reference()
     faddeeva_table()
@@ -123,6 +159,7 @@ def main():
     run_case(ref, cases.grid_case(), "case_grid12.npz", GRID12_CONFIGS)
     run_case(ref, cases.edge_case(), "case_edge.npz", EDGE_CONFIGS)
     voronoi_case(ref)
+    voronoi_lattice_case(ref)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print("%-24s %8d bytes" % (f, os.path.getsize(os.path.join(HERE, f))))

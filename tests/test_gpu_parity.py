@@ -81,9 +81,12 @@ def test_tau_colden_golden(priv, golden_dir, name, configs, voigt):
             assert same_zero and rel < TOL, (name, tag, "colden", rel)
 
 
-def test_voronoi_golden(torch_cuda, priv, golden_dir):
+@pytest.mark.parametrize("fixture", ["case_voronoi8.npz", "case_voronoi_lattice.npz"])
+def test_voronoi_golden(torch_cuda, priv, golden_dir, fixture):
+    """case_voronoi_lattice: cells on a lattice and sightlines equidistant from 4 / 2 / 1 cell columns: every march point
+    of assign_cells is an exact tie that the first candidate must win (index_table.cpp:181-190)."""
     from fake_spectra_b200 import native
-    d = load(golden_dir, "case_voronoi8.npz")
+    d = load(golden_dir, fixture)
     t = dev(torch_cuda, d)
     idx = native.CandidateIndex(d["box"], t["cofm"], t["axis"], t["pos"], t["h"])
     cells = idx.assign_cells(t["cofm"], t["axis"], t["pos"]).cpu().numpy()
@@ -434,3 +437,21 @@ def test_list_longer_than_the_in_kernel_sort(torch_cuda, priv, oracle):
     want = oracle.compute_colden(**p, pos=d["pos"], dens=d["dens"], h=d["h"], axis=d["axis"], cofm=d["cofm"])
     rel, same_zero = cases.rel_err(interp(priv, 0, p, d), want)
     assert same_zero and rel < TOL, rel
+
+
+def test_sightline_ranges_equal_one_pass(torch_cuda):
+    """fsb_compute_tau_multi_range: the index's sightlines processed block by block give, bit for bit, the rows of one
+    pass over all of them (one work row per sightline in both), and rows outside a block stay untouched."""
+    from fake_spectra_b200 import _lib, native
+    d = cases.random_case(nside=16, nlos=90, axis="cycle", seed=5, los_seed=6)
+    t = dev(torch_cuda, d)
+    idx = native.CandidateIndex(d["box"], t["cofm"], t["axis"], t["pos"], t["h"])
+    prm = [_lib.make_params(**cases.params(d, line=ln), seg_pairs=1 << 30) for ln in ("HI1215", "HI1025")]
+    whole = idx.compute_tau(prm, t["pos"], t["vel"], t["dens"], t["temp"], t["h"])
+    parts = torch_cuda.zeros_like(whole)
+    for b0, b1 in ((0, 17), (17, 17), (17, 64), (64, 90)):
+        before = parts.clone()
+        idx.compute_tau(prm, t["pos"], t["vel"], t["dens"], t["temp"], t["h"], out=parts, lines=(b0, b1))
+        assert torch_cuda.equal(parts[:, :b0], before[:, :b0]) and torch_cuda.equal(parts[:, b1:], before[:, b1:])
+    assert torch_cuda.equal(parts, whole)
+    assert float(whole.mean()) > 0

@@ -14,7 +14,8 @@ import cases  # noqa: E402
 from golden import make_golden as mg  # noqa: E402
 
 FIXTURES = [("case_random16.npz", mg.RANDOM16_CONFIGS), ("case_grid12.npz", mg.GRID12_CONFIGS),
-            ("case_edge.npz", mg.EDGE_CONFIGS), ("case_voronoi8.npz", mg.VORONOI_CONFIGS)]
+            ("case_edge.npz", mg.EDGE_CONFIGS), ("case_voronoi8.npz", mg.VORONOI_CONFIGS),
+            ("case_voronoi_lattice.npz", mg.VORONOI_CONFIGS)]
 
 
 def load(golden_dir, name):
@@ -48,8 +49,9 @@ def test_tau_colden(oracle, golden_dir, name, configs):
         assert same_zero and rel < 1e-12, (name, tag, rel)
 
 
-def test_voronoi_cells(oracle, golden_dir):
-    d = load(golden_dir, "case_voronoi8.npz")
+@pytest.mark.parametrize("fixture", ["case_voronoi8.npz", "case_voronoi_lattice.npz"])
+def test_voronoi_cells(oracle, golden_dir, fixture):
+    d = load(golden_dir, fixture)
     for line in range(d["cofm"].shape[0]):
         err, arr = oracle.assign_cells(d["cofm"], d["axis"], d["box"], line, d["pos"], d["h"])
         assert err == 0
