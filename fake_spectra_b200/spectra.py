@@ -534,20 +534,26 @@ class Spectra:
         if self.resident:
             import torch
             acc = torch.zeros((nl, nlocal, self.nbins), dtype=torch.float64, device="cuda")
-            engines = [e for e in (self._engine(seg, elem, ion) for seg in self._segments()) if e is not None]
             # sightline-sharded optical depths on several GPUs: the kernel of the LAST segment stores every finished row
             # (all segments summed) into every rank's full array over NVLink; no gather afterwards (native.PeerRows)
             peer = self._peer_rows(nl) if (get_tau and self.kernel_int != 2 and self._push_rows()) else None
-            for n, eng in enumerate(engines):
+            segs = self._segments()
+            pushed = False
+            for n, seg in enumerate(segs):
+                eng = self._engine(seg, elem, ion)  # used at once: a later _engine call may release it (LRU bound)
+                if eng is None:
+                    continue
                 if get_tau:
-                    push = peer.push_spec(0, self._my_slice.start) if (peer is not None and n == len(engines) - 1) else None
+                    push = peer.push_spec(0, self._my_slice.start) if (peer is not None and n == len(segs) - 1) else None
                     eng.tau([self._params(self._line(elem, ion, ll), eng.amumass, unsegmented=peer is not None) for ll in lls],
                             out=acc, push=push)
+                    pushed = pushed or push is not None
                 else:
                     acc += eng.colden(self._params(self.lines[("H", 1)][1215], eng.amumass))
             if peer is not None:
-                if not engines:  # no particle of the snapshot reaches this rank's sightlines: its rows are zero
-                    peer.zero_block(self._my_slice.start, nlocal)
+                if not pushed:  # the last segment has no particle near this rank's sightlines: plain copies to every array
+                    for v in peer.views:
+                        v[:, self._my_slice.start:self._my_slice.start + nlocal] = acc
                 torch.cuda.synchronize()
                 peer.barrier()
                 return peer.full.cpu().numpy()
