@@ -24,6 +24,21 @@ class Params(C.Structure):
                 ("seg_pairs", C.c_int32), ("reserved", C.c_int32)]
 
 
+class Prep(C.Structure):
+    """struct fsb_prep."""
+    _fields_ = [(n, C.c_float) for n in ("dens_conv", "rscale", "unit_ienergy", "temp_factor", "hy_mass",
+                                         "nelec_const", "mass_frac_const", "amumass", "dens_thresh_code")] + \
+               [(n, C.c_int32) for n in ("reserved", "neutral_hydrogen", "sf_neutral", "redshift_coverage")] + \
+               [(n, C.c_double) for n in ("gray_opac", "gamma_uvb", "f_bar", "sqrt_atime")]
+
+
+class IonTable(C.Structure):
+    """struct fsb_ion_table."""
+    _fields_ = [("coef", C.c_void_p)] + [(n, C.c_int32) for n in ("nd", "nt", "pad", "reserved")] + \
+               [(n, C.c_double) for n in ("dens0", "dens_span", "temp0", "temp_span")] + \
+               [(n, C.c_float) for n in ("dens_lo", "dens_hi", "temp_lo", "temp_hi", "rho_factor", "reserved2")]
+
+
 MAX_PEERS = 16
 
 
@@ -73,6 +88,10 @@ SIGNATURES = {
     "fsb_assign_cells": (C.c_int, [_P, C.c_double, _P, _P, _P, _P, _P]),
     "fsb_measure_fma_peak": (C.c_int, [C.c_int32, C.POINTER(C.c_double), _P]),
     "fsb_voigt_profile": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, _P]),
+    "fsb_prepare_particles": (C.c_int, [C.POINTER(Prep), _P, C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int64,
+                                        C.POINTER(IonTable), _P, _P, _P, _P, _P, _P]),
+    "fsb_smoothing_lengths": (C.c_int, [_P, _P, C.c_int64, C.c_int32, _P, _P]),
+    "fsb_prepare_select": (C.c_int, [C.POINTER(Prep), _P, C.c_int64, _P, _P, C.c_int64, _P, C.POINTER(C.c_int64), _P]),
     "fsb_rescale_mean_flux": (C.c_int, [_P, C.c_int64, C.c_double, C.c_double, C.c_double, C.POINTER(C.c_double),
                                         C.POINTER(C.c_int32), _P]),
     "fsb_flux_sums": (C.c_int, [_P, C.c_int64, C.c_double, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double),

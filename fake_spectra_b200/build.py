@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfsb200.so")
-SOURCES = ["fsb_api.cu", "fsb_index.cu", "fsb_items.cu", "fsb_tau.cu", "fsb_colden.cu", "fsb_voronoi.cu", "fsb_stats.cu", "fsb_microbench.cu"]
+SOURCES = ["fsb_api.cu", "fsb_index.cu", "fsb_items.cu", "fsb_tau.cu", "fsb_colden.cu", "fsb_voronoi.cu", "fsb_stats.cu", "fsb_prep.cu", "fsb_microbench.cu"]
 HEADERS = ["fsb_common.cuh", "fsb_scan.cuh", "fsb_voigt.cuh", "fsb_voigt_tables.h", "fsb_items.cuh"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

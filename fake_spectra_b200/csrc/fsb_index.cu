@@ -402,39 +402,6 @@ __global__ void k_dr2_of_list(const int32_t *__restrict__ particle, double *__re
     if (i < n) dr2[i] = pair_dr2(pos, particle[i], cofm, line, axis[line], box);
 }
 
-// Flag compaction for near_lines: per-block popcounts, then ordered scatter.
-__global__ void __launch_bounds__(1024) k_flag_block_counts(const uint8_t *__restrict__ flag, int64_t npart,
-                                                            int32_t *__restrict__ block_count)
-{
-    __shared__ int warp_cnt[32];
-    const int64_t p = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
-    const bool f = p < npart && flag[p];
-    const unsigned b = __ballot_sync(0xffffffffu, f);
-    if ((threadIdx.x & 31) == 0) warp_cnt[threadIdx.x >> 5] = __popc(b);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int t = 0;
-        for (int w = 0; w < 32; ++w) t += warp_cnt[w];
-        block_count[blockIdx.x] = t;
-    }
-}
-
-__global__ void __launch_bounds__(1024) k_flag_compact(const uint8_t *__restrict__ flag, int64_t npart,
-                                                       const int64_t *__restrict__ block_start,
-                                                       int32_t *__restrict__ out)
-{
-    __shared__ int warp_cnt[32];
-    const int64_t p = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
-    const bool f = p < npart && flag[p];
-    const unsigned b = __ballot_sync(0xffffffffu, f);
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (lane == 0) warp_cnt[wid] = __popc(b);
-    __syncthreads();
-    int before = 0;
-    for (int w = 0; w < wid; ++w) before += warp_cnt[w];
-    if (f) out[block_start[blockIdx.x] + before + __popc(b & ((1u << lane) - 1u))] = (int32_t) p;
-}
-
 struct BuiltTable {
     Scratch cell_start, line_id, key, proj2, bad_axis;
     LineTable T;
@@ -673,7 +640,7 @@ extern "C" int fsb_near_lines(double box, const float *pos, const float *h, int6
     count_launch(); k_pairs<2><<<(unsigned) ((npart + 255) / 256), 256, 0, stream>>>(bt.T, pos, h, npart, nullptr, nullptr, nullptr, flag.as<uint8_t>());
     count_launch(); k_flag_block_counts<<<(unsigned) nblocks, threads, 0, stream>>>(flag.as<uint8_t>(), npart, block_count.as<int32_t>());
     count_launch(); k_scan_single<int32_t, int64_t><<<1, 1024, 0, stream>>>(block_count.as<int32_t>(), block_start.as<int64_t>(), nblocks, nullptr);
-    count_launch(); k_flag_compact<<<(unsigned) nblocks, threads, 0, stream>>>(flag.as<uint8_t>(), npart, block_start.as<int64_t>(), out_index);
+    count_launch(); k_flag_compact<<<(unsigned) nblocks, threads, 0, stream>>>(flag.as<uint8_t>(), npart, block_start.as<int64_t>(), nullptr, out_index);
     FSB_CUDA_TRY(cudaGetLastError());
     int32_t h_bad[2] = {0, 0};
     FSB_CUDA_TRY(cudaMemcpyAsync(h_bad, bt.bad_axis.ptr, sizeof(h_bad), cudaMemcpyDeviceToHost, stream));

@@ -64,4 +64,38 @@ __global__ void k_scan_single(const TIn *__restrict__ in, TOut *__restrict__ out
     }
 }
 
+// Ordered flag compaction (near_lines, particle selection): per-block popcounts, single-CTA scan of the block counts,
+// then an ordered scatter of the flagged positions (or of map[position]).
+static __global__ void __launch_bounds__(1024) k_flag_block_counts(const uint8_t *__restrict__ flag, int64_t npart,
+                                                            int32_t *__restrict__ block_count)
+{
+    __shared__ int warp_cnt[32];
+    const int64_t p = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    const bool f = p < npart && flag[p];
+    const unsigned b = __ballot_sync(0xffffffffu, f);
+    if ((threadIdx.x & 31) == 0) warp_cnt[threadIdx.x >> 5] = __popc(b);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < 32; ++w) t += warp_cnt[w];
+        block_count[blockIdx.x] = t;
+    }
+}
+
+static __global__ void __launch_bounds__(1024) k_flag_compact(const uint8_t *__restrict__ flag, int64_t npart,
+                                                       const int64_t *__restrict__ block_start,
+                                                       const int32_t *__restrict__ map, int32_t *__restrict__ out)
+{
+    __shared__ int warp_cnt[32];
+    const int64_t p = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    const bool f = p < npart && flag[p];
+    const unsigned b = __ballot_sync(0xffffffffu, f);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) warp_cnt[wid] = __popc(b);
+    __syncthreads();
+    int before = 0;
+    for (int w = 0; w < wid; ++w) before += warp_cnt[w];
+    if (f) out[block_start[blockIdx.x] + before + __popc(b & ((1u << lane) - 1u))] = map ? map[p] : (int32_t) p;
+}
+
 }  // namespace fsb

@@ -245,6 +245,62 @@ def count_pairs(box, pos, h, axis, cofm):
     return counts[:cofm.shape[0]]
 
 
+def prepare_particles(cfg, index, position, velocity, density, ienergy, nelec, nh0, smoothing, mass_frac=None,
+                      want_vel=True, want_temp=True, ion_table=None):
+    """Snapshot fields of one segment (CUDA float32 tensors) -> (pos, vel, elem_den, temp, hh) of the particles in
+    ``index`` (int32 CUDA tensor, or None for all): fsb_prepare_particles.  ``smoothing``: support radii of all
+    particles (smoothing_lengths); ``mass_frac``: a 1-D view of one column of
+    the metal table (any stride) or None; ``ion_table``: an ``_lib.IonTable`` (metal ions) or None."""
+    lib = _lib.load()
+    dev = position.device
+    m = int(index.shape[0]) if index is not None else int(position.shape[0])
+    f32 = dict(dtype=torch.float32, device=dev)
+    pos, hh, elem_den = torch.empty((m, 3), **f32), torch.empty(m, **f32), torch.empty(m, **f32)
+    vel = torch.empty((m, 3), **f32) if want_vel else None
+    temp = torch.empty(m, **f32) if want_temp else None
+    stride = _mass_frac_stride(mass_frac)
+    with torch.cuda.device(dev):
+        rc = lib.fsb_prepare_particles(C.byref(cfg), _dptr(index), m, _dptr(position), _dptr(velocity), _dptr(density),
+                                       _dptr(ienergy), _dptr(nelec), _dptr(nh0), _dptr(smoothing), _dptr(mass_frac), stride,
+                                       C.byref(ion_table) if ion_table is not None else None,
+                                       _dptr(pos), _dptr(vel), _dptr(elem_den), _dptr(temp), _dptr(hh), _stream())
+    _lib.check(rc, "fsb_prepare_particles")
+    return pos, vel, elem_den, temp, hh
+
+
+def smoothing_lengths(a, b=None, mode=0):
+    """Kernel support radii from SmoothingLength (mode 0), Volume (1) or Masses / Density (2): fsb_smoothing_lengths."""
+    lib = _lib.load()
+    hh = torch.empty_like(a)
+    with torch.cuda.device(a.device):
+        rc = lib.fsb_smoothing_lengths(_dptr(a), _dptr(b), int(a.shape[0]), int(mode), _dptr(hh), _stream())
+    _lib.check(rc, "fsb_smoothing_lengths")
+    return hh
+
+
+def _mass_frac_stride(mass_frac):
+    if mass_frac is None:
+        return 0
+    if mass_frac.dtype != torch.float32 or mass_frac.dim() != 1:
+        raise TypeError("mass_frac must be a 1-D float32 view")
+    return int(mass_frac.stride(0))
+
+
+def select_particles(cfg, index, density, mass_frac=None):
+    """The entries of ``index`` (int32 CUDA tensor; None = all particles) with mass in the element, in order:
+    fsb_prepare_select (the reference's _filter_particles, spectra.py:600)."""
+    lib = _lib.load()
+    dev = density.device
+    m = int(index.shape[0]) if index is not None else int(density.shape[0])
+    out = torch.empty(m, dtype=torch.int32, device=dev)
+    count = C.c_int64(0)
+    with torch.cuda.device(dev):
+        rc = lib.fsb_prepare_select(C.byref(cfg), _dptr(index), m, _dptr(density), _dptr(mass_frac), _mass_frac_stride(mass_frac),
+                                    _dptr(out), C.byref(count), _stream())
+    _lib.check(rc, "fsb_prepare_select")
+    return out[:count.value]
+
+
 def voigt_profile(x, y, voigt=_lib.VOIGT_FAST):
     """Re w(x + i y) on the device (test hook)."""
     lib = _lib.load()

@@ -22,6 +22,7 @@ import numpy as np
 
 from . import _spectra_priv
 from . import abstractsnapshot as absn
+from . import cloudy
 from . import gas_properties
 from . import line_data
 from . import sharding
@@ -41,7 +42,8 @@ class _SegmentEngine:
         self.torch, self.native = torch, native
         dev = torch.device("cuda", torch.cuda.current_device())
         self.dev = dev
-        up = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev)  # noqa: E731
+        # host arrays (the reference's _read_particle_data) are uploaded; device tensors (_device_particle_data) are taken as is
+        up = lambda a: a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev)  # noqa: E731
         self.pos, self.vel, self.dens, self.temp, self.h = up(pos), up(vel), up(elem_den), up(temp), up(hh)
         self.cofm = torch.from_numpy(np.ascontiguousarray(spec._my_cofm)).to(dev)
         self.axis = torch.from_numpy(np.ascontiguousarray(spec._my_axis)).to(dev)
@@ -90,6 +92,8 @@ class Spectra:
     resident   keep particles + candidate index in HBM between calls (default: on when CUDA is there)
     backend    object providing _Particle_Interpolate / _near_lines (default: the CUDA boundary
                module; the CPU tests of the host logic pass a checker here)
+    device_prep  resident route: prepare the particle arrays (selection, temperatures, neutral fractions, species
+               densities) on the device from the raw snapshot fields instead of with host numpy (H I and ion == -1)
     seg_pairs  candidate pairs per work item of the kernels (fsb_params.seg_pairs).  None = one work row per
                sightline when sharded (every row is then bit-identical whatever the number of GPUs), automatic
                otherwise (few sightlines are cut into segments with private rows, summed in list order: faster on one
@@ -100,7 +104,7 @@ class Spectra:
                  savedir=None, reload_file=False, spec_res=0, load_halo=False, units=None, sf_neutral=True,
                  turn_off_selfshield=False, quiet=False, load_snapshot=True, gasprop=None, gasprop_args=None,
                  kernel=None, use_external_Hz=None, precision="fp64", voigt="fast", shard=None, group=None,
-                 resident=None, backend=None, seg_pairs=None):
+                 resident=None, backend=None, seg_pairs=None, device_prep=True):
         _ = (load_halo, load_snapshot)
         self.num = num
         self.base = base
@@ -128,6 +132,7 @@ class Spectra:
         self.minwidth = 500.
         self.tautail = 1e-7  # spectra.py:135
         self.seg_pairs = seg_pairs
+        self.device_prep = bool(device_prep)
         self.precision = _PRECISION[precision]
         self.voigt = _VOIGT[voigt]
         self._backend = backend if backend is not None else _spectra_priv
@@ -343,16 +348,33 @@ class Spectra:
         _ = (pos, velocity, den)
         return np.where(elem_den > 0)
 
+    def _cloudy(self):
+        """The Cloudy table at this redshift (spectra.py:641-645): ``self.cloudy_table`` when the caller set one, else
+        read from ``cdir`` / $FAKE_SPECTRA_CLOUDY_DIR on first use; None when there is neither."""
+        table = self.__dict__.get("cloudy_table")
+        if table is None and (self.cdir is not None or cloudy.default_directory() is not None):
+            table = self.cloudy_table = cloudy.CloudyTable(self.red, self.cdir)
+        return table
+
     def _get_elem_den(self, elem, ion, den, temp, ind, ind2):
-        """Ionisation fraction of a metal ion.  The reference looks it up in Cloudy tables
-        (convert_cloudy.py:167-200), an input of the hot path that is not rebuilt here; a snapshot or
-        subclass may provide ``ion_fraction(elem, ion, den, temp)``."""
+        """Ionisation fraction of a metal ion for host-prepared particles (spectra.py:637-664): the Cloudy table with
+        densities and temperatures clipped to its bounds; without a table a snapshot (or subclass) may provide
+        ``ion_fraction(elem, ion, nH, temp)``."""
         _ = (ind, ind2)
-        fn = getattr(self.snapshot_set, "ion_fraction", None)
-        if fn is None:
-            raise NotImplementedError("ion fractions for %s %d need a table: give the snapshot an "
-                                      "ion_fraction(elem, ion, nH, temp) method or override _get_elem_den" % (elem, ion))
-        return np.float32(fn(elem, ion, den, temp))
+        table = self._cloudy()
+        if table is None:
+            fn = getattr(self.snapshot_set, "ion_fraction", None)
+            if fn is None:
+                raise IOError("ion fractions for %s %d need a Cloudy table (cdir=, $FAKE_SPECTRA_CLOUDY_DIR or a "
+                              "cloudy_table attribute) or a snapshot with ion_fraction(elem, ion, nH, temp)" % (elem, ion))
+            return np.float32(fn(elem, ion, den, temp))
+        clipped = []
+        for values, (lo, hi) in ((den, table.get_dens_bounds()), (temp, table.get_temp_bounds())):
+            values = np.array(values)  # the lookup scales its density argument in place
+            values[values > hi] = hi
+            values[values < lo] = lo
+            clipped.append(values)
+        return np.float32(table.ion(elem, ion, clipped[0], clipped[1]))
 
     def _read_particle_data(self, fn, elem, ion, get_tau):
         """(pos, vel, elem_den, temp, hh, amumass) of the particles of segment ``fn`` near this
@@ -401,6 +423,113 @@ class Spectra:
             elem_den = elem_den[ind2] * self._get_elem_den(elem, ion, den[ind2], temp, ind, ind2)
         elem_den /= amumass
         return (pos, vel, np.ascontiguousarray(elem_den, dtype=np.float32), temp, hh, amumass)
+
+    # ---- particle data prepared on the device (row f3) ------------------------------------------------------
+    _RAW_FIELDS = ("Position", "Velocities", "Density", "InternalEnergy", "ElectronAbundance", "NeutralHydrogenFraction")
+
+    def _device_prep_ok(self, elem, ion):
+        """The device route covers H I (snapshot neutral fraction + Rahmati et al. 2013 above the star-formation
+        threshold), all ionisation states of an element (ion == -1) and metal ions looked up in a Cloudy table
+        (cloudy.CloudyTable).  Needs the stock GasProperties (a user-supplied gasprop class, an overridden
+        _get_elem_den / _filter_particles or a snapshot-provided ion_fraction keep the host route) and the CUDA boundary."""
+        if not (self.resident and self.device_prep and self._backend is _spectra_priv and self._cuda_available()):
+            return False
+        if type(self.gasprop) is not gas_properties.GasProperties or elem == "Z":
+            return False
+        if (elem == "H" and ion == 1) or ion == -1:
+            return True
+        cls = type(self)
+        if cls._get_elem_den is not Spectra._get_elem_den or cls._filter_particles is not Spectra._filter_particles:
+            return False
+        return isinstance(self._cloudy(), cloudy.CloudyTable)
+
+    def _raw_fields(self, fn):
+        """Raw float32 fields of a snapshot segment in HBM (one segment is kept: the next species of the same
+        segment reuses the upload)."""
+        import torch
+        cache = self.__dict__.setdefault("_raw_cache", {})
+        if fn in cache:
+            return cache[fn]
+        cache.clear()
+        snap = self.snapshot_set
+        dev = torch.device("cuda", torch.cuda.current_device())
+        up = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev)  # noqa: E731
+        raw = {}
+        for name in self._RAW_FIELDS:
+            try:
+                raw[name] = up(snap.get_data(0, name, segment=fn))
+            except KeyError:
+                raw[name] = None
+        from . import native
+        try:  # the three cases of get_smooth_length (abstractsnapshot.py:253-282)
+            raw["hh"] = native.smoothing_lengths(up(snap.get_data(0, "Volume", segment=fn)), mode=1)
+        except KeyError:
+            try:
+                raw["hh"] = native.smoothing_lengths(up(snap.get_data(0, "SmoothingLength", segment=fn)), mode=0)
+            except KeyError:
+                raw["hh"] = native.smoothing_lengths(up(snap.get_data(0, "Masses", segment=fn)), raw["Density"], mode=2)
+        try:
+            raw["metals"] = up(snap.get_data(0, "GFM_Metals", segment=fn))
+        except KeyError:
+            raw["metals"] = None
+        cache[fn] = raw
+        return raw
+
+    def _device_particle_data(self, fn, elem, ion):
+        """_read_particle_data on the device: (pos, vel, elem_den, temp, hh, amumass) as CUDA tensors for the particles
+        of segment ``fn`` near this rank's sightlines (six times False when there are none).  Same selection
+        (fsb_near_lines), same formulae, float32 like the host route (values agree to float32 rounding)."""
+        import torch
+        from . import _lib, native
+        none = (False, False, False, False, False, False)
+        raw = self._raw_fields(fn)
+        if raw["Position"] is None or raw["Position"].shape[0] == 0 or np.size(self._my_axis) == 0:
+            return none
+        dev = raw["Position"].device
+        cofm = torch.from_numpy(np.ascontiguousarray(self._my_cofm)).to(dev)
+        axis = torch.from_numpy(np.ascontiguousarray(self._my_axis)).to(dev)
+        ind = native.near_lines(self.box, raw["Position"], raw["hh"], axis, cofm)
+        if self._sharder.mode == "particles" and self._sharder.size > 1:
+            ind = ind[self._sharder.my_particles(int(ind.shape[0]))].contiguous()
+        if ind.shape[0] == 0:
+            return none
+        gp, units = self.gasprop, self.units
+        amumass = self.lines.get_mass(elem)
+        cfg = _lib.Prep()
+        cfg.sqrt_atime = np.sqrt(self.snapshot_set.get_header_attr("Time"))
+        cfg.dens_conv = gp._density_conversion()
+        cfg.rscale = self.rscale
+        cfg.unit_ienergy = np.float32(units.UnitInternalEnergy_in_cgs)
+        cfg.temp_factor = np.float32((units.gamma - 1) * units.protonmass / units.boltzmann)
+        cfg.hy_mass = 0.76
+        cfg.nelec_const = 1.0
+        nelem = self.species.index(elem)
+        cfg.mass_frac_const = float(np.array([0.76, 0.24], dtype=np.float32)[nelem]) if (raw["metals"] is None and nelem < 2) else 0.0
+        cfg.amumass = np.float32(amumass)
+        cfg.dens_thresh_code = np.float32(gp.PhysDensThresh / 0.76 / gp._density_conversion())
+        cfg.neutral_hydrogen = 1 if (elem == "H" and ion == 1) else 0
+        cfg.sf_neutral = 1 if gp.sf_neutral else 0
+        cfg.redshift_coverage = 1 if gp.redshift_coverage else 0
+        if gp.redshift_coverage:
+            cfg.gray_opac, cfg.gamma_uvb = gp.gray_opac, gp.gamma_UVB
+        cfg.f_bar = gp.f_bar
+        if raw["metals"] is None and nelem >= 2:
+            raise KeyError("GFM_Metals")  # like the reference: no metal table, no metal mass fraction (spectra.py:700-706)
+        mass_frac = raw["metals"][:, nelem] if raw["metals"] is not None else None
+        ion_table = None
+        if not cfg.neutral_hydrogen and ion != -1:
+            # metal ion: drop the particles without mass in the element, then look the ion fraction up (spectra.py:598-610)
+            ind = native.select_particles(cfg, ind, raw["Density"], mass_frac)
+            if ind.shape[0] == 0:
+                return none
+            ion_table, _owner = self._cloudy().device_table(elem, ion, dev)
+        for name in ("InternalEnergy", "ElectronAbundance") + (("NeutralHydrogenFraction",) if cfg.neutral_hydrogen else ()):
+            if raw[name] is None:
+                raise KeyError(name)  # as the reference's get_temp / get_reproc_HI would
+        pos, vel, elem_den, temp, hh = native.prepare_particles(
+            cfg, ind, raw["Position"], raw["Velocities"], raw["Density"], raw["InternalEnergy"], raw["ElectronAbundance"],
+            raw["NeutralHydrogenFraction"], raw["hh"], mass_frac, ion_table=ion_table)
+        return (pos, vel, elem_den, temp, hh, amumass)
 
     def find_all_particles(self):
         """Positions and smoothing lengths of all particles near sightlines."""
@@ -478,7 +607,10 @@ class Spectra:
             eng = self._engines.pop(key)
             self._engines[key] = eng  # most recently used last
             return eng
-        (pos, vel, elem_den, temp, hh, amumass) = self._read_particle_data(fn, elem, ion, True)
+        if self._device_prep_ok(elem, ion):
+            (pos, vel, elem_den, temp, hh, amumass) = self._device_particle_data(fn, elem, ion)
+        else:
+            (pos, vel, elem_den, temp, hh, amumass) = self._read_particle_data(fn, elem, ion, True)
         eng = None
         if amumass is not False and np.size(self._my_axis) > 0:
             eng = _SegmentEngine(self, pos, vel, elem_den, temp, hh)

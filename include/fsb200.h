@@ -221,6 +221,62 @@ FSB_API int fsb_assign_cells(const fsb_index *idx, double box, const double *cof
  * else FP32: 8 independent chains per thread, best of several launches.  Synchronous. */
 FSB_API int fsb_measure_fma_peak(int32_t fp64, double *tflops, void *stream);
 
+/* ---- snapshot fields -> inputs of the interpolation, on the device -------------------------
+ * Replaces the host numpy of Spectra._read_particle_data (spectra.py:550-617) with its helpers
+ * AbstractSnapshot.get_peculiar_velocity / get_temp / get_smooth_length (abstractsnapshot.py:114-154,253-282) and
+ * GasProperties.get_code_rhoH / get_reproc_HI (gas_properties.py:104-146) for the particles listed in `index`
+ * (e.g. the output of fsb_near_lines; NULL = all m particles).  Inputs are the raw snapshot fields of one segment
+ * (DEVICE, float32, Gadget-HDF5 names): Coordinates[n][3], Velocities[n][3], Density, InternalEnergy,
+ * ElectronAbundance (NULL: cfg.nelec_const), NeutralHydrogenAbundance (needed when cfg.neutral_hydrogen),
+ * the kernel support radii of all n particles (fsb_smoothing_lengths), and an optional mass-fraction column (element e of GFM_Metals[n][9]: pointer to
+ * [0][e], stride 9; NULL: cfg.mass_frac_const).  Outputs (DEVICE, float32, m entries): pos[m][3], vel[m][3] (NULL to
+ * skip), elem_den, temp (NULL to skip; values <= 0 become 1), hh.
+ * Metal ions (spectra.py:598-611,637-664): fsb_prepare_select keeps the particles with mass in the element
+ * (_filter_particles), and `ion` (may be NULL) is the Cloudy table of CloudyTable.ion (convert_cloudy.py:167-200) at the
+ * snapshot's redshift for one (element, ion): log10 of the ion fraction on a regular (log10 nH, log10 T) grid,
+ * interpolated with cubic B-splines in scipy.ndimage.map_coordinates' mode "nearest". */
+typedef struct fsb_prep {
+    float dens_conv;         /* code density -> physical H atoms / cm^3 (gas_properties.py:108)                 */
+    float rscale;            /* cm per comoving kpc/h (spectra.py:210)                                          */
+    float unit_ienergy;      /* UnitInternalEnergy_in_cgs                                                       */
+    float temp_factor;       /* (gamma - 1) m_p / k_B                                                           */
+    float hy_mass;           /* hydrogen mass fraction of the temperature formula (0.76)                        */
+    float nelec_const;       /* electron abundance when the snapshot has none                                   */
+    float mass_frac_const;   /* element mass fraction when the snapshot has no metal table (0.76 / 0.24)        */
+    float amumass;           /* ion mass in amu (1 for "Z")                                                     */
+    float dens_thresh_code;  /* star-formation threshold in code density units (gas_properties.py:138)          */
+    int32_t reserved;
+    int32_t neutral_hydrogen;/* multiply by the (reprocessed) neutral fraction: H I                             */
+    int32_t sf_neutral;      /* replace the neutral fraction above the threshold by the Rahmati value at 1e4 K  */
+    int32_t redshift_coverage; /* the UVB table covers the redshift (else star-forming gas is fully neutral)    */
+    double gray_opac, gamma_uvb, f_bar; /* Rahmati et al. 2013 parameters at this redshift                      */
+    double sqrt_atime;       /* peculiar velocity = (float)(Velocities * sqrt(a)), abstractsnapshot.py:114-119  */
+} fsb_prep;
+typedef struct fsb_ion_table {
+    const double *coef;      /* DEVICE [nd + 2 pad][nt + 2 pad]: B-spline coefficients of the table padded by `pad` cells
+                                of edge values per side (scipy.ndimage.spline_filter(order 3, mode "nearest") of it) */
+    int32_t nd, nt, pad, reserved;
+    double dens0, dens_span; /* log10 nH of the first grid point, last minus first                              */
+    double temp0, temp_span; /* log10 T  of the first grid point, last minus first                              */
+    float dens_lo, dens_hi;  /* nH and T are clipped to the table's bounds first (spectra.py:649-663)           */
+    float temp_lo, temp_hi;
+    float rho_factor;        /* gas density -> Cloudy hden, 0.774132 (convert_cloudy.py:183)                    */
+    float reserved2;
+} fsb_ion_table;
+FSB_API int fsb_prepare_particles(const fsb_prep *cfg, const int32_t *index, int64_t m, const float *position,
+                          const float *velocity, const float *density, const float *ienergy, const float *nelec,
+                          const float *nh0, const float *smoothing, const float *mass_frac,
+                          int64_t mass_frac_stride, const fsb_ion_table *ion, float *pos, float *vel, float *elem_den,
+                          float *temp, float *hh, void *stream);
+/* get_smooth_length (abstractsnapshot.py:253-282) for the n particles of a segment, DEVICE float32.  mode 0:
+ * a = SmoothingLength -> a / 2 (Gadget); 1: a = Volume -> a^(1/3) (Arepo); 2: a = Masses, b = Density -> (a / b)^(1/3). */
+FSB_API int fsb_smoothing_lengths(const float *a, const float *b, int64_t n, int32_t mode, float *hh, void *stream);
+/* The entries of index[m] (NULL = 0..m-1) whose element density (Density * dens_conv * rscale) * mass fraction is
+ * positive, in order (DEVICE int32 out_index[m]); *count (HOST) is valid on return (synchronises the stream). */
+FSB_API int fsb_prepare_select(const fsb_prep *cfg, const int32_t *index, int64_t m, const float *density,
+                          const float *mass_frac, int64_t mass_frac_stride, int32_t *out_index, int64_t *count,
+                          void *stream);
+
 /* ---- flux statistics on device-resident tau ----------------------------- */
 /* Replaces get_mean_flux_scale / _rescale_mean_flux (py_module.cpp:235-282): the factor s with
  * mean(exp(-s tau)) = mean_flux_desired over the pixels with tau <= thresh, by the reference's Newton
