@@ -26,10 +26,11 @@ class Params(C.Structure):
 
 class Prep(C.Structure):
     """struct fsb_prep."""
-    _fields_ = [(n, C.c_float) for n in ("dens_conv", "rscale", "unit_ienergy", "temp_factor", "hy_mass",
+    _fields_ = [(n, C.c_float) for n in ("dens_conv", "rscale", "hy_mass",
                                          "nelec_const", "mass_frac_const", "amumass", "dens_thresh_code")] + \
-               [(n, C.c_int32) for n in ("reserved", "neutral_hydrogen", "sf_neutral", "redshift_coverage")] + \
-               [(n, C.c_double) for n in ("gray_opac", "gamma_uvb", "f_bar", "sqrt_atime")]
+               [(n, C.c_int32) for n in ("velocity_divides", "neutral_hydrogen", "sf_neutral", "redshift_coverage")] + \
+               [(n, C.c_double) for n in ("gray_opac", "gamma_uvb", "f_bar", "unit_ienergy", "temp_factor")] + \
+               [("temp_double", C.c_int32), ("reserved", C.c_int32), ("velocity_factor", C.c_double)]
 
 
 class IonTable(C.Structure):
@@ -94,6 +95,7 @@ SIGNATURES = {
     "fsb_prepare_select": (C.c_int, [C.POINTER(Prep), _P, C.c_int64, _P, _P, C.c_int64, _P, C.POINTER(C.c_int64), _P]),
     "fsb_rescale_mean_flux": (C.c_int, [_P, C.c_int64, C.c_double, C.c_double, C.c_double, C.POINTER(C.c_double),
                                         C.POINTER(C.c_int32), _P]),
+    "fsb_row_max": (C.c_int, [_P, C.c_int64, C.c_int64, _P, _P]),
     "fsb_flux_sums": (C.c_int, [_P, C.c_int64, C.c_double, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                 C.POINTER(C.c_int64), _P]),
     "fsb_flux_pdf": (C.c_int, [_P, C.c_int64, C.c_double, C.c_int32, _P, _P]),

@@ -119,21 +119,28 @@ __global__ void __launch_bounds__(256) k_prepare(fsb_prep cfg, fsb_ion_table ion
     const int64_t p = index ? (int64_t) index[i] : i;
     pos[3 * i] = position[3 * p], pos[3 * i + 1] = position[3 * p + 1], pos[3 * i + 2] = position[3 * p + 2];
     if (vel) {
-        // vel *= np.sqrt(atime) with a float64 scalar: numpy forms the product in double and rounds it back to float32
-        const double sa = cfg.sqrt_atime;
-        vel[3 * i] = (float) ((double) velocity[3 * p] * sa), vel[3 * i + 1] = (float) ((double) velocity[3 * p + 1] * sa);
-        vel[3 * i + 2] = (float) ((double) velocity[3 * p + 2] * sa);
+        // vel *= np.sqrt(atime) (or vel /= atime) with a float64 scalar: numpy forms the result in double and rounds it
+        // back to float32
+        const double f = cfg.velocity_factor;
+        #pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const double v = (double) velocity[3 * p + c];
+            vel[3 * i + c] = (float) (cfg.velocity_divides ? v / f : v * f);
+        }
     }
     hh[i] = smoothing[p];
     const float rho = density[p];
     const float den = __fmul_rn(rho, cfg.dens_conv);  // physical H atoms / cm^3
     float t_used = 0;
     if (temp || ion.coef) {
-        // abstractsnapshot.py:121-154, float32 like numpy: ienergy * unit, 4 / (hy (3 + 4 ne) + 1) * ienergy, * (gamma-1) mp / kB
-        const float ie = __fmul_rn(ienergy[p], cfg.unit_ienergy);
+        // abstractsnapshot.py:121-154: mu = 4 / (hy (3 + 4 ne) + 1) in float32; then, with a unit system of Python floats,
+        // ienergy * unit, mu * ienergy and the (gamma-1) mp / kB factor in float32 as well; with numpy float64 units
+        // (headers read from files) those three products are double and the result is rounded to float32 once
         const float ne = nelec ? nelec[p] : cfg.nelec_const;
         const float mu = __fdiv_rn(4.0f, __fadd_rn(__fmul_rn(cfg.hy_mass, __fadd_rn(3.0f, __fmul_rn(4.0f, ne))), 1.0f));
-        const float t = __fmul_rn(cfg.temp_factor, __fmul_rn(mu, ie));
+        float t;
+        if (cfg.temp_double) t = (float) (cfg.temp_factor * ((double) mu * ((double) ienergy[p] * cfg.unit_ienergy)));
+        else t = __fmul_rn((float) cfg.temp_factor, __fmul_rn(mu, __fmul_rn(ienergy[p], (float) cfg.unit_ienergy)));
         t_used = t <= 0 ? 1.0f : t;
         if (temp) temp[i] = t_used;
     }

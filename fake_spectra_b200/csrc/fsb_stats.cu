@@ -269,6 +269,30 @@ extern "C" int fsb_flux_sums(const double *tau, int64_t n, double scale, double 
     return FSB_OK;
 }
 
+// Row maxima of a [nrows][n] array: one warp per row (the damped-absorber cut of Spectra._filter_tau, spectra.py:1258).
+__global__ void __launch_bounds__(256) k_row_max(const double *__restrict__ a, int64_t nrows, int64_t n, double *__restrict__ out)
+{
+    const int64_t row = (int64_t) blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= nrows) return;
+    const double *r = a + row * n;
+    double m = -INFINITY;
+    for (int64_t j = threadIdx.x & 31; j < n; j += 32) m = fmax(m, r[j]);
+    #pragma unroll
+    for (int d = 16; d > 0; d >>= 1) m = fmax(m, __shfl_down_sync(0xffffffffu, m, d));
+    if ((threadIdx.x & 31) == 0) out[row] = m;
+}
+
+extern "C" int fsb_row_max(const double *a, int64_t nrows, int64_t n, double *out, void *stream_v)
+{
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    FSB_REQUIRE(nrows >= 0 && n >= 1, "bad sizes");
+    if (nrows == 0) return FSB_OK;
+    FSB_REQUIRE(a != nullptr && out != nullptr, "NULL array");
+    count_launch(); k_row_max<<<(unsigned) ((nrows + 7) / 8), 256, 0, stream>>>(a, nrows, n, out);
+    FSB_CUDA_TRY(cudaGetLastError());
+    return FSB_OK;
+}
+
 extern "C" int fsb_flux_pdf(const double *tau, int64_t n, double scale, int32_t nbins, uint64_t *counts, void *stream_v)
 {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_v);

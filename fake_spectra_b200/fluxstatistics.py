@@ -147,6 +147,55 @@ def flux_sums(tau, scale=1.0, thresh=1e30):
     return sf.value, stf.value, used.value
 
 
+def row_max(tau):
+    """Maximum optical depth of every sightline (device reduction, fsb_row_max)."""
+    import torch
+    t = _device_tau(tau)
+    if t.dim() != 2:
+        raise ValueError("tau must have shape (NumLos, npix)")
+    out = torch.empty(t.shape[0], dtype=torch.float64, device=t.device)
+    with torch.cuda.device(t.device):
+        rc = _lib.load().fsb_row_max(C.c_void_p(t.data_ptr()), t.shape[0], t.shape[1], C.c_void_p(out.data_ptr()), _stream())
+    _lib.check(rc, "fsb_row_max")
+    return out.cpu().numpy()
+
+
+def mask_damped_region(tt, taueff, tau_thresh=1e6, thresh2=0.25):
+    """One spectrum with a damped absorber (spectra.py:1219-1252, after Chabanier et al. 2019): around every maximum above
+    ``tau_thresh`` the pixels are set to ``taueff`` outwards in both directions (periodic) for as long as they exceed
+    ``taueff + thresh2``.  Alters ``tt``; returns (tt, a pixel count as the reference tallies it)."""
+    n = tt.shape[0]
+    limit = taueff + thresh2
+    tot = 0
+    while tt.max() > tau_thresh:
+        peak = int(tt.argmax())
+        for direction, first in ((-1, 0), (1, 1)):
+            j = first
+            while tt[(peak + direction * j) % n] > limit:
+                tt[(peak + direction * j) % n] = taueff
+                j += 1
+            # the reference's upward counter runs modulo the pixel count once it wraps (spectra.py:1243-1250)
+            tot += j if direction < 0 or peak + j < n else j - n
+    return tt, tot
+
+
+def filter_tau(tau, tau_thresh):
+    """Spectra._filter_tau (spectra.py:1254-1270): sightlines whose maximum optical depth exceeds ``tau_thresh`` have
+    their damped regions replaced by the effective optical depth -log <exp(-tau)> of the whole sample.  The two
+    reductions over the sample (mean flux, row maxima) run on the device; the few affected rows are edited on the host.
+    Alters ``tau`` (a host array) in place like the reference."""
+    if tau_thresh is None:
+        return tau
+    t = _device_tau(tau)
+    taueff = -math.log(_mean_exp(t))
+    rows = np.where(row_max(t) > tau_thresh)[0]
+    for i in rows:
+        tau[i], _ = mask_damped_region(tau[i], taueff, tau_thresh=tau_thresh)
+    if rows.size:
+        assert max(tau[i].max() for i in rows) < tau_thresh * 1.01
+    return tau
+
+
 def _mean_exp(t):
     sf, _, used = flux_sums(t)
     return sf / used if used else float("nan")

@@ -24,8 +24,11 @@ class GasProperties:
         self.sf_neutral = sf_neutral
         self.redshift_coverage = redshift <= _ZZ[-1]
         if self.redshift_coverage:
-            self.gray_opac = float(np.interp(redshift, _ZZ, _GRAY_OPAC))
-            self.gamma_UVB = float(np.interp(redshift, _ZZ, _GAMMA_UVB))
+            # numpy float64 scalars on purpose (the reference holds 0-d float64 arrays from interp1d, gas_properties.py:
+            # 51-54): they promote the float32 densities, so the Rahmati formulae below run in double and the neutral
+            # fraction is rounded to float32 once, when it is stored
+            self.gray_opac = np.float64(np.interp(redshift, _ZZ, _GRAY_OPAC))
+            self.gamma_UVB = np.float64(np.interp(redshift, _ZZ, _GAMMA_UVB))
         else:
             print("Warning: no self-shielding at z=", redshift)
         self.gamma = 5. / 3

@@ -496,11 +496,17 @@ class Spectra:
         gp, units = self.gasprop, self.units
         amumass = self.lines.get_mass(elem)
         cfg = _lib.Prep()
-        cfg.sqrt_atime = np.sqrt(self.snapshot_set.get_header_attr("Time"))
+        # Gadget HDF5: velocities times sqrt(a); MP-Gadget BigFile: divided by a unless already peculiar
+        if hasattr(self.snapshot_set, "velocity_divisor"):
+            cfg.velocity_factor, cfg.velocity_divides = self.snapshot_set.velocity_divisor(), 1
+        else:
+            cfg.velocity_factor, cfg.velocity_divides = np.sqrt(self.snapshot_set.get_header_attr("Time")), 0
         cfg.dens_conv = gp._density_conversion()
         cfg.rscale = self.rscale
-        cfg.unit_ienergy = np.float32(units.UnitInternalEnergy_in_cgs)
-        cfg.temp_factor = np.float32((units.gamma - 1) * units.protonmass / units.boltzmann)
+        cfg.unit_ienergy = units.UnitInternalEnergy_in_cgs
+        cfg.temp_factor = (units.gamma - 1) * units.protonmass / units.boltzmann
+        # numpy scalars (unit systems built from file headers) promote the float32 fields to double, Python floats do not
+        cfg.temp_double = 1 if isinstance(units.UnitInternalEnergy_in_cgs, np.floating) else 0
         cfg.hy_mass = 0.76
         cfg.nelec_const = 1.0
         nelem = self.species.index(elem)
@@ -875,12 +881,16 @@ class Spectra:
         return ntau
 
     # -- flux statistics (spectra.py:1254-1301): the reductions run on the device, fluxstatistics.py ------
+    def _filter_single_tau_complex(self, tt, taueff, tau_thresh=1e6, thresh2=0.25):
+        """One spectrum: damped regions set to ``taueff`` (spectra.py:1219-1252)."""
+        from . import fluxstatistics as fstat
+        return fstat.mask_damped_region(tt, taueff, tau_thresh=tau_thresh, thresh2=thresh2)
+
     def _filter_tau(self, tau, tau_thresh=None):
-        """The reference masks damped absorbers here (spectra.py:1254-1270); that filter is outside the
-        hot path and not provided: only tau_thresh=None is accepted."""
-        if tau_thresh is not None:
-            raise NotImplementedError("tau_thresh filtering of damped absorbers is not provided")
-        return tau
+        """Sightlines with an optically thick absorber (maximum above ``tau_thresh``) have it masked
+        (spectra.py:1254-1270); alters ``tau`` like the reference."""
+        from . import fluxstatistics as fstat
+        return fstat.filter_tau(tau, tau_thresh)
 
     def get_mean_flux(self, elem="H", ion=1, line=1215, tau_thresh=None):
         """Mean flux <exp(-tau)> along the sightlines (spectra.py:1272-1276)."""

@@ -231,3 +231,31 @@ class SyntheticSnapshot:
         nelec = self.get_data(part_type, "ElectronAbundance", segment=segment)
         muienergy = 4 / (hy_mass * (3 + 4 * nelec) + 1) * ienergy
         return (units.gamma - 1) * units.protonmass / units.boltzmann * muienergy
+
+
+def write_bigfile(snapshot, path, num=0, nfile=2, peculiar=False):
+    """Export a :class:`SyntheticSnapshot` in MP-Gadget's BigFile layout under ``path/PART_<num>`` (block names and
+    velocity convention of MP-Gadget: Velocity = a v_pec unless ``peculiar``): an input for
+    :class:`fake_spectra_b200.abstractsnapshot.BigFileSnapshot`.  Returns ``path``."""
+    import os
+
+    from .abstractsnapshot import HDF_TO_BIGFILE, write_bigfile_block
+    root = os.path.join(path, "PART_" + str(num).rjust(3, "0"))
+    h = snapshot.header
+    atime = float(h["Time"])
+    attrs = {"BoxSize": float(h["BoxSize"]), "Time": atime, "HubbleParam": float(h["HubbleParam"]),
+             "Omega0": float(h["Omega0"]), "OmegaLambda": float(h["OmegaLambda"]), "OmegaBaryon": float(h["OmegaBaryon"]),
+             "TotNumPart": np.asarray(h["NumPart_Total"], dtype=np.uint64),
+             "UnitLength_in_cm": float(h["UnitLength_in_cm"]), "UnitMass_in_g": float(h["UnitMass_in_g"]),
+             "UnitVelocity_in_cm_per_s": float(h["UnitVelocity_in_cm_per_s"]),
+             "UsePeculiarVelocity": np.int32(1 if peculiar else 0), "DensityKernel": np.int32(1), "CodeVersion": "synthetic"}
+    write_bigfile_block(os.path.join(root, "Header"), None, attrs=attrs)
+    for name, data in snapshot.fields.items():
+        if name in ("Volume",):
+            continue  # MP-Gadget output is SPH
+        out = data
+        if name == "Velocities":  # stored Gadget-style as v_pec / sqrt(a)
+            vpec = data.astype(np.float64) * np.sqrt(atime)
+            out = (vpec if peculiar else vpec * atime).astype(np.float32)
+        write_bigfile_block(os.path.join(root, "0", HDF_TO_BIGFILE.get(name, name)), out, nfile=nfile)
+    return path

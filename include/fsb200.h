@@ -238,19 +238,24 @@ FSB_API int fsb_measure_fma_peak(int32_t fp64, double *tflops, void *stream);
 typedef struct fsb_prep {
     float dens_conv;         /* code density -> physical H atoms / cm^3 (gas_properties.py:108)                 */
     float rscale;            /* cm per comoving kpc/h (spectra.py:210)                                          */
-    float unit_ienergy;      /* UnitInternalEnergy_in_cgs                                                       */
-    float temp_factor;       /* (gamma - 1) m_p / k_B                                                           */
     float hy_mass;           /* hydrogen mass fraction of the temperature formula (0.76)                        */
     float nelec_const;       /* electron abundance when the snapshot has none                                   */
     float mass_frac_const;   /* element mass fraction when the snapshot has no metal table (0.76 / 0.24)        */
     float amumass;           /* ion mass in amu (1 for "Z")                                                     */
     float dens_thresh_code;  /* star-formation threshold in code density units (gas_properties.py:138)          */
-    int32_t reserved;
+    int32_t velocity_divides;/* peculiar velocity = Velocities / velocity_factor (MP-Gadget) instead of times it      */
     int32_t neutral_hydrogen;/* multiply by the (reprocessed) neutral fraction: H I                             */
     int32_t sf_neutral;      /* replace the neutral fraction above the threshold by the Rahmati value at 1e4 K  */
     int32_t redshift_coverage; /* the UVB table covers the redshift (else star-forming gas is fully neutral)    */
     double gray_opac, gamma_uvb, f_bar; /* Rahmati et al. 2013 parameters at this redshift                      */
-    double sqrt_atime;       /* peculiar velocity = (float)(Velocities * sqrt(a)), abstractsnapshot.py:114-119  */
+    double unit_ienergy;     /* UnitInternalEnergy_in_cgs                                                       */
+    double temp_factor;      /* (gamma - 1) m_p / k_B                                                           */
+    int32_t temp_double;     /* the unit system holds numpy float64 values (headers read from files): numpy then forms
+                                the temperature in double and the reference rounds it to float32 once; 0: Python
+                                floats, every operation in float32 */
+    int32_t reserved;
+    double velocity_factor;  /* peculiar velocity = (float)(Velocities * sqrt(a)) for Gadget HDF5 (abstractsnapshot.py:
+                                114-119), (float)(Velocities / a) for MP-Gadget (:398-405), formed in double */
 } fsb_prep;
 typedef struct fsb_ion_table {
     const double *coef;      /* DEVICE [nd + 2 pad][nt + 2 pad]: B-spline coefficients of the table padded by `pad` cells
@@ -290,6 +295,9 @@ FSB_API int fsb_rescale_mean_flux(const double *tau, int64_t n, double mean_flux
  * (spectra.py:1272-1276) is sum_flux / used at scale 1.  Synchronises `stream`. */
 FSB_API int fsb_flux_sums(const double *tau, int64_t n, double scale, double thresh, double *sum_flux, double *sum_tau_flux,
                   int64_t *used, void *stream);
+/* out[r] = max_j a[r][j] for a DEVICE array of nrows x n doubles: the per-sightline maximum optical depth that
+ * Spectra._filter_tau compares with tau_thresh (spectra.py:1258). */
+FSB_API int fsb_row_max(const double *a, int64_t nrows, int64_t n, double *out, void *stream);
 /* counts[nbins] (DEVICE, overwritten) = histogram of exp(-scale tau) on nbins equal bins of [0, 1] with
  * numpy.histogram's edge rules: the counts behind fluxstatistics.flux_pdf (fluxstatistics.py:43-52). */
 FSB_API int fsb_flux_pdf(const double *tau, int64_t n, double scale, int32_t nbins, uint64_t *counts, void *stream);

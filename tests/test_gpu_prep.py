@@ -5,8 +5,9 @@ gas_properties.py:104-146, convert_cloudy.py:167-200).
 Tolerances: selection, positions, Gadget smoothing lengths and velocities are bit-equal (same float32 / float64
 operations); Arepo smoothing lengths Volume^(1/3) within one float32 ulp (numpy's float32 power is a SIMD routine that is
 not correctly rounded -- it differs from glibc's powf for 20 % of arguments -- while the kernel returns the correctly
-rounded power); temperatures bit-equal; species densities within 4e-6 relative (float32 results of formulae whose transcendental parts
-the reference evaluates in float32 numpy and the kernel in double, rounded once); ion fractions from a smooth Cloudy
+rounded power); temperatures bit-equal; species densities within 2.5e-7 relative (two float32 ulps: the Rahmati neutral fraction is
+evaluated in double by numpy and by the kernel and rounded to float32 once, the libraries' pow / exp differ in the last
+bits of the double); ion fractions from a smooth Cloudy
 table within 2e-5 relative (numpy's float32 log10 is an ulp off the correctly rounded value the kernel uses for half of
 its arguments; the difference scales with the table's slope), and within 1e-6 of the restatement with correctly rounded
 logarithms on a table with Cloudy's -30 plateau (27 dex per cell at its edge).  The optical depths
@@ -60,7 +61,7 @@ def test_device_prep_matches_host_route(elem, ion, arepo):
         assert np.array_equal(vel, want[1])
         assert np.array_equal(temp, want[3])
         assert temp.min() >= 1.0 and (temp == 1.0).any()
-        tol = 2e-5 if (ion > 0 and elem != "H") else 4e-6
+        tol = 2e-5 if (ion > 0 and elem != "H") else 2.5e-7
         assert den.dtype == np.float32 and (np.all(den > 0) if ion > 0 else (elem != "C" or (den == 0).any()))
         ok = want[2] > 0
         assert np.array_equal(den == 0, want[2] == 0) and np.max(np.abs(den[ok] - want[2][ok]) / want[2][ok]) < tol
@@ -82,9 +83,9 @@ def test_ion_lookup_on_a_plateau_table():
     dev = torch.device("cuda", 0)
     up = lambda name: torch.from_numpy(snap.get_data(0, name, segment=0)).to(dev)  # noqa: E731
     cfg = _lib.Prep()
-    cfg.sqrt_atime, cfg.dens_conv, cfg.rscale = np.sqrt(rs.atime), gp._density_conversion(), rs.rscale
-    cfg.unit_ienergy = np.float32(rs.units.UnitInternalEnergy_in_cgs)
-    cfg.temp_factor = np.float32((rs.units.gamma - 1) * rs.units.protonmass / rs.units.boltzmann)
+    cfg.velocity_factor, cfg.dens_conv, cfg.rscale = np.sqrt(rs.atime), gp._density_conversion(), rs.rscale
+    cfg.unit_ienergy = rs.units.UnitInternalEnergy_in_cgs
+    cfg.temp_factor = (rs.units.gamma - 1) * rs.units.protonmass / rs.units.boltzmann
     cfg.hy_mass, cfg.amumass = 0.76, np.float32(14.0067)
     metals = up("GFM_Metals")
     ion_table, _owner = tb.device_table("N", 5, dev)
@@ -104,6 +105,27 @@ def test_ion_lookup_on_a_plateau_table():
     want = (ed * np.float32(10 ** ions)) / np.float32(14.0067)
     assert (ions < -20).any() and (ions > -8).any()  # both sides of the plateau's edge were sampled
     assert np.max(np.abs(got[2].cpu().numpy() - want) / want) < 1e-6
+
+
+@pytest.mark.parametrize("peculiar", [False, True])
+def test_device_prep_from_a_bigfile_snapshot(tmp_path, peculiar):
+    """A snapshot on disc (MP-Gadget layout): header values are numpy float64, so numpy forms temperatures in double and
+    velocities as v / a in double; the kernel's second arithmetic mode reproduces both bit for bit."""
+    from fake_spectra_b200 import abstractsnapshot as absn, synthetic
+    path = synthetic.write_bigfile(snapshot(arepo=False), str(tmp_path), num=1, nfile=3, peculiar=peculiar)
+    table, reds = make_table()
+    rs = randspectra.RandSpectra(1, path, numlos=24, thresh=0., res=2., quiet=True)
+    rs.cloudy_table = cloudy.CloudyTable(rs.red, table=table, reds=reds)
+    assert isinstance(rs.snapshot_set, absn.BigFileSnapshot) and isinstance(rs.units.UnitInternalEnergy_in_cgs, np.floating)
+    for elem, ion in (("H", 1), ("C", 4)):
+        want = rs._read_particle_data(0, elem, ion, True)
+        got = [g.cpu().numpy() for g in rs._device_particle_data(0, elem, ion)[:5]]
+        assert np.array_equal(got[0], want[0]) and np.array_equal(got[4], want[4])
+        assert np.array_equal(got[1], want[1])
+        assert np.array_equal(got[3], want[3].astype(np.float32))
+        assert np.max(np.abs(got[2] - want[2]) / want[2]) < (2.5e-7 if elem == "H" else 2e-5)
+    tau = rs.get_tau("H", 1, 1215)
+    assert rs._engines and np.isfinite(tau).all() and tau.max() > 0
 
 
 def test_smoothing_length_from_masses():

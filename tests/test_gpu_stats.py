@@ -148,5 +148,34 @@ def test_spectra_class_statistics(oracle):
     kf, pk = rs.get_flux_power_1D()
     wk, want = statcases.flux_power_np(tau, rs.vmax)
     assert np.array_equal(kf, wk[1:]) and np.max(np.abs(pk - want[1:])) <= 1e-10 * np.max(want)
-    with pytest.raises(NotImplementedError):
-        rs.get_mean_flux(tau_thresh=1e6)
+    assert abs(rs.get_mean_flux(tau_thresh=1e6) - np.mean(np.exp(-tau))) < 1e-13  # nothing is that thick here
+
+
+def test_damped_absorbers_are_masked(fstat):
+    """tau_thresh (spectra.py:1254-1270): rows whose maximum exceeds the threshold have the damped region set to the
+    sample's effective optical depth out to taueff + 0.25 on both sides, periodically; other rows are untouched."""
+    tau = forest(64, 500, seed=9) * 0.3
+    tau[tau > 50] = 1.0
+    ref = tau.copy()
+    x = np.arange(500)
+    tau[7] += 2e6 * np.exp(-((x - 120) / 4.0) ** 2)           # a damped absorber in the middle of row 7
+    tau[30] += 5e6 * np.exp(-((((x - 2) + 250) % 500 - 250) / 3.0) ** 2)  # one that straddles the periodic edge of row 30
+    dirty = tau.copy()
+    taueff = -math.log(np.mean(np.exp(-dirty)))
+    assert np.allclose(fstat.row_max(dirty), dirty.max(axis=1), rtol=0, atol=0)
+    out = fstat.filter_tau(tau, 1e6)
+    assert out is tau
+    keep = np.ones(64, dtype=bool)
+    keep[[7, 30]] = False
+    assert np.array_equal(tau[keep], dirty[keep])
+    for row, centre in ((7, 120), (30, 2)):
+        masked = tau[row] != dirty[row]
+        assert masked[centre] and np.all(tau[row][masked] == taueff)
+        assert tau[row].max() < 1e6 and masked.sum() > 10
+        # the masked region is one periodic run around the peak, bounded by the first pixels at or below taueff + 0.25
+        idx = (np.where(masked)[0] - centre + 250) % 500 - 250
+        lo, hi = idx.min(), idx.max()
+        assert np.array_equal(np.sort(idx), np.arange(lo, hi + 1))
+        assert dirty[row][(centre + lo - 1) % 500] <= taueff + 0.25 and dirty[row][(centre + hi + 1) % 500] <= taueff + 0.25
+        assert np.all(dirty[row][(centre + np.arange(lo, hi + 1)) % 500] > taueff + 0.25)
+    assert ref.shape == tau.shape
