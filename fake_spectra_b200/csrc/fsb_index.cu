@@ -219,30 +219,84 @@ __device__ __forceinline__ void pairs_in_group(const LineTable &T, const AxisGri
     }
 }
 
-// MODE 0: count pairs per line.  MODE 1: fill the lists.  MODE 2: flag particles with >= 1 line.
-template <int MODE>
-__global__ void __launch_bounds__(256) k_pairs(LineTable T, const float *__restrict__ pos, const float *__restrict__ hh,
-                                               int64_t npart, int32_t *__restrict__ count,
-                                               const int64_t *__restrict__ offsets, int32_t *__restrict__ particle,
-                                               uint8_t *__restrict__ flag)
+// ---- bulk asynchronous copies (TMA, 1-D form) with an mbarrier in shared memory ---------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
 {
-    // positions arrive as [npart][3] floats: the CTA's 768 consecutive floats are staged through shared memory
-    // with coalesced 4-byte loads (a thread reading its own three floats touches every sector three times)
-    __shared__ float s_pos[3 * 256];
-    const int64_t p0 = (int64_t) blockIdx.x * 256;
-    const int nhere = (int) min((int64_t) 256, npart - p0);
-    for (int i = threadIdx.x; i < 3 * nhere; i += 256) s_pos[i] = pos[3 * p0 + i];
-    __syncthreads();
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred done;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 done, [%0], %1;\n\t"
+        "@!done bra WAIT_%=;\n\t}" ::"r"(smem_addr(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// MODE 0: count pairs per line.  MODE 1: fill the lists.  MODE 2: flag particles with >= 1 line.
+//
+// One CTA per tile of 256 particles.  The tile's positions ([256][3] floats, 3 KB) and smoothing lengths (1 KB) are
+// contiguous in global memory: one elected thread fetches them with two bulk asynchronous copies (cp.async.bulk, the
+// 1-D TMA path) into shared memory and arms an mbarrier with the byte count; the threads then pick their particle
+// out of shared memory (a thread reading its own three floats from global memory would touch every sector three
+// times, and staging through registers costs eight load/store instructions per thread).  The four CTAs resident on an
+// SM overlap each other's copy with the sightline-grid walk, which is a chain of dependent loads.  A persistent variant
+// with a two-stage ring in one CTA was built and dropped: the loop state pushed the walk over 64 registers (spills, or a
+// resident CTA less).  The last tile, when its byte counts are not multiples of 16, and unaligned base pointers take
+// plain coalesced loads.
+constexpr int kPairTile = 256;
+
+template <int MODE>
+__global__ void __launch_bounds__(kPairTile) k_pairs(LineTable T, const float *__restrict__ pos, const float *__restrict__ hh,
+                                                     int64_t npart, int32_t *__restrict__ count,
+                                                     const int64_t *__restrict__ offsets, int32_t *__restrict__ particle,
+                                                     uint8_t *__restrict__ flag)
+{
+    __shared__ __align__(128) float s_pos[3 * kPairTile];
+    __shared__ __align__(128) float s_h[kPairTile];
+    __shared__ __align__(8) uint64_t s_bar;
+    const int64_t p0 = (int64_t) blockIdx.x * kPairTile, p = p0 + threadIdx.x;
+    const int nhere = (int) min((int64_t) kPairTile, npart - p0);
+    const bool bulk = nhere == kPairTile && ((reinterpret_cast<uintptr_t>(pos) | reinterpret_cast<uintptr_t>(hh)) & 15u) == 0;
+    if (bulk) {
+        if (threadIdx.x == 0) {
+            mbar_init(&s_bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            mbar_expect_tx(&s_bar, 16 * kPairTile);
+            bulk_load(s_pos, pos + 3 * p0, 12 * kPairTile, &s_bar);
+            bulk_load(s_h, hh + p0, 4 * kPairTile, &s_bar);
+        }
+        __syncthreads();  // the barrier is initialised before anyone polls it
+        mbar_wait(&s_bar, 0);
+    } else {
+        for (int i = threadIdx.x; i < 3 * nhere; i += kPairTile) s_pos[i] = pos[3 * p0 + i];
+        if ((int) threadIdx.x < nhere) s_h[threadIdx.x] = hh[p];
+        __syncthreads();
+    }
     if ((int) threadIdx.x >= nhere) return;
-    const int64_t p = p0 + threadIdx.x;
     const float px = s_pos[3 * threadIdx.x], py = s_pos[3 * threadIdx.x + 1], pz = s_pos[3 * threadIdx.x + 2];
-    const float h = hh[p];
+    const float h = s_h[threadIdx.x];
     bool any = false;
     pairs_in_group<MODE, 0>(T, T.grid[0], px, py, pz, h, p, count, offsets, particle, any);
     if (!(MODE == 2 && any)) pairs_in_group<MODE, 1>(T, T.grid[1], px, py, pz, h, p, count, offsets, particle, any);
     if (!(MODE == 2 && any)) pairs_in_group<MODE, 2>(T, T.grid[2], px, py, pz, h, p, count, offsets, particle, any);
     if (MODE == 2) flag[p] = any ? 1 : 0;
 }
+
+static unsigned pair_grid(int64_t npart) { return (unsigned) ((npart + kPairTile - 1) / kPairTile); }
 
 // Squared periodic impact parameter of (particle, line): index_table.cpp:44,70-87.
 __device__ __forceinline__ double pair_dr2(const float *__restrict__ pos, int64_t p, const double *__restrict__ cofm,
@@ -495,7 +549,7 @@ static int index_build_impl(fsb_index *idx, double box, const double *cofm, cons
     FSB_TRY(max_list.alloc(sizeof(int64_t), stream));
     FSB_CUDA_TRY(cudaMemsetAsync(count.ptr, 0, sizeof(int32_t) * (nl + 1), stream));
     const int threads = 256;
-    const unsigned pblocks = (unsigned) ((npart + threads - 1) / threads);
+    const unsigned pblocks = pair_grid(npart);
     // list sizes: counted here, or handed in by a caller that already ran fsb_count_pairs on these sightlines
     if (counts_in) {
         if (nlos > 0) FSB_CUDA_TRY(cudaMemcpyAsync(count.ptr, counts_in, sizeof(int32_t) * (size_t) nlos, cudaMemcpyDeviceToDevice, stream));
@@ -637,7 +691,7 @@ extern "C" int fsb_near_lines(double box, const float *pos, const float *h, int6
     FSB_TRY(flag.alloc((size_t) npart, stream));
     FSB_TRY(block_count.alloc(sizeof(int32_t) * (size_t) (nblocks + 1), stream));
     FSB_TRY(block_start.alloc(sizeof(int64_t) * (size_t) (nblocks + 1), stream));
-    count_launch(); k_pairs<2><<<(unsigned) ((npart + 255) / 256), 256, 0, stream>>>(bt.T, pos, h, npart, nullptr, nullptr, nullptr, flag.as<uint8_t>());
+    count_launch(); k_pairs<2><<<pair_grid(npart), kPairTile, 0, stream>>>(bt.T, pos, h, npart, nullptr, nullptr, nullptr, flag.as<uint8_t>());
     count_launch(); k_flag_block_counts<<<(unsigned) nblocks, threads, 0, stream>>>(flag.as<uint8_t>(), npart, block_count.as<int32_t>());
     count_launch(); k_scan_single<int32_t, int64_t><<<1, 1024, 0, stream>>>(block_count.as<int32_t>(), block_start.as<int64_t>(), nblocks, nullptr);
     count_launch(); k_flag_compact<<<(unsigned) nblocks, threads, 0, stream>>>(flag.as<uint8_t>(), npart, block_start.as<int64_t>(), nullptr, out_index);
@@ -666,7 +720,7 @@ extern "C" int fsb_count_pairs(double box, const float *pos, const float *h, int
     FSB_REQUIRE(pos && h, "NULL array");
     BuiltTable bt;
     FSB_TRY(build_line_table(box, cofm, axis, nlos, npart, stream, bt));
-    count_launch(); k_pairs<0><<<(unsigned) ((npart + 255) / 256), 256, 0, stream>>>(bt.T, pos, h, npart, counts, nullptr, nullptr, nullptr);
+    count_launch(); k_pairs<0><<<pair_grid(npart), kPairTile, 0, stream>>>(bt.T, pos, h, npart, counts, nullptr, nullptr, nullptr);
     FSB_CUDA_TRY(cudaGetLastError());
     // the line table is released when this function returns: finish the pass first (also reports a bad axis)
     int32_t h_bad[2] = {0, 0};

@@ -36,6 +36,9 @@ ncumetal) echo "== ncu full k_tau NL=1 (metal lines, mini3 workload)"
 ncuidx) echo "== ncu full index + colden kernels (c2)"
   timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'k_pairs|k_sort|k_colden|k_bin|k_fill|k_cand' -s 0 -c 8 -o $OUT/prof_idx_c2 \
     $B --workload c2_grid256_lya_lyb --steps 1 --warmup 0 --no-cpu-baseline --no-e2e > $OUT/prof_idx_c2.log 2>&1; tail -2 $OUT/prof_idx_c2.log | cut -c1-300;;
+ncucol) echo "== ncu full k_colden (c2, first launch of the extras leg)"
+  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:k_colden -s 0 -c 1 -o $OUT/prof_colden_c2 \
+    $B --workload c2_grid256_lya_lyb --steps 1 --warmup 0 --no-cpu-baseline --no-e2e > $OUT/prof_colden_c2.log 2>&1; tail -2 $OUT/prof_colden_c2.log | cut -c1-300;;
 multi) NG=${NG:-2}; WL=${WL:-c2_grid256_lya_lyb}; echo "== bench $WL on $NG GPUs (strong scaling)"
   timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $NG --workload $WL --steps 3 --warmup 2 > $OUT/bench_${WL}_${NG}gpu.json 2> $OUT/bench_${WL}_${NG}gpu.err; tail -c 2500 $OUT/bench_${WL}_${NG}gpu.json; tail -5 $OUT/bench_${WL}_${NG}gpu.err;;
 testmulti) echo "== pytest multi-GPU"; timeout 900 python -m pytest tests/test_gpu_multi.py -m gpu -x -q -s > $OUT/pytest_gpu_multi.log 2>&1; echo "rc=$?" >> $OUT/pytest_gpu_multi.log; tail -12 $OUT/pytest_gpu_multi.log | cut -c1-600;;

@@ -170,7 +170,7 @@ def test_damped_absorbers_are_masked(fstat):
     assert np.array_equal(tau[keep], dirty[keep])
     for row, centre in ((7, 120), (30, 2)):
         masked = tau[row] != dirty[row]
-        assert masked[centre] and np.all(tau[row][masked] == taueff)
+        assert masked[centre] and np.all(np.abs(tau[row][masked] - taueff) < 1e-12) and np.unique(tau[row][masked]).size == 1
         assert tau[row].max() < 1e6 and masked.sum() > 10
         # the masked region is one periodic run around the peak, bounded by the first pixels at or below taueff + 0.25
         idx = (np.where(masked)[0] - centre + 250) % 500 - 250
