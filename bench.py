@@ -369,7 +369,9 @@ def run_b200(args):
             idx.free()
             n_first.append(int(c1.cpu()[2]))
     n_voigt_step = int(sum(n_all))
-    algo_flop_step = sum(flop_first * a + flop_fused * (b - a) for a, b in zip(n_first, n_all))
+    flop_per_group = [flop_first * a + flop_fused * (b - a) for a, b in zip(n_first, n_all)]
+    algo_flop_step = sum(flop_per_group)
+    route_names = ["near_gauss", "near", "far", "straddle", "slow_or_subsampled"]
     for _ in range(max(args.warmup, 0)):
         step()
     torch.cuda.synchronize()
@@ -552,11 +554,18 @@ def run_b200(args):
                                  "peak = FMA rate measured on this device by fsb_measure_fma_peak in the same precision "
                                  "(MEASURED_PEAKS.json has no FP64/FP32 FMA entry)" % (flop_first, flop_fused, max(flop_ranks), n_tau_launches, tau_s),
                          "reference_equivalent_tflops": FLOP_PER_VOIGT_REFERENCE * n_voigt_step / tau_s / 1e12,
-                         "march_steps_by_route": dict(zip(["near_gauss", "near", "far", "straddle", "slow_or_subsampled"], [int(v) for v in routes])),
+                         "march_steps_by_route": dict(zip(route_names, [int(v) for v in routes])),
                          "tau_share_of_step": tau_s * 1e3 / step_ms,
                          "k_tau_ms_per_rank": [round(v, 3) for v in tau_ms_ranks],
                          "k_tau_ms_per_ion_pass": {groups[gi][0]: round(float(np.mean([m[gi].elapsed_time(m[gi + 1]) for m in ev["ion"]])), 3)
-                                                   for gi in range(len(groups))} if ev["ion"] else None},
+                                                   for gi in range(len(groups))} if ev["ion"] else None,
+                         # the same fraction per launch (this rank's flop and time): hydrogen (two fused lines, long damping
+                         # wings) against the metal ions (one weak line each: a few march steps per particle)
+                         "frac_per_ion_pass": {groups[gi][0]: round(flop_per_group[gi] / (float(np.mean([m[gi].elapsed_time(m[gi + 1]) for m in ev["ion"]])) * 1e-3)
+                                                                     / 1e12 / fma_peak, 4) for gi in range(len(groups))} if ev["ion"] else None,
+                         "march_steps_per_ion_pass": {groups[gi][0]: dict(zip(route_names, [int(v) for v in cvals[gi][4:9]]))
+                                                      for gi in range(len(groups))},
+                         "pairs_per_ion_pass": int(npairs)},
             "index_build": {"bound": "hbm", "ms": index_s * 1e3, "ms_per_rank": [round(v, 3) for v in index_ms_ranks],
                             "algorithmic_bytes": index_bytes, "achieved": index_bytes / index_s / 1e9, "peak": hbm, "unit": "GB/s",
                             "frac": index_bytes / index_s / 1e9 / hbm, "peak_source": hbm_src, "share_of_step": index_s * 1e3 / step_ms,

@@ -7,6 +7,7 @@ fields), which the one-shot boundary in :mod:`_spectra_priv` cannot.
 """
 import ctypes as C
 
+import numpy as np
 import torch
 
 from . import _lib
@@ -126,6 +127,92 @@ class CandidateIndex:
                                            _stream())
         _lib.check(rc, "fsb_assign_cells")
         return cells[:self.npairs]
+
+
+MAX_PAIRS_PER_INDEX = 1 << 30  # one candidate index holds fewer than 2^31 pairs (32-bit list positions); half as a margin
+
+
+def sightline_blocks(counts, max_pairs=MAX_PAIRS_PER_INDEX):
+    """Contiguous sightline blocks [(begin, end), ...] whose candidate-pair totals stay at or below ``max_pairs``
+    (``counts``: pairs per sightline, a host array; a single sightline above the bound gets a block of its own)."""
+    counts = np.asarray(counts, dtype=np.int64)
+    edges, begin, total = [], 0, 0
+    for i, c in enumerate(counts):
+        if i > begin and total + c > max_pairs:
+            edges.append((begin, i))
+            begin, total = i, 0
+        total += int(c)
+    edges.append((begin, len(counts)))
+    return edges
+
+
+class BlockedIndex:
+    """A candidate index for any number of sightlines: one CandidateIndex when the pairs fit (fewer than 2^31),
+    otherwise one per contiguous sightline block found from a count pass (fsb_count_pairs), built and used one after the
+    other so that only one block's lists live in HBM at a time.  Same accumulation calls as CandidateIndex."""
+
+    def __init__(self, box, cofm, axis, pos, h, max_pairs=MAX_PAIRS_PER_INDEX):
+        self.box, self.cofm, self.axis, self.pos, self.h = float(box), cofm, axis, pos, h
+        self.nlos, self.device = cofm.shape[0], pos.device
+        counts = count_pairs(box, pos, h, axis, cofm)
+        host = counts.cpu().numpy()
+        self.npairs = int(host.astype(np.int64).sum())
+        self.blocks = sightline_blocks(host, max_pairs)
+        self._counts = counts
+        self._single = None
+        if len(self.blocks) == 1:
+            self._single = CandidateIndex(box, cofm, axis, pos, h, counts=counts)
+
+    def _each(self):
+        if self._single is not None:
+            yield 0, self.nlos, self._single
+            return
+        for b0, b1 in self.blocks:
+            idx = CandidateIndex(self.box, self.cofm[b0:b1].contiguous(), self.axis[b0:b1].contiguous(), self.pos, self.h,
+                                 counts=self._counts[b0:b1].contiguous())
+            try:
+                yield b0, b1, idx
+            finally:
+                idx.free()
+
+    def compute_tau(self, params, pos, vel, dens, temp, h, out=None, counters=None, push=None, lines=None):
+        if self._single is not None:
+            return self._single.compute_tau(params, pos, vel, dens, temp, h, out=out, counters=counters, push=push, lines=lines)
+        if push is not None or lines is not None or counters is not None:
+            raise ValueError("push, lines and counters need a single index (fewer than 2^31 candidate pairs)")
+        plist = params if isinstance(params, (list, tuple)) else [params]
+        shape = (len(plist), self.nlos, plist[0].nbins)
+        full = out.view(shape) if out is not None else torch.zeros(shape, dtype=torch.float64, device=self.device)
+        for b0, b1, idx in self._each():
+            if len(plist) == 1:
+                idx.compute_tau(plist, pos, vel, dens, temp, h, out=full[:, b0:b1])  # one line: the block's rows are contiguous
+            else:
+                full[:, b0:b1] += idx.compute_tau(plist, pos, vel, dens, temp, h)
+        return full if isinstance(params, (list, tuple)) else full.view(self.nlos, plist[0].nbins)
+
+    def compute_colden(self, params, pos, dens, h, out=None, counters=None):
+        if self._single is not None:
+            return self._single.compute_colden(params, pos, dens, h, out=out, counters=counters)
+        nw = 1 if dens.dim() == 1 else dens.shape[0]
+        shape = (nw, self.nlos, params.nbins)
+        full = out.view(shape) if out is not None else torch.zeros(shape, dtype=torch.float64, device=self.device)
+        for b0, b1, idx in self._each():
+            if nw == 1:
+                idx.compute_colden(params, pos, dens, h, out=full[:, b0:b1])
+            else:
+                full[:, b0:b1] += idx.compute_colden(params, pos, dens, h).view(nw, b1 - b0, params.nbins)
+        return full if dens.dim() == 2 else full.view(self.nlos, params.nbins)
+
+    def free(self):
+        if self._single is not None:
+            self._single.free()
+            self._single = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
 
 
 class _RawCuda:

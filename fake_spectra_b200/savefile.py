@@ -130,3 +130,43 @@ def load_array(savefile, array_name, key):
     if name not in z.files:
         raise KeyError(name)
     return z[name]
+
+
+# ---- the binary spectra file of the reference's C extractor (cextract/main.cpp:247-257, read back by
+# cextract/statistic.c:116-157): a 128-byte header -- redshift f64, box (kpc/h) f64, nbins i32, NumLos i32 and 26 int32
+# of padding -- then the H I optical depths and the H I column densities, float64 [NumLos][nbins] each, native byte order.
+CEXTRACT_HEADER_BYTES = 128
+_CEXTRACT_HEADER = np.dtype([("redshift", "<f8"), ("box", "<f8"), ("nbins", "<i4"), ("numlos", "<i4"), ("pad", "<i4", (26,))])
+assert _CEXTRACT_HEADER.itemsize == CEXTRACT_HEADER_BYTES
+
+
+def write_cextract(path, redshift, box, tau, colden):
+    """Write ``tau`` and ``colden`` (float64 [NumLos, nbins]) in the C extractor's ``*_spectra.dat`` layout."""
+    tau = np.ascontiguousarray(tau, dtype="<f8")
+    colden = np.ascontiguousarray(colden, dtype="<f8")
+    if tau.ndim != 2 or tau.shape != colden.shape:
+        raise ValueError("tau and colden must both have shape (NumLos, nbins)")
+    head = np.zeros(1, dtype=_CEXTRACT_HEADER)
+    head["redshift"], head["box"], head["nbins"], head["numlos"] = redshift, box, tau.shape[1], tau.shape[0]
+    with open(path, "wb") as f:
+        head.tofile(f)
+        tau.tofile(f)
+        colden.tofile(f)
+
+
+def read_cextract(path):
+    """(redshift, box, tau, colden) from a ``*_spectra.dat`` file; the column densities are None for files that stop
+    after the optical depths."""
+    with open(path, "rb") as f:
+        head = np.fromfile(f, dtype=_CEXTRACT_HEADER, count=1)
+        if head.size != 1:
+            raise IOError("%s is shorter than the %d-byte header" % (path, CEXTRACT_HEADER_BYTES))
+        nbins, numlos = int(head["nbins"][0]), int(head["numlos"][0])
+        if nbins <= 0 or numlos < 0:
+            raise IOError("%s: bad header (nbins %d, NumLos %d)" % (path, nbins, numlos))
+        tau = np.fromfile(f, dtype="<f8", count=nbins * numlos)
+        if tau.size != nbins * numlos:
+            raise IOError("%s: optical depths truncated" % path)
+        colden = np.fromfile(f, dtype="<f8", count=nbins * numlos)
+    colden = colden.reshape(numlos, nbins) if colden.size == nbins * numlos else None
+    return float(head["redshift"][0]), float(head["box"][0]), tau.reshape(numlos, nbins), colden

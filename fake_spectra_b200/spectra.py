@@ -47,7 +47,8 @@ class _SegmentEngine:
         self.pos, self.vel, self.dens, self.temp, self.h = up(pos), up(vel), up(elem_den), up(temp), up(hh)
         self.cofm = torch.from_numpy(np.ascontiguousarray(spec._my_cofm)).to(dev)
         self.axis = torch.from_numpy(np.ascontiguousarray(spec._my_axis)).to(dev)
-        self.index = native.CandidateIndex(spec.box, self.cofm, self.axis, self.pos, self.h)
+        # one candidate index, or one per sightline block when the pairs exceed what an index holds (2^31)
+        self.index = native.BlockedIndex(spec.box, self.cofm, self.axis, self.pos, self.h)
         self.cells = None
 
     def tau(self, params_list, out=None, push=None):
@@ -306,6 +307,12 @@ class Spectra:
         if self._sharder.rank == 0 and self.rank == 0 and global_rank == 0:
             sf.save(self, self.savefile)
 
+    def save_cextract(self, path, elem="H", ion=1, line=1215):
+        """Optical depths and column densities of one line in the binary layout of the reference's C extractor
+        (cextract/main.cpp:247-257; savefile.write_cextract)."""
+        from . import savefile as sf
+        sf.write_cextract(path, self.red, self.box, self.get_tau(elem, ion, line), self.get_col_density(elem, ion))
+
     def _really_load_array(self, key, array, array_name):
         """Lazy loading of saved arrays: a one-element placeholder means 'on disc'."""
         if np.size(array[key]) > 1:
@@ -328,21 +335,20 @@ class Spectra:
                                          np.ascontiguousarray(cofm, dtype=np.float64))
 
     def get_mass_frac(self, elem, fn, ind):
-        """Mass fraction of an element for the particles ``ind`` of segment ``fn``."""
+        """Mass fraction (float32, never negative) of ``elem`` for the particles ``ind`` of segment ``fn``: the snapshot's
+        metal table when it has one, primordial hydrogen / helium otherwise; "Z" is the total metallicity
+        (spectra.py:686-710)."""
+        snap = self.snapshot_set
         if elem == "Z":
-            mass_frac = self.snapshot_set.get_data(0, "Metallicity", segment=fn).astype(np.float32)
+            column = snap.get_data(0, "Metallicity", segment=fn)
         else:
-            nelem = self.species.index(elem)
+            which = self.species.index(elem)
             try:
-                mass_frac = (self.snapshot_set.get_data(0, "GFM_Metals", segment=fn).astype(np.float32))[:, nelem]
+                column = snap.get_data(0, "GFM_Metals", segment=fn)[:, which]
             except KeyError:
-                metal_abund = np.array([0.76, 0.24], dtype=np.float32)  # primordial
-                nvalues = self.snapshot_set.get_blocklen(0, "Density", segment=fn)
-                mass_frac = metal_abund[nelem] * np.ones(nvalues, dtype=np.float32)
-        mass_frac = mass_frac[ind]
-        mass_frac[np.where(mass_frac <= 0)] = 0
-        assert mass_frac.dtype == np.float32
-        return mass_frac
+                primordial = (0.76, 0.24)  # no metal table: hydrogen and helium only (IndexError for anything else)
+                column = np.full(snap.get_blocklen(0, "Density", segment=fn), primordial[which], dtype=np.float32)
+        return np.maximum(np.asarray(column, dtype=np.float32)[ind], np.float32(0))
 
     def _filter_particles(self, elem_den, pos, velocity, den):
         _ = (pos, velocity, den)
@@ -376,51 +382,53 @@ class Spectra:
             clipped.append(values)
         return np.float32(table.ion(elem, ion, clipped[0], clipped[1]))
 
-    def _read_particle_data(self, fn, elem, ion, get_tau):
-        """(pos, vel, elem_den, temp, hh, amumass) of the particles of segment ``fn`` near this
-        rank's sightlines, all float32; six times False when there are none."""
-        none = (False, False, False, False, False, False)
-        pos = self.snapshot_set.get_data(0, "Position", segment=fn).astype(np.float32)
-        hh = self.snapshot_set.get_smooth_length(0, segment=fn).astype(np.float32)
-        if self.cofm_final:
-            try:
-                ind = self.part_ind[fn]
-            except KeyError:
-                ind = self.particles_near_lines(pos, hh)
-                self.part_ind[fn] = ind
+    def _near_particles(self, fn, pos, hh):
+        """Indices of the particles of segment ``fn`` whose kernel reaches one of this rank's sightlines (kept per
+        segment once the sightline set is final; this rank's slice of them in particle-sharded mode)."""
+        if self.cofm_final and fn in self.part_ind:
+            ind = self.part_ind[fn]
         else:
             ind = self.particles_near_lines(pos, hh)
+            if self.cofm_final:
+                self.part_ind[fn] = ind
         if self._sharder.mode == "particles" and self._sharder.size > 1:
             ind = ind[self._sharder.my_particles(np.size(ind))]
+        return ind
+
+    def _read_particle_data(self, fn, elem, ion, get_tau):
+        """Host-prepared inputs of the interpolation for segment ``fn`` (the device route is _device_particle_data):
+        (pos, vel, elem_den, temp, hh, amumass), all float32, for the particles near this rank's sightlines; six times
+        False when nothing is left.  Values as the reference forms them (spectra.py:550-617): species density =
+        (n_H rscale) x mass fraction x neutral or ion fraction / atomic mass; velocities and temperatures are only read
+        when something needs them (one-element placeholders otherwise)."""
+        nothing = (False,) * 6
+        snap, gas = self.snapshot_set, self.gasprop
+        f32 = lambda a: np.asarray(a).astype(np.float32)  # noqa: E731
+        pos, hh = f32(snap.get_data(0, "Position", segment=fn)), f32(snap.get_smooth_length(0, segment=fn))
+        ind = self._near_particles(fn, pos, hh)
         if np.size(ind) == 0:
-            return none
-        pos = pos[ind, :]
-        hh = hh[ind]
-        vel = np.zeros(1, dtype=np.float32)
-        temp = np.zeros(1, dtype=np.float32)
-        if get_tau:
-            vel = self.snapshot_set.get_peculiar_velocity(0, segment=fn).astype(np.float32)
-            vel = vel[ind, :]
-        den = self.gasprop.get_code_rhoH(0, segment=fn).astype(np.float32)
-        amumass = self.lines.get_mass(elem) if elem != "Z" else 1
-        den = den[ind]
-        if get_tau or (ion != -1 and elem != 'H'):
-            temp = self.gasprop.get_temp(0, segment=fn).astype(np.float32)
-            temp = temp[ind]
-            temp[np.where(temp <= 0)] = 1
+            return nothing
+        pos, hh = pos[ind, :], hh[ind]
+        placeholder = np.zeros(1, dtype=np.float32)
+        vel = f32(snap.get_peculiar_velocity(0, segment=fn))[ind, :] if get_tau else placeholder
+        den = f32(gas.get_code_rhoH(0, segment=fn))[ind]
+        metal_ion = ion != -1 and not (elem == "H" and ion == 1)
+        temp = placeholder
+        if get_tau or (ion != -1 and elem != "H"):
+            temp = f32(gas.get_temp(0, segment=fn))[ind]
+            temp[temp <= 0] = 1
+        amumass = 1 if elem == "Z" else self.lines.get_mass(elem)
         elem_den = (den * self.rscale) * self.get_mass_frac(elem, fn, ind)
-        if elem == 'H' and ion == 1:
-            elem_den *= (self.gasprop.get_reproc_HI(0, segment=fn)[ind]).astype(np.float32)
-        elif ion != -1:
-            ind2 = self._filter_particles(elem_den, pos, vel, den)
-            if np.size(ind2) == 0:
-                return none
-            temp = temp[ind2]
-            pos = pos[ind2]
-            hh = hh[ind2]
+        if elem == "H" and ion == 1:
+            elem_den *= f32(gas.get_reproc_HI(0, segment=fn)[ind])
+        elif metal_ion:
+            keep = self._filter_particles(elem_den, pos, vel, den)  # particles with mass in the element
+            if np.size(keep) == 0:
+                return nothing
+            pos, hh, temp = pos[keep], hh[keep], temp[keep]
             if get_tau:
-                vel = vel[ind2]
-            elem_den = elem_den[ind2] * self._get_elem_den(elem, ion, den[ind2], temp, ind, ind2)
+                vel = vel[keep]
+            elem_den = elem_den[keep] * self._get_elem_den(elem, ion, den[keep], temp, ind, keep)
         elem_den /= amumass
         return (pos, vel, np.ascontiguousarray(elem_den, dtype=np.float32), temp, hh, amumass)
 
