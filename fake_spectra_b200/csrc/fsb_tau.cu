@@ -264,7 +264,7 @@ __device__ __noinline__ void node_sum_mixed(double xb, double step, const double
             MG[0] = fma(g, wt, MG[0]), MG[1] = fma(g, w1, MG[1]), MG[2] = fma(g, w2, MG[2]), MG[3] = fma(g, w3, MG[3]);
             MW[0] += wt, MW[1] += w1, MW[2] += w2;
             if (__any_sync(kFull, active && s < xu2)) {
-                const double u = s < xu2 ? exp(-s) : 0.0;
+                const double u = s < xu2 ? fast_exp(-s) : 0.0;
                 MU[0] = fma(u, wt, MU[0]), MU[1] = fma(u, w1, MU[1]), MU[2] = fma(u, w2, MU[2]), MU[3] = fma(u, w3, MU[3]);
             }
         }
@@ -389,7 +389,7 @@ __device__ __noinline__ double node_sum_generic(double vouter, const double *__r
         if (ax >= kFarXMin) {
             hval = cd * voigt_far(s, y);
         } else {
-            const double U = s < xu2 ? exp(-s) : 0.0;
+            const double U = s < xu2 ? fast_exp(-s) : 0.0;
             const double G = g_table(ax, tabA);
             const double Pe = fma(fma(fma(p23.y, s, p23.x), s, p01.y), s, p01.x);
             const double A = fma(fma(fma(a23.y, s, a23.x), s, a01.y), s, a01.x);
@@ -571,12 +571,14 @@ __device__ __forceinline__ void march_fast(const double *__restrict__ sl, const 
                         R *= dir ? lud.y : lud.x;
                     } else {
                         const double x1 = xb + step;
-                        U0 = exp(-x1 * x1);
-                        R = exp(-fma(2.0, x1, step) * step);
-                        rec_valid = rec_ok;
+                        U0 = fast_exp(-x1 * x1);
+                        R = fast_exp(-fma(2.0, x1, step) * step);
+                        // the march-step recurrence only pays when another step within reach of the Gaussian follows
+                        // (weak metal lines end inside their first step: one exponential less per particle)
+                        rec_valid = rec_ok && base + 16 < gauss_end;
                         if (rec_valid) {
                             const double delta = (dir ? 16.0 : -16.0) * pix;
-                            rho = exp(-fma(2.0, x1, delta) * delta);
+                            rho = fast_exp(-fma(2.0, x1, delta) * delta);
                         }
                     }
                 } else {
@@ -606,8 +608,8 @@ __device__ __forceinline__ void march_fast(const double *__restrict__ sl, const 
                     } else {
                         if (gauss) {
                             const double x1 = xb + step;
-                            U0 = exp(-x1 * x1);
-                            R = exp(-fma(2.0, x1, step) * step);
+                            U0 = fast_exp(-x1 * x1);
+                            R = fast_exp(-fma(2.0, x1, step) * step);
                         }
                         node_sum_near<NL>(xb, step, sl, tab, U0, R, SF(S_Q), gauss, cubic, lmask, tot);
                     }
@@ -718,8 +720,8 @@ __device__ __noinline__ void march_sub(const double *__restrict__ sl, const doub
                 double U0 = 0, R = 0;
                 if (gauss) {
                     const double x1 = xb + step;
-                    U0 = exp(-x1 * x1);
-                    R = exp(-fma(2.0, x1, step) * step);
+                    U0 = fast_exp(-x1 * x1);
+                    R = fast_exp(-fma(2.0, x1, step) * step);
                 }
                 node_sum_near<NL>(xb, step, sl, tab, U0, R, q, gauss, true, lmask, tot);
             } else {
@@ -852,7 +854,7 @@ __device__ __noinline__ void setup_particle(const InterpConsts &C, double *__res
     SF(S_HALFB) = btherm / 2.;
     SF(S_STEP) = step;
     SF(S_XOFF) = -vhigh * inv_b;
-    SF(S_Q) = exp(-2.0 * step * step);
+    SF(S_Q) = fast_exp(-2.0 * step * step);
     // kernel weights and their moments about xb, in units of btherm: M_n = sum kw_i (i step)^n.  A rolled loop on
     // purpose: this function runs once per batch of particles and its length is paid in instruction fetches.
     double M[5] = {0, 0, 0, 0, 0};
@@ -887,9 +889,9 @@ __device__ __noinline__ void setup_particle(const InterpConsts &C, double *__res
     const double D16 = 16.0 * pix;
     const bool rec_usable = step <= 1.0 && D16 <= 10.0;
     if (rec_usable) {
-        SF(S_K16) = exp(-2.0 * D16 * D16);
-        SF(S_LU16) = exp(2.0 * D16 * step);
-        SF(S_LD16) = exp(-2.0 * D16 * step);
+        SF(S_K16) = fast_exp(-2.0 * D16 * D16);
+        SF(S_LU16) = fast_exp(2.0 * D16 * step);
+        SF(S_LD16) = fast_exp(-2.0 * D16 * step);
     }
     double ymin = 1e300, ymax = 0;
     #pragma unroll

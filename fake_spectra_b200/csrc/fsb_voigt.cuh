@@ -265,6 +265,35 @@ __device__ __forceinline__ void far_polys(double u, double &p1, double &p3, doub
     p5 = fma(10.5, u, 1.0);
 }
 
+// exp(x) for |x| <= 700 (arguments beyond are clamped): Cody-Waite reduction x = k ln2 + r, |r| <= ln2 / 2, the Taylor
+// polynomial of degree 12 (remainder 1.7e-16 relative) and the exponent added into the high word; none of the library
+// routine's special cases (NaN, overflow, denormal results): 24 instructions where exp() inlines 60.  Relative error
+// below 4e-16.  The Gaussian factors of the march and of the per-particle set-up are the only callers.
+__device__ __forceinline__ double fast_exp(double x)
+{
+    x = fmin(fmax(x, -700.0), 700.0);
+    const double magic = 6755399441055744.0;  // 2^52 + 2^51: the sum's low word holds rint(x log2 e)
+    const double t = fma(x, 1.4426950408889634074, magic);
+    const int k = __double2loint(t);
+    const double kd = t - magic;
+    double r = fma(kd, -6.93147180369123816490e-01, x);
+    r = fma(kd, -1.90821492927058770002e-10, r);
+    double p = 2.08767569878680989792e-09;  // 1/12!
+    p = fma(p, r, 2.50521083854417187751e-08);
+    p = fma(p, r, 2.75573192239858906526e-07);
+    p = fma(p, r, 2.75573192239858906526e-06);
+    p = fma(p, r, 2.48015873015873015873e-05);
+    p = fma(p, r, 1.98412698412698412698e-04);
+    p = fma(p, r, 1.38888888888888888889e-03);
+    p = fma(p, r, 8.33333333333333333333e-03);
+    p = fma(p, r, 4.16666666666666666667e-02);
+    p = fma(p, r, 1.66666666666666666667e-01);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+}
+
 // 1/s for a normal positive s (the wing series has s = x^2 >= 256): hardware seed (relative error 2^-23) and
 // two Newton steps, none of the library routine's special-case handling.  Within an ulp of 1/s.
 __device__ __forceinline__ double fast_rcp(double s)
