@@ -637,12 +637,29 @@ def extra_legs(args, w, t, dens, params, native, dev, hbm):
     scale = fstat.mean_flux(tau[0], 0.7)
     torch.cuda.synchronize()
     newton_s = time.perf_counter() - t0
+    fstat.flux_power(tau[0][:256], w["vmax"] if "vmax" in w else 1.0)  # warm-up (tables, attributes)
+    torch.cuda.synchronize()
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    fstat.flux_power(tau[0], w["vmax"] if "vmax" in w else 1.0)
+    p1.record()
+    torch.cuda.synchronize()
+    power_s = p0.elapsed_time(p1) * 1e-3
+    npx = int(tau[0].shape[1])
+    n2f = max(d for d in range(1, int(npx ** 0.5) + 1) if npx % d == 0)
+    n1f = npx // n2f
+    # real FMAs of the two-level transform per sightline: stage A 2 x n2 x (n1/2 + 1) x n1, stage B 4 x (n/2 + 1) x n2
+    power_fma = float(tau[0].shape[0]) * (2.0 * n2f * (n1f // 2 + 1) * n1f + 4.0 * (npx // 2 + 1) * n2f)
+    flux_power = {"kernel": "k_flux_power", "sightlines": int(tau[0].shape[0]), "pixels": npx, "factors": [n1f, n2f], "ms": power_s * 1e3,
+                  "bound": "fp64", "achieved": 2.0 * power_fma / power_s / 1e12, "unit": "TFLOP/s",
+                  "note": "own two-level Fourier sum in shared memory (no FFT library), flux contrast formed on the fly; includes the "
+                          "mean-flux reduction and the host round trip of the call"}
     flux_stats = {"bound": "hbm", "kernel": "k_flux_sums", "pixels": int(flat.numel()), "ms_per_pass": pass_s * 1e3,
                   "algorithmic_bytes": 8.0 * flat.numel(), "achieved": 8.0 * flat.numel() / pass_s / 1e9, "peak": hbm,
                   "unit": "GB/s", "frac": 8.0 * flat.numel() / pass_s / 1e9 / hbm,
                   "mean_flux": sums[0] / max(sums[2], 1),
                   "rescale_to_0.7": {"scale": scale, "ms": newton_s * 1e3, "pixels": int(tau[0].numel())}}
-    return {"colden": colden, "flux_stats": flux_stats}
+    return {"colden": colden, "flux_stats": flux_stats, "flux_power": flux_power}
 
 
 def e2e_leg(args, w, state, groups, params, dens, t, world, rank, dev, dist, barrier, max_over_ranks, pshard, sharder):

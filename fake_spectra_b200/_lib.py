@@ -95,6 +95,7 @@ SIGNATURES = {
     "fsb_prepare_select": (C.c_int, [C.POINTER(Prep), _P, C.c_int64, _P, _P, C.c_int64, _P, C.POINTER(C.c_int64), _P]),
     "fsb_rescale_mean_flux": (C.c_int, [_P, C.c_int64, C.c_double, C.c_double, C.c_double, C.POINTER(C.c_double),
                                         C.POINTER(C.c_int32), _P]),
+    "fsb_flux_power": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_double, _P, _P, _P]),
     "fsb_row_max": (C.c_int, [_P, C.c_int64, C.c_int64, _P, _P]),
     "fsb_flux_sums": (C.c_int, [_P, C.c_int64, C.c_double, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                 C.POINTER(C.c_int64), _P]),

@@ -4,8 +4,8 @@
 Same function names, arguments and return values as the reference.  ``tau`` may be a numpy array
 (uploaded once) or a CUDA tensor that is already resident, e.g. what
 ``native.CandidateIndex.compute_tau`` returns: nothing is copied back but the small results.  The
-reductions, the histogram and the |rfft|^2 accumulation are this library's kernels (fsb_stats.cu);
-the FFT itself is cuFFT through ``torch.fft.rfft``.  There is no CPU fallback.
+reductions, the histogram and the Fourier transform behind the power spectrum are this library's kernels
+(fsb_stats.cu; no FFT library).  There is no CPU fallback.
 
 The 3-D flux power (nbodykit) is outside the hot path and not provided.
 """
@@ -76,14 +76,21 @@ def flux_pdf(tau, nbins=20, mean_flux_desired=None):
 
 
 def _powerspectrum(inarray, axis=-1):
-    """|rfft|^2 / n^2 along ``axis`` (fluxstatistics.py:54-61); device tensors stay on the device."""
+    """|rfft|^2 / n^2 along ``axis`` (fluxstatistics.py:54-61) by this library's own transform (fsb_flux_power: a
+    two-level direct Fourier sum in shared memory, any length); device tensors stay on the device."""
     import torch
-    if isinstance(inarray, torch.Tensor):
-        f = torch.fft.rfft(inarray, dim=axis)
-        return (f.real ** 2 + f.imag ** 2) / inarray.shape[axis] ** 2
+    on_device = isinstance(inarray, torch.Tensor)
     t = _device_tau(inarray)
-    f = torch.fft.rfft(t, dim=axis)
-    return ((f.real ** 2 + f.imag ** 2) / t.shape[axis] ** 2).cpu().numpy()
+    t = t.movedim(axis, -1).contiguous()
+    lead, n = t.shape[:-1], t.shape[-1]
+    rows = t.reshape(-1, n)
+    out = torch.empty((rows.shape[0], n // 2 + 1), dtype=torch.float64, device=t.device)
+    with torch.cuda.device(t.device):
+        rc = _lib.load().fsb_flux_power(C.c_void_p(rows.data_ptr()), rows.shape[0], n, 1, 1.0, 1.0, 1.0, None,
+                                        C.c_void_p(out.data_ptr()), _stream())
+    _lib.check(rc, "fsb_flux_power")
+    out = out.reshape(lead + (n // 2 + 1,)).movedim(-1, axis)
+    return out if on_device else out.cpu().numpy()
 
 
 def _window_function(k, *, R, dv):
@@ -98,16 +105,16 @@ def _flux_power_bins(vmax, npix):
     return kf * 2.0 * math.pi * npix / vmax
 
 
-def flux_power(tau, vmax, spec_res=8, mean_flux_desired=None, window=False, batch=8192):
+def flux_power(tau, vmax, spec_res=8, mean_flux_desired=None, window=False):
     """Mean 1-D flux power spectrum of delta_F = exp(-tau)/<F> - 1 over the sightlines
     (fluxstatistics.py:74-108): returns (k [s/km], P_F [km/s]), both of length npix//2 + 1.
-    Sightlines are processed in batches of ``batch`` to bound the rfft workspace."""
+    One pass over the resident optical depths: the flux contrast is formed inside the transform kernel
+    (fsb_flux_power), nothing of the size of tau is written."""
     import torch
     t = _device_tau(tau)
     if t.dim() != 2:
         raise ValueError("tau must have shape (NumLos, npix)")
     nspec, npix = t.shape
-    lib = _lib.load()
     scale = 1.
     if mean_flux_desired is not None:
         scale = mean_flux(t, mean_flux_desired)
@@ -115,18 +122,11 @@ def flux_power(tau, vmax, spec_res=8, mean_flux_desired=None, window=False, batc
         mean_flux_desired = _mean_exp(t)  # np.mean(np.exp(-tau)), fluxstatistics.py:96
     nk = npix // 2 + 1
     power = torch.zeros(nk, dtype=torch.float64, device=t.device)
-    dflux = torch.empty((min(batch, nspec), npix), dtype=torch.float64, device=t.device)
     with torch.cuda.device(t.device):
-        for s0 in range(0, nspec, batch):
-            s1 = min(nspec, s0 + batch)
-            part = t[s0:s1]
-            out = dflux[: s1 - s0]
-            _lib.check(lib.fsb_delta_flux(C.c_void_p(part.data_ptr()), part.numel(), float(scale), float(mean_flux_desired),
-                                          C.c_void_p(out.data_ptr()), _stream()), "fsb_delta_flux")
-            f = torch.view_as_real(torch.fft.rfft(out, dim=1)).contiguous()
-            # vmax * |F|^2 / npix^2, averaged over all sightlines
-            _lib.check(lib.fsb_power_accumulate(C.c_void_p(f.data_ptr()), s1 - s0, nk, vmax / (1. * npix * npix) / nspec,
-                                                C.c_void_p(power.data_ptr()), _stream()), "fsb_power_accumulate")
+        # vmax * |F|^2 / npix^2, averaged over all sightlines
+        rc = _lib.load().fsb_flux_power(C.c_void_p(t.data_ptr()), nspec, npix, 0, float(scale), float(mean_flux_desired),
+                                        vmax / (1. * npix * npix) / nspec, C.c_void_p(power.data_ptr()), None, _stream())
+    _lib.check(rc, "fsb_flux_power")
     mean_flux_power = power.cpu().numpy()
     kf = _flux_power_bins(vmax, npix)
     if window and spec_res > 0:

@@ -303,6 +303,13 @@ FSB_API int fsb_row_max(const double *a, int64_t nrows, int64_t n, double *out, 
 FSB_API int fsb_flux_pdf(const double *tau, int64_t n, double scale, int32_t nbins, uint64_t *counts, void *stream);
 /* out[i] = exp(-scale tau[i]) / mean_flux - 1 (fluxstatistics.py:100), DEVICE arrays. */
 FSB_API int fsb_delta_flux(const double *tau, int64_t n, double scale, double mean_flux, double *out, void *stream);
+/* The 1-D flux power of fluxstatistics.flux_power (fluxstatistics.py:74-108) without a library FFT: a two-level
+ * direct Fourier sum in shared memory for any pixel count (csrc/fsb_stats.cu).  in: DEVICE [nspec][npix] doubles.
+ * mode 0: x_s = exp(-scale in_s) / mean_flux - 1 formed on the fly; mode 1: x_s = in_s.  per_row == NULL:
+ * power[k] += factor * sum_s |rfft(x_s)[k]|^2 (DEVICE [npix/2 + 1]); else per_row[s][k] = |rfft(x_s)[k]|^2 / npix^2
+ * (fluxstatistics._powerspectrum, fluxstatistics.py:54-61) and power is not touched. */
+FSB_API int fsb_flux_power(const double *in, int64_t nspec, int32_t npix, int32_t mode, double scale, double mean_flux,
+                   double factor, double *power, double *per_row, void *stream);
 /* power[k] += factor * sum_s (re^2 + im^2) of rfft_interleaved[s][k] (nspec x nk complex doubles, DEVICE):
  * the accumulation of fluxstatistics.py:54-61,102-104 for one batch of sightlines. */
 FSB_API int fsb_power_accumulate(const double *rfft_interleaved, int64_t nspec, int32_t nk, double factor, double *power,

@@ -17,6 +17,10 @@ bench) echo "== bench default (c3)"; timeout 1500 $B --steps 3 --warmup 2 > $OUT
 benchq) echo "== bench c3 quick"; timeout 900 $B --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --no-extras > $OUT/bench_c3q.json 2> $OUT/bench_c3q.err; tail -c 1200 $OUT/bench_c3q.json; tail -3 $OUT/bench_c3q.err;;
 c2) echo "== bench c2"; timeout 900 $B --workload c2_grid256_lya_lyb --steps 3 --warmup 3 > $OUT/bench_c2.json 2> $OUT/bench_c2.err; tail -c 1200 $OUT/bench_c2.json; tail -3 $OUT/bench_c2.err;;
 c2q) echo "== bench c2 quick"; timeout 600 $B --workload c2_grid256_lya_lyb --steps 3 --warmup 2 --no-cpu-baseline --no-e2e --no-extras > $OUT/bench_c2q.json 2> $OUT/bench_c2q.err; tail -c 900 $OUT/bench_c2q.json; tail -3 $OUT/bench_c2q.err;;
+c2x) echo "== bench c2 with the extra legs (colden, flux statistics, flux power)"; timeout 600 $B --workload c2_grid256_lya_lyb --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > $OUT/bench_c2x.json 2> $OUT/bench_c2x.err; python -c "
+import json,sys
+d=json.loads(open('$OUT/bench_c2x.json').read().strip().splitlines()[-1])
+print(json.dumps({k:d[k] for k in ('colden','flux_stats','flux_power') if k in d})[:1500])"; tail -3 $OUT/bench_c2x.err;;
 refbench) echo "== bench --impl reference"; timeout 1200 $B --impl reference --steps 3 --warmup 1 > $OUT/bench_reference.json 2> $OUT/bench_reference.err; tail -c 800 $OUT/bench_reference.json;;
 variants) echo "== variants (c2 quick per library)"; for L in fake_spectra_b200/libfsb200*.so; do echo "-- $L"; FSB200_LIB=$PWD/$L timeout 600 $B --workload ${VW:-c2_grid256_lya_lyb} --steps 3 --warmup 2 --no-cpu-baseline --no-e2e --no-extras 2>&1 | tail -1 | python -c "
 import sys,json

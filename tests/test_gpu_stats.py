@@ -111,7 +111,7 @@ def test_flux_pdf_matches_numpy_histogram(fstat, oracle, nbins):
 @pytest.mark.parametrize("npix", [200, 201, 1115])
 def test_flux_power_matches_numpy(fstat, oracle, npix):
     tau = forest(123, npix)
-    kf, power = fstat.flux_power(tau, vmax=1234.5, batch=50)
+    kf, power = fstat.flux_power(tau, vmax=1234.5)
     wk, want = statcases.flux_power_np(tau, vmax=1234.5)
     assert np.array_equal(kf, wk)
     assert np.max(np.abs(power - want)) <= 1e-10 * np.max(want)
@@ -119,6 +119,21 @@ def test_flux_power_matches_numpy(fstat, oracle, npix):
     kf, power = fstat.flux_power(tau, vmax=1234.5, mean_flux_desired=0.66, spec_res=8, window=True)
     wk, want = statcases.flux_power_np(tau, vmax=1234.5, scale=scale, mean_flux_desired=0.66, spec_res=8, window=True)
     assert np.max(np.abs(power / want - 1)) <= 1e-6   # the two Newton runs stop within tol = 1e-5 of each other
+
+
+@pytest.mark.parametrize("npix", [1, 2, 3, 17, 64, 223, 1115, 4460, 8921, 9973])
+def test_own_transform_matches_numpy_rfft(fstat, npix):
+    """|rfft|^2 / n^2 by the two-level direct Fourier sum (fsb_flux_power) against numpy for composite, prime, even,
+    odd and degenerate lengths: C1 (1115 = 5 223), C2 (4460 = 2^2 5 223), C3 (8921 = 11 811), a prime close to the
+    shared-memory limit (9973)."""
+    rng = np.random.default_rng(npix)
+    x = rng.normal(0, 1, (5, npix)) + 0.3
+    want = np.abs(np.fft.rfft(x, axis=1)) ** 2 / npix ** 2
+    got = fstat._powerspectrum(x, axis=1)
+    assert got.shape == want.shape
+    assert np.max(np.abs(got - want)) <= 2e-12 * np.max(want)
+    if npix > 1:
+        assert np.allclose(fstat._powerspectrum(x.T.copy(), axis=0), want.T, rtol=0, atol=2e-12 * np.max(want))
 
 
 def test_flux_power_known_answers_on_device(fstat):
