@@ -197,13 +197,15 @@ k_power_final(const double *__restrict__ partial, int nslabs, int nk, double fac
 //     j = j1 n2 + j2,  k = k1 + n1 k2:
 //     X[k] = sum_j2 W_n2^(j2 k2) { W_n^(j2 k1) sum_j1 x[j1 n2 + j2] W_n1^(j1 k1) },
 // stage A (the braces) is n direct sums of length n1 over the REAL input (only k1 <= n1/2 is summed, the rest follows by
-// conjugation), stage B n/2 + 1 direct sums of length n2.  Cost n (n1 / 2 + n2 / 2) complex multiply-adds per
+// conjugation, two k1 per thread sharing the input value), stage B n/2 + 1 direct sums of length n2 that apply the
+// twiddle W_n^(j2 k1) on the way.  Cost n (n1 / 2 + n2 / 2) complex multiply-adds per
 // sightline -- O(n^1.5) for composite n, the plain O(n^2) sum for prime n -- all of it FP64 FMAs on operands in
 // shared memory, no index permutation passes, no workspace in HBM: 7e11 FMAs for 1e5 sightlines of 8921 pixels
 // (40 ms at the FP64 peak).  One persistent CTA per SM takes sightlines in turn: delta_F = exp(-s tau)/<F> - 1 is
 // formed on the fly (the input of the transform never exists in HBM) and |X|^2 is added to the CTA's own row of
 // partial sums, which k_power_final adds in a fixed order (deterministic).
-// Twiddles: tables in global memory (read through L1), exact to double rounding (sincospi of reduced arguments).
+// Roots of unity: tables built on the device (sincospi of reduced arguments: exact to double rounding); the n1 roots of
+// stage A are staged in shared memory.
 constexpr int kDftThreads = 1024;
 
 __global__ void k_dft_tables(int n, int n1, int n2, double2 *__restrict__ w1, double2 *__restrict__ w2, double2 *__restrict__ tw)
@@ -226,58 +228,67 @@ __device__ __forceinline__ double2 cmul(double2 a, double2 b) { return make_doub
 
 // mode 0: x = exp(-scale in) inv_mean - 1 (in = optical depths); mode 1: x = in.
 // per_row == nullptr: partial[blockIdx.x][k] += |X_k|^2; else per_row[s][k] = |X_k|^2 / n^2.
+// Shared memory: x[n] | I[(n1/2 + 1) n2] (the inner sums of stage A for k1 <= n1/2; the other half is their conjugate)
+// | the n1 roots of unity of stage A.  `flags` bit 0: I lives in global memory (i_global, one slice per CTA), bit 1: the
+// roots are read from global memory (very long prime lengths).
 __global__ void __launch_bounds__(kDftThreads, 1)
 k_flux_power(const double *__restrict__ in, int64_t nspec, int n, int n1, int n2, int mode, double scale, double inv_mean,
              const double2 *__restrict__ w1, const double2 *__restrict__ w2, const double2 *__restrict__ tw,
-             double *__restrict__ partial, double *__restrict__ per_row, double2 *__restrict__ y_global)
+             double *__restrict__ partial, double *__restrict__ per_row, double2 *__restrict__ i_global, int flags)
 {
     extern __shared__ __align__(16) double dft_smem[];
     __shared__ double etab[64];
     stage_exp_table(etab);
-    double *x = dft_smem;                                                   // [n]
-    double2 *Y = y_global ? y_global + (int64_t) blockIdx.x * n : reinterpret_cast<double2 *>(dft_smem + n + (n & 1));  // [n1][n2]
-    const int nk = n / 2 + 1, h1 = n1 / 2;
+    const int nk = n / 2 + 1, h1 = n1 / 2, ni = (h1 + 1) * n2;
+    double *x = dft_smem;  // [n]
+    double2 *I = (flags & 1) ? i_global + (int64_t) blockIdx.x * ni : reinterpret_cast<double2 *>(dft_smem + n + (n & 1));
+    const double2 *wr = w1;
+    if (!(flags & 2)) {
+        double2 *ws = reinterpret_cast<double2 *>(dft_smem + n + (n & 1)) + ((flags & 1) ? 0 : ni);
+        for (int i = threadIdx.x; i < n1; i += kDftThreads) ws[i] = w1[i];
+        wr = ws;
+    }
     const double inv_n2 = 1.0 / ((double) n * (double) n);
     for (int64_t s = blockIdx.x; s < nspec; s += gridDim.x) {
         const double *row = in + s * n;
         for (int i = threadIdx.x; i < n; i += kDftThreads) x[i] = mode == 0 ? exp_nonpos(-scale * row[i], etab) * inv_mean - 1.0 : row[i];
         __syncthreads();
-        // stage A: thread <-> (k1, j2), j2 fastest: consecutive lanes read consecutive x, the twiddle is (nearly) a broadcast
-        for (int item = threadIdx.x; item < (h1 + 1) * n2; item += kDftThreads) {
-            const int k1 = item / n2, j2 = item - k1 * n2;
-            double re = 0, im = 0, re2 = 0, im2 = 0;
-            int idx = 0;
+        // stage A: thread <-> (pair of k1, j2), j2 fastest: consecutive lanes read consecutive x, one x per two outputs,
+        // the roots are (nearly) broadcasts
+        const int npair = (h1 + 2) / 2;
+        for (int item = threadIdx.x; item < npair * n2; item += kDftThreads) {
+            const int kp = item / n2, j2 = item - kp * n2;
+            const int ka = 2 * kp, kb = min(2 * kp + 1, h1);
+            double ar = 0, ai = 0, br = 0, bi = 0;
+            int ia = 0, ib = 0;
             const double *xp = x + j2;
-            int j1 = 0;
-            for (; j1 + 1 < n1; j1 += 2) {
-                const double v0 = xp[(int64_t) j1 * n2], v1 = xp[(int64_t) (j1 + 1) * n2];
-                const double2 a = __ldg(w1 + idx);
-                idx += k1;
-                idx -= idx >= n1 ? n1 : 0;
-                const double2 b = __ldg(w1 + idx);
-                idx += k1;
-                idx -= idx >= n1 ? n1 : 0;
-                re = fma(v0, a.x, re), im = fma(v0, a.y, im);
-                re2 = fma(v1, b.x, re2), im2 = fma(v1, b.y, im2);
+            #pragma unroll 2
+            for (int j1 = 0; j1 < n1; ++j1) {
+                const double v = xp[(int64_t) j1 * n2];
+                const double2 a = wr[ia], b = wr[ib];
+                ar = fma(v, a.x, ar), ai = fma(v, a.y, ai);
+                br = fma(v, b.x, br), bi = fma(v, b.y, bi);
+                ia += ka;
+                ia -= ia >= n1 ? n1 : 0;
+                ib += kb;
+                ib -= ib >= n1 ? n1 : 0;
             }
-            if (j1 < n1) {
-                const double v0 = xp[(int64_t) j1 * n2];
-                const double2 a = __ldg(w1 + idx);
-                re = fma(v0, a.x, re), im = fma(v0, a.y, im);
-            }
-            re += re2, im += im2;
-            Y[k1 * n2 + j2] = cmul(make_double2(re, im), __ldg(tw + k1 * n2 + j2));
-            const int km = n1 - k1;
-            if (k1 != 0 && km != k1) Y[km * n2 + j2] = cmul(make_double2(re, -im), __ldg(tw + km * n2 + j2));
+            I[ka * n2 + j2] = make_double2(ar, ai);
+            I[kb * n2 + j2] = make_double2(br, bi);
         }
         __syncthreads();
         // stage B: thread <-> output k = k1 + n1 k2 <= n / 2
         for (int k = threadIdx.x; k < nk; k += kDftThreads) {
             const int k2 = k / n1, k1 = k - k2 * n1;
+            const bool mirror = k1 > h1;
+            const double2 *ip = I + (mirror ? n1 - k1 : k1) * n2;
+            const double2 *tp = tw + k1 * n2;
             double2 acc = make_double2(0, 0);
             int idx = 0;
             for (int j2 = 0; j2 < n2; ++j2) {
-                const double2 t = cmul(Y[k1 * n2 + j2], __ldg(w2 + idx));
+                double2 v = ip[j2];
+                v.y = mirror ? -v.y : v.y;
+                const double2 t = cmul(cmul(v, __ldg(tp + j2)), __ldg(w2 + idx));
                 acc.x += t.x, acc.y += t.y;
                 idx += k2;
                 idx -= idx >= n2 ? n2 : 0;
@@ -468,15 +479,21 @@ extern "C" int fsb_flux_power(const double *in, int64_t nspec, int32_t npix, int
     FSB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     FSB_CUDA_TRY(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     const int grid = (int) std::min<int64_t>(nspec, sms);
-    const size_t smem_all = sizeof(double) * (size_t) (npix + (npix & 1)) + sizeof(double2) * (size_t) npix;
-    const bool y_in_smem = smem_all + 1024 <= (size_t) smem_max;
-    const size_t smem = y_in_smem ? smem_all : sizeof(double) * (size_t) npix;
-    FSB_REQUIRE(smem + 1024 <= (size_t) smem_max, "too many pixels per sightline for the shared-memory transform");
+    // shared memory: x always; the inner sums and the stage-A roots when they fit
+    const size_t budget = (size_t) smem_max - 1024;
+    const size_t ni = (size_t) (n1 / 2 + 1) * (size_t) n2;
+    size_t smem = sizeof(double) * (size_t) (npix + (npix & 1));
+    FSB_REQUIRE(smem <= budget, "too many pixels per sightline for the shared-memory transform");
+    int flags = 0;
+    if (smem + sizeof(double2) * ni <= budget) smem += sizeof(double2) * ni;
+    else flags |= 1;
+    if (smem + sizeof(double2) * (size_t) n1 <= budget) smem += sizeof(double2) * (size_t) n1;
+    else flags |= 2;
     Scratch w1, w2, tw, partial, yglob;
     FSB_TRY(w1.alloc(sizeof(double2) * (size_t) n1, stream));
     FSB_TRY(w2.alloc(sizeof(double2) * (size_t) n2, stream));
     FSB_TRY(tw.alloc(sizeof(double2) * (size_t) npix, stream));
-    if (!y_in_smem) FSB_TRY(yglob.alloc(sizeof(double2) * (size_t) npix * (size_t) grid, stream));
+    if (flags & 1) FSB_TRY(yglob.alloc(sizeof(double2) * ni * (size_t) grid, stream));
     if (!per_row) {
         FSB_TRY(partial.alloc(sizeof(double) * (size_t) grid * (size_t) nk, stream));
         FSB_CUDA_TRY(cudaMemsetAsync(partial.ptr, 0, sizeof(double) * (size_t) grid * (size_t) nk, stream));
@@ -485,7 +502,7 @@ extern "C" int fsb_flux_power(const double *in, int64_t nspec, int32_t npix, int
     FSB_CUDA_TRY(cudaFuncSetAttribute(k_flux_power, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     count_launch();
     k_flux_power<<<grid, kDftThreads, smem, stream>>>(in, nspec, npix, n1, n2, mode, scale, mode == 0 ? 1.0 / mean_flux : 1.0, w1.as<double2>(),
-                                                      w2.as<double2>(), tw.as<double2>(), partial.as<double>(), per_row, yglob.as<double2>());
+                                                      w2.as<double2>(), tw.as<double2>(), partial.as<double>(), per_row, yglob.as<double2>(), flags);
     FSB_CUDA_TRY(cudaGetLastError());
     if (!per_row) {
         count_launch();

@@ -34,6 +34,9 @@ launches3) echo "== ncu launch list (c3)"
 ncu) echo "== ncu full k_tau (c2, the timed launch)"
   timeout 1200 ncu --set full --clock-control none --import-source on -k regex:k_tau -s 3 -c 1 -o $OUT/prof_tau_c2 \
     $B --workload c2_grid256_lya_lyb --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --no-extras > $OUT/prof_tau_c2.log 2>&1; tail -2 $OUT/prof_tau_c2.log | cut -c1-300;;
+ncu3) echo "== ncu full k_tau, the three launches (HI, CIV, MgII) of one C3 step"
+  timeout 1500 ncu --set full --clock-control none --import-source on -k regex:k_tau -s 4 -c 3 -o $OUT/prof_tau_c3 \
+    $B --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --no-extras > $OUT/prof_tau_c3.log 2>&1; tail -2 $OUT/prof_tau_c3.log | cut -c1-300;;
 ncumetal) echo "== ncu full k_tau NL=1 (metal lines, mini3 workload)"
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_tau -s 8 -c 2 -o $OUT/prof_tau_metal \
     $B --workload mini3_rand6k_3axes_4lines --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --no-extras > $OUT/prof_tau_metal.log 2>&1; tail -2 $OUT/prof_tau_metal.log | cut -c1-300;;

@@ -143,6 +143,31 @@ def test_cold_comb_and_dense_wings(priv, oracle):
     assert same_zero and rel < TOL, rel
 
 
+@pytest.mark.parametrize("gamma_zero", [False, True])
+def test_zero_density_runaway_velocities_and_pixel_centres(priv, oracle, gamma_zero):
+    """particles without mass (add 0, then stop at once), peculiar velocities that carry velfac*pos + vel
+    below 0 and beyond vbox (negative zmax, modulo wrap, absorption.cpp:246-259), and particles sitting exactly on a
+    pixel edge with zero velocity (the quadrature's central node is then at x == 0 exactly: Faddeeva.cpp:681-683);
+    with and without damping (gamma == 0: the y == 0 branch, :684-686)."""
+    d = cases.random_case(nside=12, nlos=36, axis="cycle", seed=11)
+    p = cases.params(d, gamma_zero=gamma_zero)
+    vbox = p["box"] * p["velfac"]
+    d["dens"][::4] = 0.0
+    d["vel"][1::4] -= np.float32(1.7 * vbox)
+    d["vel"][2::4] += np.float32(2.3 * vbox)
+    bintov = vbox / p["nbins"]
+    k = np.arange(3, d["pos"].shape[0], 8)
+    d["vel"][k] = 0.0
+    d["pos"][k] = (np.round(d["pos"][k] * p["velfac"] / bintov) * bintov / p["velfac"]).astype(np.float32)
+    want = oracle.compute_tau(**p, pos=d["pos"], vel=d["vel"], dens=d["dens"], temp=d["temp"], h=d["h"],
+                              axis=d["axis"], cofm=d["cofm"])
+    rel, same_zero = cases.rel_err(interp(priv, 1, p, d), want)
+    assert same_zero and rel < TOL, rel
+    want = oracle.compute_colden(**p, pos=d["pos"], dens=d["dens"], h=d["h"], axis=d["axis"], cofm=d["cofm"])
+    rel, same_zero = cases.rel_err(interp(priv, 0, p, d), want)
+    assert same_zero and rel < TOL, rel
+
+
 def test_wide_kernels_cold_gas(priv, oracle):
     """Kernels much wider than the thermal width (300-3000 K gas, 0.25 km/s pixels): the seven
     quadrature nodes of one pixel reach from the line core to beyond |x| = 16, and very dense
