@@ -683,8 +683,25 @@ def e2e_leg(args, w, state, groups, params, dens, t, world, rank, dev, dist, bar
     maxl = max(len(lns) for _, lns in groups)
     seg = UNSEGMENTED if (world > 1 and not pshard) else 0
 
-    def calls(arr, dn, outbuf):
+    def calls(arr, dn, outbuf, one_call=False):
         res = []
+        if one_call and len(groups) > 1:
+            # every ion from one upload and one candidate index (extra_ions -> fsb_particle_interpolate_ions_host)
+            ion0, lns0 = groups[0]
+            _, lam, gam, fosc = LINES[lns0[0]]
+            others = [(dn[ion], IONS[ion][0], [LINES[ln][1:] for ln in lns]) for ion, lns in groups[1:]]
+            nl_all = sum(len(lns) for _, lns in groups)
+            o = None if outbuf is None else outbuf[:nl_all * nloc * nbins]
+            r = _spectra_priv._Particle_Interpolate(
+                1, nbins, w["kernel"], w["box"], w["velfac"], w["atime"], lam, gam, fosc, IONS[ion0][0], TAUTAIL,
+                arr["pos"], arr["vel"], dn[ion0], arr["temp"], arr["h"], arr["axis"], arr["cofm"], voigt=vg, precision=prec,
+                out=o, extra_lines=[LINES[ln][1:] for ln in lns0[1:]], seg_pairs=seg, extra_ions=others)
+            r = r.reshape(nl_all, nloc, nbins)
+            first = 0
+            for _, lns in groups:
+                res.append(float(np.mean(r[first][: min(64, nloc)])))
+                first += len(lns)
+            return res
         for ion, lns in groups:
             _, lam, gam, fosc = LINES[lns[0]]
             extra = [LINES[ln][1:] for ln in lns[1:]]
@@ -726,7 +743,9 @@ def e2e_leg(args, w, state, groups, params, dens, t, world, rank, dev, dist, bar
 
     pin = {k: torch.from_numpy(host[k]).pin_memory() for k in host}
     pdens = {ion: torch.from_numpy(hdens[ion]).pin_memory() for ion in hdens}
-    hout = torch.empty(maxl * nloc * nbins if not pshard else len(w["lines"]) * L * nbins, dtype=torch.float64).pin_memory()
+    one_call = (not pshard) and len(groups) > 1
+    hout = torch.empty((len(w["lines"]) if one_call else maxl) * nloc * nbins if not pshard else len(w["lines"]) * L * nbins,
+                       dtype=torch.float64).pin_memory()
     if pshard:
         el, chk = run(lambda: pshard_step(pin, pdens[groups[0][0]], hout))
         ncalls = 1
@@ -734,17 +753,26 @@ def e2e_leg(args, w, state, groups, params, dens, t, world, rank, dev, dist, bar
         pa = {k: pin[k].numpy() for k in pin}
         pd = {ion: pdens[ion].numpy() for ion in pdens}
         ho = hout.numpy()
-        el, chk = run(lambda: calls(pa, pd, ho))
-        ncalls = len(groups)
+        el, chk = run(lambda: calls(pa, pd, ho, one_call))
+        ncalls = 1 if one_call else len(groups)
+        if one_call:  # the same through one call per ion (particles uploaded and the index built once per ion)
+            el_ion, chk_ion = run(lambda: calls(pa, pd, ho))
     h2d = ncalls * sum(int(host[k].nbytes) for k in host) + (0 if pshard else 0)
     h2d += sum(int(hdens[ion].nbytes) for ion, _ in groups) if not pshard else int(hdens[groups[0][0]].nbytes)
     d2h = len(w["lines"]) * (L if pshard else nloc) * nbins * 8
     e2e = {"value": L * esteps / el, "unit": "spectra/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
            "ms_per_step": el / esteps * 1e3, "steps": esteps, "buffers": "page-locked",
            "call": ("pinned host -> device, native.CandidateIndex + compute_tau, NCCL sum, device -> pinned host" if pshard else
-                    "%d x _spectra_priv._Particle_Interpolate(host buffers, extra_lines) -> fsb_particle_interpolate_multi_host, "
-                    "one call per ion%s" % (ncalls, "" if world == 1 else ", this rank's block of sightlines")),
+                    ("1 x _spectra_priv._Particle_Interpolate(host buffers, extra_lines, extra_ions) -> fsb_particle_interpolate_ions_host: "
+                     "every line of every ion from one upload and one candidate index%s" if one_call else
+                     "%d x _spectra_priv._Particle_Interpolate(host buffers, extra_lines) -> fsb_particle_interpolate_multi_host, "
+                     "one call per ion%%s" % ncalls) % ("" if world == 1 else ", this rank's block of sightlines")),
            "mean_tau_check": chk}
+    if not pshard and one_call:
+        e2e["one_call_per_ion"] = {"value": L * esteps / el_ion, "unit": "spectra/s", "ms_per_step": el_ion / esteps * 1e3,
+                                   "h2d_bytes_per_step": int(len(groups) * sum(int(host[k].nbytes) for k in host)
+                                                             + sum(int(hdens[ion].nbytes) for ion, _ in groups)),
+                                   "buffers": "page-locked", "mean_tau_check": chk_ion}
     del pin, pdens, hout
     if not pshard:
         el2, chk2 = run(lambda: calls(host, hdens, None))

@@ -82,6 +82,8 @@ SIGNATURES = {
                                                 C.c_int32, _P]),
     "fsb_particle_interpolate_multi_host": (C.c_int, [C.c_int32, C.POINTER(Params), C.c_int32, _P, _P, _P, _P, _P,
                                                       C.c_int64, _P, _P, C.c_int32, _P]),
+    "fsb_particle_interpolate_ions_host": (C.c_int, [C.POINTER(Params), C.c_int32, _P, C.c_int32, _P, _P, _P, _P, _P,
+                                                     C.c_int64, _P, _P, C.c_int32, _P]),
     "fsb_near_lines": (C.c_int, [C.c_double, _P, _P, C.c_int64, _P, _P, C.c_int32, _P, C.POINTER(C.c_int64), _P]),
     "fsb_near_lines_host": (C.c_int, [C.c_double, _P, _P, C.c_int64, _P, _P, C.c_int32, _P, C.POINTER(C.c_int64)]),
     "fsb_count_pairs": (C.c_int, [C.c_double, _P, _P, C.c_int64, _P, _P, C.c_int32, _P, _P]),

@@ -39,7 +39,7 @@ def _is_f32(a):
 
 def _Particle_Interpolate(compute_tau, nbins, kernel, box, velfac, atime, lambda_cm, gamma, fosc, amumass, tautail,
                           pos, vel, dens, temp, h, axis, cofm, precision=None, voigt=None, out=None,
-                          extra_lines=(), extra_weights=(), seg_pairs=0):
+                          extra_lines=(), extra_weights=(), seg_pairs=0, extra_ions=()):
     """Optical depth (compute_tau != 0) or column density on every sightline.
 
     Arguments, order and units as py_module.cpp:115; returns a new float64 array [NumLos, nbins].
@@ -50,7 +50,9 @@ def _Particle_Interpolate(compute_tau, nbins, kernel, box, velfac, atime, lambda
     same ion computed from the same upload and candidate index, result [1+len, NumLos, nbins];
     ``extra_weights`` (column density only) = further float32 density-like arrays interpolated in
     the same geometry pass, result [1+len, NumLos, nbins]; ``seg_pairs`` = candidate pairs per work item
-    (0 = automatic; see fsb_params.seg_pairs)."""
+    (0 = automatic; see fsb_params.seg_pairs); ``extra_ions`` (optical depths only) = [(dens, amumass, [(lambda_cm,
+    gamma, fosc), ...]), ...]: further ions of the same particles (their species densities, masses and lines) computed
+    from the same upload and the same candidate index; their lines follow the first ion's in the result."""
     for a in (pos, vel, dens, temp, h):
         if not _is_f32(a):
             raise TypeError("One of the data arrays does not have 32-bit float type")
@@ -82,6 +84,20 @@ def _Particle_Interpolate(compute_tau, nbins, kernel, box, velfac, atime, lambda
     vgt = DEFAULT_VOIGT if voigt is None else voigt
     plist = [p] + [_lib.make_params(nbins, kernel, box, velfac, atime, lam, gam, fo, amumass, tautail, precision=prec,
                                     voigt=vgt, seg_pairs=seg_pairs) for (lam, gam, fo) in extra_lines]
+    line_ion = [0] * len(plist)
+    if extra_ions:
+        if not compute_tau or extra_weights:
+            raise ValueError("extra_ions only apply to optical depths")
+        columns = [dens]
+        for k, (idens, iamu, ilines) in enumerate(extra_ions):
+            if not _is_f32(idens) or idens.shape != (npart,):
+                raise TypeError("ion densities must be float32 arrays as long as pos")
+            columns.append(idens)
+            for (lam, gam, fo) in ilines:
+                plist.append(_lib.make_params(nbins, kernel, box, velfac, atime, lam, gam, fo, iamu, tautail, precision=prec,
+                                              voigt=vgt, seg_pairs=seg_pairs))
+                line_ion.append(k + 1)
+        columns = [np.ascontiguousarray(c) for c in columns]  # used where they lie: no stacked copy
     ncols = len(plist) if compute_tau or not extra_weights else 1 + len(extra_weights)
     shape = (numlos, int(nbins)) if ncols == 1 else (ncols, numlos, int(nbins))
     if out is None:
@@ -95,8 +111,14 @@ def _Particle_Interpolate(compute_tau, nbins, kernel, box, velfac, atime, lambda
         pvel, ptemp = _ptr(vel), _ptr(temp)
     else:
         pvel = ptemp = None
-    rc = lib.fsb_particle_interpolate_multi_host(1 if compute_tau else 0, parr, ncols, _ptr(pos), pvel, _ptr(dens),
-                                                 ptemp, _ptr(h), npart, _ptr(axis), _ptr(cofm), numlos, _ptr(out))
+    if extra_ions:
+        ions = np.asarray(line_ion, dtype=np.int32)
+        cols = (C.c_void_p * len(columns))(*[c.ctypes.data for c in columns])
+        rc = lib.fsb_particle_interpolate_ions_host(parr, ncols, _ptr(ions), len(columns), _ptr(pos), pvel, cols,
+                                                    ptemp, _ptr(h), npart, _ptr(axis), _ptr(cofm), numlos, _ptr(out))
+    else:
+        rc = lib.fsb_particle_interpolate_multi_host(1 if compute_tau else 0, parr, ncols, _ptr(pos), pvel, _ptr(dens),
+                                                     ptemp, _ptr(h), npart, _ptr(axis), _ptr(cofm), numlos, _ptr(out))
     _lib.check(rc, "_Particle_Interpolate")
     return out.reshape(shape)
 

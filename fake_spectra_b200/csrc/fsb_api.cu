@@ -356,13 +356,26 @@ struct OwnedStream {
 };
 }  // namespace
 
-extern "C" int fsb_particle_interpolate_multi_host(int32_t compute_tau, const fsb_params *p, int32_t nlines,
-                                                   const float *pos, const float *vel, const float *dens,
-                                                   const float *temp, const float *h, int64_t npart, const int32_t *axis,
-                                                   const double *cofm, int32_t nlos, double *out)
+namespace {
+// The host entries: one upload of the particle arrays and one candidate index serve every line.  line_ion == NULL: all
+// lines belong to one ion (dens is one column; or, for column density, nlines weight columns).  Otherwise (tau only)
+// dens_columns[nions] point at one host array of npart densities per ion (wherever the caller holds them: nothing is
+// gathered on the host) and line_ion[i] names the column of line i; lines of one ion must be consecutive.
+int interpolate_host(int32_t compute_tau, const fsb_params *p, int32_t nlines, const int32_t *line_ion, int32_t nions,
+                     const float *pos, const float *vel, const float *dens, const float *const *dens_columns, const float *temp,
+                     const float *h, int64_t npart, const int32_t *axis, const double *cofm, int32_t nlos, double *out)
 {
     FSB_REQUIRE(p != nullptr && out != nullptr, "params/out NULL");
     FSB_REQUIRE(nlines >= 1, "nlines must be >= 1");
+    if (line_ion) {
+        FSB_REQUIRE(compute_tau && nions >= 1, "several ions: optical depths only");
+        FSB_REQUIRE(p[0].kernel != FSB_KERNEL_VORONOI, "several ions in one call: not for the Voronoi kernel");
+        for (int32_t i = 0; i < nlines; ++i) {
+            FSB_REQUIRE(line_ion[i] >= 0 && line_ion[i] < nions, "line_ion out of range");
+            FSB_REQUIRE(i == 0 || line_ion[i] >= line_ion[i - 1], "lines of one ion must be consecutive (ascending line_ion)");
+            FSB_REQUIRE(p[i].nbins == p[0].nbins && p[i].box == p[0].box && p[i].kernel == p[0].kernel, "lines must share nbins, box and kernel");
+        }
+    }
     FSB_REQUIRE(nlos >= 0 && npart >= 0 && p[0].nbins > 0, "bad sizes");
     FSB_TRY(retain_pool_memory());
     // own streams (declared first: destroyed after the buffers that are freed on them): compute, and a copy
@@ -388,7 +401,15 @@ extern "C" int fsb_particle_interpolate_multi_host(int32_t compute_tau, const fs
     FSB_TRY(daxis.upload(axis, sizeof(int32_t) * nl, s));
     FSB_TRY(dcofm.upload(cofm, sizeof(double) * 3 * nl, s));
     // column density: nlines counts weight columns, dens is [nlines][npart]
-    FSB_TRY(ddens.upload(dens, sizeof(float) * np * (compute_tau ? 1 : (size_t) nlines), copy.s));
+    if (line_ion) {
+        FSB_TRY(ddens.upload(nullptr, sizeof(float) * np * (size_t) nions, copy.s));
+        for (int32_t k = 0; k < nions && np > 0; ++k) {
+            FSB_REQUIRE(dens_columns && dens_columns[k], "NULL density column");
+            FSB_CUDA_TRY(cudaMemcpyAsync((float *) ddens.ptr + (size_t) k * np, dens_columns[k], sizeof(float) * np, cudaMemcpyHostToDevice, copy.s));
+        }
+    } else {
+        FSB_TRY(ddens.upload(dens, sizeof(float) * np * (compute_tau ? 1 : (size_t) nlines), copy.s));
+    }
     if (compute_tau) {
         FSB_REQUIRE(npart == 0 || (vel && temp), "vel/temp NULL with compute_tau");
         FSB_TRY(dvel.upload(vel, sizeof(float) * 3 * np, copy.s));
@@ -428,9 +449,18 @@ extern "C" int fsb_particle_interpolate_multi_host(int32_t compute_tau, const fs
         }
         if (rc == FSB_OK) {
             if (compute_tau) {
-                rc = compute_tau_multi_impl(idx, p, nlines, (const float *) dpos.ptr, (const float *) dvel.ptr,
-                                            (const float *) ddens.ptr, (const float *) dtemp.ptr, (const float *) dh.ptr,
-                                            (double *) dout.ptr, nullptr, s, out, copy.s);
+                // one pass per ion: its lines are consecutive, its density column follows line_ion
+                for (int32_t l0 = 0; l0 < nlines && rc == FSB_OK;) {
+                    int32_t l1 = nlines;
+                    if (line_ion)
+                        for (l1 = l0 + 1; l1 < nlines && line_ion[l1] == line_ion[l0]; ++l1) {}
+                    const size_t off = (size_t) l0 * nl * (size_t) p[0].nbins;
+                    rc = compute_tau_multi_impl(idx, p + l0, l1 - l0, (const float *) dpos.ptr, (const float *) dvel.ptr,
+                                                (const float *) ddens.ptr + (line_ion ? (size_t) line_ion[l0] * np : 0),
+                                                (const float *) dtemp.ptr, (const float *) dh.ptr, (double *) dout.ptr + off, nullptr, s,
+                                                out + off, copy.s);
+                    l0 = l1;
+                }
                 delivered = rc == FSB_OK;
             } else {
                 rc = fsb_compute_colden(idx, p, (const float *) dpos.ptr, (const float *) ddens.ptr, nlines,
@@ -450,6 +480,24 @@ extern "C" int fsb_particle_interpolate_multi_host(int32_t compute_tau, const fs
         rc = FSB_ECUDA;
     }
     return rc;
+}
+}  // namespace
+
+extern "C" int fsb_particle_interpolate_multi_host(int32_t compute_tau, const fsb_params *p, int32_t nlines,
+                                                   const float *pos, const float *vel, const float *dens,
+                                                   const float *temp, const float *h, int64_t npart, const int32_t *axis,
+                                                   const double *cofm, int32_t nlos, double *out)
+{
+    return interpolate_host(compute_tau, p, nlines, nullptr, 1, pos, vel, dens, nullptr, temp, h, npart, axis, cofm, nlos, out);
+}
+
+extern "C" int fsb_particle_interpolate_ions_host(const fsb_params *p, int32_t nlines, const int32_t *line_ion, int32_t nions,
+                                                  const float *pos, const float *vel, const float *const *dens_columns,
+                                                  const float *temp, const float *h, int64_t npart, const int32_t *axis,
+                                                  const double *cofm, int32_t nlos, double *out)
+{
+    FSB_REQUIRE(line_ion != nullptr && dens_columns != nullptr, "line_ion / dens_columns NULL");
+    return interpolate_host(1, p, nlines, line_ion, nions, pos, vel, nullptr, dens_columns, temp, h, npart, axis, cofm, nlos, out);
 }
 
 extern "C" int fsb_particle_interpolate_host(int32_t compute_tau, const fsb_params *p, const float *pos, const float *vel,

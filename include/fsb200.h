@@ -191,6 +191,15 @@ FSB_API int fsb_particle_interpolate_multi_host(int32_t compute_tau, const fsb_p
                                         const float *pos, const float *vel, const float *dens, const float *temp,
                                         const float *h, int64_t npart, const int32_t *axis, const double *cofm,
                                         int32_t nlos, double *out);
+/* Optical depths of several IONS from one upload and one index (HOST pointers): what Spectra.get_tau does for H I, C IV,
+ * Mg II ... as one boundary call per ion and line (spectra.py:801-831), each re-reading the particles and rebuilding the
+ * index (part_int.cpp:22).  dens_columns[nions]: one HOST array of npart species densities per ion (used where they
+ * lie); line_ion[i] (ascending) names the column of line i, p[i].amumass the ion's mass; out[nlines][nlos*nbins].  Not
+ * for the Voronoi kernel. */
+FSB_API int fsb_particle_interpolate_ions_host(const fsb_params *p, int32_t nlines, const int32_t *line_ion, int32_t nions,
+                                       const float *pos, const float *vel, const float *const *dens_columns, const float *temp,
+                                       const float *h, int64_t npart, const int32_t *axis, const double *cofm,
+                                       int32_t nlos, double *out);
 
 /* ---- particle filter (replaces Py_near_lines, py_module.cpp:25-99) ------------------------- */
 /* Ascending indices of particles with at least one candidate sightline.  out_index must hold

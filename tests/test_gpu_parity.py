@@ -313,6 +313,42 @@ def test_fused_lines(torch_cuda):
         assert same_zero and rel < 1e-13
 
 
+def test_several_ions_in_one_host_call(priv, oracle):
+    """extra_ions (fsb_particle_interpolate_ions_host): H I Lya + Lyb, C IV and Mg II from one upload and one candidate
+    index equal one boundary call per ion bit for bit, and the CPU oracle to 1e-10."""
+    d = cases.random_case(nside=14, nlos=40, axis="cycle", seed=29)
+    rng = np.random.default_rng(4)
+    dens = {"HI": d["dens"], "CIV": (d["dens"] * 1e-5 * rng.random(d["dens"].size)).astype(np.float32),
+            "MgII": (d["dens"] * 3e-6 * rng.random(d["dens"].size)).astype(np.float32)}
+    groups = [("HI", ["HI1215", "HI1025"]), ("CIV", ["CIV1548"]), ("MgII", ["MgII2796"])]
+    pp = {ln: cases.params(d, line=ln) for _, lns in groups for ln in lns}
+    seg = 1 << 30
+
+    def call(ion, lns, **kw):
+        p = pp[lns[0]]
+        extra = [(pp[ln]["lambda_cm"], pp[ln]["gamma"], pp[ln]["fosc"]) for ln in lns[1:]]
+        dd = dict(d, dens=dens[ion])
+        return interp(priv, 1, p, dd, extra_lines=extra, seg_pairs=seg, **kw).reshape(-1, d["cofm"].shape[0], p["nbins"])
+
+    others = [(dens[ion], pp[lns[0]]["amumass"], [(pp[ln]["lambda_cm"], pp[ln]["gamma"], pp[ln]["fosc"]) for ln in lns])
+              for ion, lns in groups[1:]]
+    allin = call("HI", groups[0][1], extra_ions=others)
+    assert allin.shape[0] == 4
+    row = 0
+    for ion, lns in groups:
+        sep = call(ion, lns)
+        for k, ln in enumerate(lns):
+            assert np.array_equal(allin[row], sep[k]), (ion, ln)
+            p = pp[ln]
+            want = oracle.compute_tau(**p, pos=d["pos"], vel=d["vel"], dens=dens[ion], temp=d["temp"], h=d["h"],
+                                      axis=d["axis"], cofm=d["cofm"])
+            rel, same_zero = cases.rel_err(allin[row], want)
+            assert same_zero and rel < TOL, (ion, ln, rel)
+            row += 1
+    with pytest.raises(ValueError):
+        interp(priv, 0, pp["HI1215"], d, extra_ions=others)
+
+
 def test_empty_inputs(priv):
     d = cases.random_case(nside=8, nlos=5, axis=1)
     p = cases.params(d)
