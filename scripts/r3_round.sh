@@ -50,8 +50,8 @@ multi) NG=${NG:-2}; WL=${WL:-c2_grid256_lya_lyb}; echo "== bench $WL on $NG GPUs
   timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $NG --workload $WL --steps 3 --warmup 2 > $OUT/bench_${WL}_${NG}gpu.json 2> $OUT/bench_${WL}_${NG}gpu.err; tail -c 2500 $OUT/bench_${WL}_${NG}gpu.json; tail -5 $OUT/bench_${WL}_${NG}gpu.err;;
 testmulti) echo "== pytest multi-GPU"; timeout 900 python -m pytest tests/test_gpu_multi.py -m gpu -x -q -s > $OUT/pytest_gpu_multi.log 2>&1; echo "rc=$?" >> $OUT/pytest_gpu_multi.log; tail -12 $OUT/pytest_gpu_multi.log | cut -c1-600;;
 sanitizer) echo "== compute-sanitizer"
-  timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "golden or tiny or edge or voronoi" > $OUT/sanitizer_memcheck.log 2>&1; echo "rc=$?" >> $OUT/sanitizer_memcheck.log; tail -4 $OUT/sanitizer_memcheck.log
-  timeout 1500 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "golden or tiny" > $OUT/sanitizer_racecheck.log 2>&1; echo "rc=$?" >> $OUT/sanitizer_racecheck.log; tail -4 $OUT/sanitizer_racecheck.log;;
+  timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py tests/test_gpu_prep.py tests/test_gpu_stats.py tests/test_gpu_blocks.py -m gpu -x -q -k "golden or tiny or empty or voronoi or several_ions or prep_matches or plateau or own_transform or damped or blocked or zero_density" > $OUT/sanitizer_memcheck.log 2>&1; echo "rc=$?" >> $OUT/sanitizer_memcheck.log; tail -4 $OUT/sanitizer_memcheck.log
+  timeout 900 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py tests/test_gpu_stats.py -m gpu -x -q -k "candidate_lists_golden or tiny or own_transform or count_pairs" > $OUT/sanitizer_racecheck.log 2>&1; echo "rc=$?" >> $OUT/sanitizer_racecheck.log; tail -4 $OUT/sanitizer_racecheck.log;;
 esac
 done
 ls -la $OUT
