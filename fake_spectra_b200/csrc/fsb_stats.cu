@@ -231,23 +231,25 @@ __device__ __forceinline__ double2 cmul(double2 a, double2 b) { return make_doub
 // Shared memory: x[n] | I[(n1/2 + 1) n2] (the inner sums of stage A for k1 <= n1/2; the other half is their conjugate)
 // | the n1 roots of unity of stage A.  `flags` bit 0: I lives in global memory (i_global, one slice per CTA), bit 1: the
 // roots are read from global memory (very long prime lengths).
+template <bool I_SMEM, bool W_SMEM>
 __global__ void __launch_bounds__(kDftThreads, 1)
 k_flux_power(const double *__restrict__ in, int64_t nspec, int n, int n1, int n2, int mode, double scale, double inv_mean,
              const double2 *__restrict__ w1, const double2 *__restrict__ w2, const double2 *__restrict__ tw,
-             double *__restrict__ partial, double *__restrict__ per_row, double2 *__restrict__ i_global, int flags)
+             double *__restrict__ partial, double *__restrict__ per_row, double2 *__restrict__ i_global)
 {
     extern __shared__ __align__(16) double dft_smem[];
     __shared__ double etab[64];
     stage_exp_table(etab);
     const int nk = n / 2 + 1, h1 = n1 / 2, ni = (h1 + 1) * n2;
     double *x = dft_smem;  // [n]
-    double2 *I = (flags & 1) ? i_global + (int64_t) blockIdx.x * ni : reinterpret_cast<double2 *>(dft_smem + n + (n & 1));
-    const double2 *wr = w1;
-    if (!(flags & 2)) {
-        double2 *ws = reinterpret_cast<double2 *>(dft_smem + n + (n & 1)) + ((flags & 1) ? 0 : ni);
-        for (int i = threadIdx.x; i < n1; i += kDftThreads) ws[i] = w1[i];
-        wr = ws;
-    }
+    // the two placements are template parameters so that the common case compiles to shared-memory loads (a pointer
+    // that may be either address space makes every access a generic load: 25 % of the stall samples when it was one)
+    double2 *const i_smem = reinterpret_cast<double2 *>(dft_smem + n + (n & 1));
+    double2 *const w_smem = i_smem + (I_SMEM ? ni : 0);
+    double2 *const I = I_SMEM ? i_smem : i_global + (int64_t) blockIdx.x * ni;
+    if (W_SMEM)
+        for (int i = threadIdx.x; i < n1; i += kDftThreads) w_smem[i] = w1[i];
+    const double2 *const wr = W_SMEM ? w_smem : w1;
     const double inv_n2 = 1.0 / ((double) n * (double) n);
     for (int64_t s = blockIdx.x; s < nspec; s += gridDim.x) {
         const double *row = in + s * n;
@@ -263,8 +265,8 @@ k_flux_power(const double *__restrict__ in, int64_t nspec, int n, int n1, int n2
             int ia = 0, ib = 0;
             const double *xp = x + j2;
             #pragma unroll 2
-            for (int j1 = 0; j1 < n1; ++j1) {
-                const double v = xp[(int64_t) j1 * n2];
+            for (int j1 = 0; j1 < n1; ++j1, xp += n2) {
+                const double v = *xp;
                 const double2 a = wr[ia], b = wr[ib];
                 ar = fma(v, a.x, ar), ai = fma(v, a.y, ai);
                 br = fma(v, b.x, br), bi = fma(v, b.y, bi);
@@ -499,11 +501,18 @@ extern "C" int fsb_flux_power(const double *in, int64_t nspec, int32_t npix, int
         FSB_CUDA_TRY(cudaMemsetAsync(partial.ptr, 0, sizeof(double) * (size_t) grid * (size_t) nk, stream));
     }
     count_launch(); k_dft_tables<<<(npix + 255) / 256, 256, 0, stream>>>(npix, n1, n2, w1.as<double2>(), w2.as<double2>(), tw.as<double2>());
-    FSB_CUDA_TRY(cudaFuncSetAttribute(k_flux_power, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-    count_launch();
-    k_flux_power<<<grid, kDftThreads, smem, stream>>>(in, nspec, npix, n1, n2, mode, scale, mode == 0 ? 1.0 / mean_flux : 1.0, w1.as<double2>(),
-                                                      w2.as<double2>(), tw.as<double2>(), partial.as<double>(), per_row, yglob.as<double2>(), flags);
-    FSB_CUDA_TRY(cudaGetLastError());
+    auto go = [&](auto kern) -> int {
+        FSB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        count_launch();
+        kern<<<grid, kDftThreads, smem, stream>>>(in, nspec, npix, n1, n2, mode, scale, mode == 0 ? 1.0 / mean_flux : 1.0, w1.as<double2>(),
+                                                  w2.as<double2>(), tw.as<double2>(), partial.as<double>(), per_row, yglob.as<double2>());
+        FSB_CUDA_TRY(cudaGetLastError());
+        return FSB_OK;
+    };
+    if (flags == 0) FSB_TRY(go(k_flux_power<true, true>));
+    else if (flags == 1) FSB_TRY(go(k_flux_power<false, true>));
+    else if (flags == 2) FSB_TRY(go(k_flux_power<true, false>));
+    else FSB_TRY(go(k_flux_power<false, false>));
     if (!per_row) {
         count_launch();
         k_power_final<<<(nk + kStatThreads - 1) / kStatThreads, kStatThreads, 0, stream>>>(partial.as<double>(), grid, nk, factor, power);
