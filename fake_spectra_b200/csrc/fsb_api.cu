@@ -166,6 +166,38 @@ int compute_tau_multi_impl(const fsb_index *idx, const fsb_params *p, int32_t nl
             if (c.nrange == 0) continue;
         }
         const size_t off = (size_t) i0 * (size_t) idx->nlos * (size_t) c.nbins;
+        // Host destination and many sightlines: the pass is cut into sightline ranges, and the rows of a finished range
+        // leave on the copy stream while the next range is computed.  (The ticketed dispatch finishes EVERY row of a
+        // launch in its last phase, so a whole-index launch has nothing to hand to the copy engine until it ends: the
+        // 7-14 GB of a C3 pass were then copied after the kernel.)  Ranges of at least 4096 sightlines keep the
+        // persistent kernel's tail below 2 %; one work item per sightline inside a range, so rows are bit-identical.
+        const int nranges = (host && line_end < 0 && !counters && !push) ? std::min(8, idx->nlos / 4096) : 0;
+        if (nranges >= 2) {
+            InterpConsts cr = c;
+            cr.seg_pairs = 1 << 30;
+            cudaEvent_t done;
+            FSB_CUDA_TRY(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+            int rc = FSB_OK;
+            for (int r = 0; r < nranges && rc == FSB_OK; ++r) {
+                const int l0 = (int) ((int64_t) idx->nlos * r / nranges), l1 = (int) ((int64_t) idx->nlos * (r + 1) / nranges);
+                cr.line0 = l0;
+                cr.nrange = l1 - l0;
+                rc = launch_tau(idx, cr, pos, vel, dens, temp, h, nullptr, tau + off, nullptr, p[i0].precision, stream, nullptr, nullptr);
+                cudaError_t e = rc == FSB_OK ? cudaEventRecord(done, stream) : cudaSuccess;
+                if (e == cudaSuccess && rc == FSB_OK) e = cudaStreamWaitEvent(copy_stream, done, 0);
+                for (int32_t k = 0; k < n && e == cudaSuccess && rc == FSB_OK; ++k) {
+                    const size_t o = off + ((size_t) k * (size_t) idx->nlos + (size_t) l0) * (size_t) c.nbins;
+                    e = cudaMemcpyAsync(host + o, tau + o, sizeof(double) * (size_t) (l1 - l0) * (size_t) c.nbins, cudaMemcpyDeviceToHost, copy_stream);
+                }
+                if (e != cudaSuccess) {
+                    set_error("row delivery: %s", cudaGetErrorString(e));
+                    rc = FSB_ECUDA;
+                }
+            }
+            cudaEventDestroy(done);
+            FSB_TRY(rc);
+            continue;
+        }
         HostSink sink;
         sink.host = host ? host + off : nullptr;
         sink.copy_stream = copy_stream;

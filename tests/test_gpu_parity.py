@@ -349,6 +349,23 @@ def test_several_ions_in_one_host_call(priv, oracle):
         interp(priv, 0, pp["HI1215"], d, extra_ions=others)
 
 
+def test_host_entry_delivers_rows_by_sightline_range(priv, torch_cuda):
+    """Many sightlines through the host boundary: the pass runs as sightline ranges whose rows leave while the next
+    range is computed (fsb_api.cu); rows equal the device-resident pass bit for bit, for one line and for fused lines."""
+    from fake_spectra_b200 import _lib, native
+    d = cases.random_case(nside=10, nlos=9000, axis="cycle", seed=31)
+    pa, pb = cases.params(d, line="HI1215", res=4.0), cases.params(d, line="HI1025", res=4.0)
+    t = dev(torch_cuda, d)
+    idx = native.CandidateIndex(d["box"], t["cofm"], t["axis"], t["pos"], t["h"])
+    want = idx.compute_tau([_lib.make_params(**pa, seg_pairs=1 << 30), _lib.make_params(**pb, seg_pairs=1 << 30)],
+                           t["pos"], t["vel"], t["dens"], t["temp"], t["h"]).cpu().numpy()
+    one = idx.compute_tau(_lib.make_params(**pb, seg_pairs=1 << 30), t["pos"], t["vel"], t["dens"], t["temp"], t["h"]).cpu().numpy()
+    idx.free()
+    both = interp(priv, 1, pa, d, extra_lines=[(pb["lambda_cm"], pb["gamma"], pb["fosc"])])
+    assert both.shape == want.shape and np.array_equal(both, want)
+    assert np.array_equal(interp(priv, 1, pb, d), one)
+
+
 def test_empty_inputs(priv):
     d = cases.random_case(nside=8, nlos=5, axis=1)
     p = cases.params(d)
