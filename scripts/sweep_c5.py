@@ -35,8 +35,9 @@ def cpu_column(d, cofm, ax, res_list, nlines):
     from oracle import Reference
     if not Reference.available():
         return {}
-    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count())
     ref = Reference()
+    # all host threads, whatever OMP_NUM_THREADS says (torchrun exports OMP_NUM_THREADS=1 to every rank)
+    ref.set_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     out = {}
     for res in res_list:
         p = cases.params(d, res=res)
