@@ -79,8 +79,9 @@ class CloudyTable:
             raise ValueError("redshift %g outside the table range [%g, %g]" % (redshift, reds[0], reds[-1]))
         hi = int(np.clip(np.searchsorted(reds, redshift), 1, reds.size - 1))
         lo = hi - 1
-        slope = (table[hi] - table[lo]) / (reds[hi] - reds[lo])
-        return slope * (redshift - reds[lo]) + table[lo]
+        # the two-weight form scipy's interp1d evaluates (exact at the tabulated redshifts)
+        span = reds[hi] - reds[lo]
+        return ((redshift - reds[lo]) / span) * table[hi] + ((reds[hi] - redshift) / span) * table[lo]
 
     def get_temp_bounds(self):
         return (10 ** np.min(self.temp), 10 ** np.max(self.temp))

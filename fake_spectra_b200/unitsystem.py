@@ -37,9 +37,10 @@ class UnitSystem:
     def UnitInternalEnergy_in_cgs(self):
         return self.UnitVelocity_in_cm_per_s ** 2
 
-    def _length_over_c(self, speclen):
-        """A comoving length in internal units (kpc/h) as a light-travel time in s/h."""
-        return speclen * self.UnitLength_in_cm / self.light
+    def _per_c_times_length(self, rate, speclen):
+        """rate [1/s] x comoving length [internal units] / c, multiplied in the reference's order (unitsystem.py:42,51) so
+        that the values agree to the last bit."""
+        return rate / self.light * speclen * self.UnitLength_in_cm
 
     def hubble(self, z, omegam0):
         """H(z) in h/s for a flat universe with matter density omegam0."""
@@ -47,11 +48,11 @@ class UnitSystem:
 
     def absorption_distance(self, speclen, red):
         """Absorption distance X of one sightline of comoving length speclen: (1+z)^2 H0 dL / c."""
-        return self.h100 * self._length_over_c(speclen) * (1 + red) ** 2
+        return self._per_c_times_length(self.h100, speclen) * (1 + red) ** 2
 
     def redshift_distance(self, speclen, red, omegam0):
         """Redshift interval spanned by the comoving length speclen: H(z) dL / c."""
-        return self.hubble(red, omegam0) * self._length_over_c(speclen)
+        return self._per_c_times_length(self.hubble(red, omegam0), speclen)
 
     def rho_crit(self, hubble):
         """Critical density today in g/cm^3 for H0 = 100 hubble km/s/Mpc."""
