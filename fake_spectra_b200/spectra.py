@@ -22,6 +22,7 @@ import numpy as np
 
 from . import _spectra_priv
 from . import abstractsnapshot as absn
+from .absorbers import AbsorberStatistics
 from . import cloudy
 from . import gas_properties
 from . import line_data
@@ -80,7 +81,7 @@ class _SegmentEngine:
         return self.index.compute_colden(params, self.pos, dens, self.h)
 
 
-class Spectra:
+class Spectra(AbsorberStatistics):
     """Interpolates particle densities along sightlines and computes their absorption.
 
     Positional and keyword arguments are those of the reference (spectra.py:85-87); ``base`` may be
