@@ -2,10 +2,12 @@
 
 The reference parses VPFIT's atom.dat (line_data.py:59-81) into ``LineData[(elem, ion)][int(lambda)]``
 objects with ``lambda_X`` (Angstrom), ``fosc_X`` and ``gamma_X`` (1/s).  This module keeps the same
-lookup interface.  A compact built-in table (laboratory values: Morton 2003 and the VPFIT
-compilation) covers the common IGM/CGM lines; :func:`read_vpfit` loads a full user-supplied
-atom.dat for anything else.
+lookup interface.  ``LineData()`` loads the shipped table of every transition of the nine species (data/
+lines_9species.dat: the same 171 lines of 28 ions the reference holds, so that get_observer_tau chooses among the same
+lines); a compact built-in table of the common IGM/CGM lines stands in when the data file is missing, and
+:func:`read_vpfit` loads a user-supplied atom.dat.
 """
+import os
 import re
 
 MASSES = {'H': 1.00794, 'He': 4.002602, 'C': 12.011, 'N': 14.00674, 'O': 15.9994, 'Ne': 20.18,
@@ -57,6 +59,23 @@ def _roman(s):
     return total
 
 
+TABLE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "lines_9species.dat")
+
+
+def read_table(path):
+    """The shipped table (data/lines_9species.dat): ``element ion lambda f_osc Gamma`` per row, every transition of the nine
+    species that the reference's LineData holds (171 lines of 28 ions), keyed like it by the integer wavelength."""
+    lines = {}
+    with open(path) as fh:
+        for raw in fh:
+            tok = raw.split()
+            if not tok or tok[0].startswith("#"):
+                continue
+            lam, fosc, gam = float(tok[2]), float(tok[3]), float(tok[4])
+            lines.setdefault((tok[0], int(tok[1])), {})[int(lam)] = Line(lam, fosc, gam)
+    return lines
+
+
 def read_vpfit(path, species=tuple(MASSES)):
     """Parse a VPFIT atom.dat: species = leading letters, ion = roman numeral, then the first three
     floats are lambda, f, Gamma."""
@@ -90,7 +109,8 @@ class LineData:
         self.species = tuple(MASSES)
         self.masses = dict(MASSES)
         if vpdat is None:
-            self.lines = {k: {int(l[0]): Line(*l) for l in v} for k, v in _BUILTIN.items()}
+            self.lines = read_table(TABLE) if os.path.exists(TABLE) else \
+                {k: {int(l[0]): Line(*l) for l in v} for k, v in _BUILTIN.items()}
         else:
             self.lines = read_vpfit(vpdat, self.species)
 

@@ -128,6 +128,13 @@ def main():
     rs.tau[("H", 1, 1215)] = np.array(tau)
     out["rand_mean_flux_thresh"] = rs.get_mean_flux(tau_thresh=thresh)
 
+    # ---- observer tau: needs a spectrograph resolution (res_corr with sigma = 0 yields NaN maxima in the reference)
+    ro = mods["randspectra"].RandSpectra(0, hostcases.snapshot(12, 1), numlos=8, thresh=0., res=1.5, spec_res=8., **common)
+    out["obs_cofm"] = ro.cofm
+    out["obs_tau_H1"] = np.array(ro.get_observer_tau("H", 1))
+    out["obs_tau_Si2"] = np.array(ro.get_observer_tau("Si", 2))
+    out["obs_tau_C4_number3"] = np.array(ro.get_observer_tau("C", 4, number=3))
+
     # ---- no self-shielding correction / no damping wings
     rs2 = mods["randspectra"].RandSpectra(0, hostcases.snapshot(12, 1), numlos=12, thresh=0., res=2.0, sf_neutral=False,
                                           turn_off_selfshield=True, **common)
