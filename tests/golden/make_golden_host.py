@@ -135,6 +135,12 @@ def main():
     out["obs_tau_Si2"] = np.array(ro.get_observer_tau("Si", 2))
     out["obs_tau_C4_number3"] = np.array(ro.get_observer_tau("C", 4, number=3))
 
+    # ---- threshold selection: sightlines below the column density threshold are replaced until ndla are found
+    rd = mods["randspectra"].RandSpectra(0, hostcases.snapshot(12, 1), numlos=12, ndla=7, thresh=1.2e14, res=2.0, **common)
+    out["dla_cofm"], out["dla_axis"], out["dla_discarded"], out["dla_numlos"] = rd.cofm, rd.axis, rd.discarded, rd.NumLos
+    out["dla_colden_H1"] = np.array(rd.get_col_density("H", 1))
+    out["dla_tau_1215"] = np.array(rd.get_tau("H", 1, 1215))
+
     # ---- no self-shielding correction / no damping wings
     rs2 = mods["randspectra"].RandSpectra(0, hostcases.snapshot(12, 1), numlos=12, thresh=0., res=2.0, sf_neutral=False,
                                           turn_off_selfshield=True, **common)
