@@ -222,6 +222,53 @@ def test_two_rank_sharding_gloo(backend, tmp_path, mode):
     assert np.array_equal(outs[0]["tau"], outs[1]["tau"])
 
 
+def _block_sum_worker(rank, world, port, out_dir):
+    import torch
+    import torch.distributed as dist
+    from fake_spectra_b200 import sharding
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sh = sharding.Sharder("particles")
+    rng = np.random.default_rng(100 + rank)
+    partial = torch.from_numpy(rng.random((1, 37, 11)))     # this rank's particles' contribution to every sightline
+    want = partial.clone()
+    dist.all_reduce(want)                                     # the unblocked sum (Sharder.combine in this mode)
+    blocks = sh.reduce_blocks(37, 5)
+    works = [sh.sum_block_async(partial, b0, b1) for b0, b1 in blocks]  # issued block by block, as blocks complete
+    for w in works:
+        w.wait()
+    flat = torch.from_numpy(rng.random((37, 11)))             # a 2-D array (one line): rows of a block are contiguous too
+    want2 = flat.clone()
+    dist.all_reduce(want2)
+    for w in [sh.sum_block_async(flat, b0, b1) for b0, b1 in blocks]:
+        w.wait()
+    bad = None
+    try:
+        sh.sum_block_async(torch.zeros((2, 37, 11), dtype=torch.float64), 3, 9)
+    except ValueError as exc:
+        bad = str(exc)
+    np.savez(os.path.join(out_dir, "b%d.npz" % rank), got=partial.numpy(), want=want.numpy(), got2=flat.numpy(), want2=want2.numpy(),
+             blocks=np.array(blocks), refused=bad is not None)
+    dist.destroy_process_group()
+
+
+def test_blocked_particle_sum_gloo(tmp_path):
+    """Particle-sharded mode sums the partial optical depths in sightline blocks, each all-reduce started as its block is
+    finished (sharding.Sharder.reduce_blocks / sum_block_async): world size 2 over gloo, block sums ==
+    the whole-array sum bit for bit (the same two addends per element), blocks tile the sightlines, a block of a
+    multi-line array is refused (its rows are not contiguous)."""
+    import torch.multiprocessing as mp
+    port = 29500 + (os.getpid() % 2000) + 31
+    mp.spawn(_block_sum_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    outs = [np.load(os.path.join(str(tmp_path), "b%d.npz" % r)) for r in range(2)]
+    for o in outs:
+        assert np.array_equal(o["got"], o["want"]) and np.array_equal(o["got2"], o["want2"]) and bool(o["refused"])
+        b = o["blocks"]
+        assert b[0, 0] == 0 and b[-1, 1] == 37 and np.array_equal(b[1:, 0], b[:-1, 1]) and len(b) == 5
+    assert np.array_equal(outs[0]["got"], outs[1]["got"])
+
+
 def test_res_corr_is_the_reference_filter():
     """spec_utils.res_corr == scipy.ndimage.gaussian_filter1d(mode='wrap') (what the reference calls, spec_utils.py:24),
     also for sigma around one pixel where a continuous Gaussian would differ by tens of per cent."""
