@@ -124,6 +124,40 @@ class AbsorberStatistics:
         """Ion to neutral hydrogen density ratio of every sightline over the element's solar abundance (spectra.py:793-799)."""
         return self.get_density(species, ion).sum(axis=1) / self.get_density("H", 1).sum(axis=1) / self.solar[species]
 
+    # ---- observational effects (spectra.py:374-432) ---------------------------------------------------------------
+    def add_noise(self, snr, flux, spec_num=-1):
+        """Adds Gaussian noise of standard deviation 1 / snr to flux spectra, in place.  Reproducible per spectrum: NumPy's
+        global generator is seeded with the spectrum's number (``spec_num`` for a single 1-D spectrum, the row number
+        otherwise).  Returns (flux, the noise of all rows concatenated -- empty for a single spectrum)."""
+        if np.ndim(flux) == 1:
+            np.random.seed(spec_num)
+            flux += np.random.normal(0, 1. / snr[spec_num], self.nbins)
+            return flux, np.array([])
+        drawn = []
+        for row in range(np.shape(flux)[0]):
+            np.random.seed(row)
+            drawn.append(np.random.normal(0, 1. / snr[row], self.nbins))
+            flux[row] += drawn[-1]
+        return flux, np.concatenate(drawn) if drawn else np.array([])
+
+    def add_cont_error(self, CE, flux, spec_num=-1, u_delta=0.6, l_delta=-0.6):
+        """Continuum placement error (eq. 2 of arXiv:2112.03930): every spectrum is divided by 1 + delta, delta drawn from
+        a Gaussian of width CE truncated to [l_delta, u_delta]; seeded with twice the spectrum's number so that it differs
+        from the noise of add_noise.  In place; returns (flux, delta)."""
+        def draw(number, width):
+            np.random.seed(2 * number)
+            while True:
+                delta = np.random.normal(0, width)
+                if l_delta <= delta <= u_delta:
+                    return delta
+        if np.ndim(flux) == 1:
+            delta = draw(spec_num, CE[spec_num])
+            flux /= (1.0 + delta)
+            return flux, delta
+        deltas = np.array([draw(row, CE[row]) for row in range(np.shape(flux)[0])])
+        flux /= (1.0 + deltas)[:, None]
+        return flux, deltas
+
     # ---- geometry --------------------------------------------------------------------------------------------------
     def get_spectra_proj_pos(self, cofm=None):
         """The two coordinates of every sightline perpendicular to the common axis (spectra.py:1213-1228)."""

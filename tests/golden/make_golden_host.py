@@ -113,6 +113,16 @@ def main():
     out["rand_metallicity_w20"] = rs.get_metallicity(width=20.)
     out["rand_ion_metallicity_C4"] = rs.get_ion_metallicity("C", 4)
     out["rand_density_H1"] = rs.get_density("H", 1)
+    flux = np.exp(-np.array(out["rand_tau_1215"]))
+    snr, cerr = np.linspace(5., 50., rs.NumLos), np.linspace(0.02, 0.3, rs.NumLos)
+    out["rand_noise_snr"], out["rand_cont_err"] = snr, cerr
+    noisy, noise = rs.add_noise(snr, np.array(flux))
+    out["rand_noisy_flux"], out["rand_noise"] = noisy, noise
+    out["rand_noisy_single"] = rs.add_noise(snr, np.array(flux[3]), spec_num=3)[0]
+    cflux, delta = rs.add_cont_error(cerr, np.array(flux))
+    out["rand_cont_flux"], out["rand_cont_delta"] = cflux, delta
+    one, d1 = rs.add_cont_error(cerr, np.array(flux[5]), spec_num=5)
+    out["rand_cont_single"], out["rand_cont_single_delta"] = one, d1
     out["rand_mean_flux"] = rs.get_mean_flux()
     out["rand_flux_pdf"] = np.array(rs.get_flux_pdf(nbins=10)[1])
     out["rand_flux_pdf_rescaled"] = np.array(rs.get_flux_pdf(nbins=10, mean_flux_desired=0.6)[1])
