@@ -565,7 +565,11 @@ def run_b200(args):
                                                                      / 1e12 / fma_peak, 4) for gi in range(len(groups))} if ev["ion"] else None,
                          "march_steps_per_ion_pass": {groups[gi][0]: dict(zip(route_names, [int(v) for v in cvals[gi][4:9]]))
                                                       for gi in range(len(groups))},
-                         "pairs_per_ion_pass": int(npairs)},
+                         "pairs_per_ion_pass": int(npairs),
+                         "frac_note": "the step's fraction is the time-weighted mix of its launches: the hydrogen launch (two fused lines, "
+                                      "7 march steps per candidate pair; the whole of config C2) runs at frac_per_ion_pass['HI'], the "
+                                      "single weak metal lines finish a pair in about one march step and are bound by per-particle fixed "
+                                      "cost and instruction fetch (DESIGN.md section 5)"},
             "index_build": {"bound": "hbm", "ms": index_s * 1e3, "ms_per_rank": [round(v, 3) for v in index_ms_ranks],
                             "algorithmic_bytes": index_bytes, "achieved": index_bytes / index_s / 1e9, "peak": hbm, "unit": "GB/s",
                             "frac": index_bytes / index_s / 1e9 / hbm, "peak_source": hbm_src, "share_of_step": index_s * 1e3 / step_ms,
