@@ -153,6 +153,38 @@ def test_savefile_keeps_untouched_arrays(backend, tmp_path):
     assert np.array_equal(last.get_tau("H", 1, 1215), tau) and np.array_equal(last.get_col_density("H", 1), col)
 
 
+def test_savefile_hdf5_branch(backend, tmp_path, monkeypatch):
+    """The h5py branch of the savefile (the reference's spectra.hdf5 tree: Header attributes, spectra/cofm, tau/<elem>/<ion>/
+    <line>, colden/<elem>/<ion>, ...; spectra.py:266-372,434-499) driven through a dictionary-backed stand-in for h5py
+    (tests/fake_h5py.py; h5py itself is not installed here): same round trip and lazy loading as the .npz tree."""
+    import fake_h5py
+    monkeypatch.setitem(sys.modules, "h5py", fake_h5py)
+    rs = make_rand(backend, savefile="spectra.hdf5", savedir=str(tmp_path))
+    tau, taub = rs.get_tau("H", 1, 1215), rs.get_tau("H", 1, 1025)
+    col, temp = rs.get_col_density("H", 1), rs.get_temp("H", 1)
+    rs.save_file()
+    with fake_h5py.File(os.path.join(str(tmp_path), "spectra.hdf5"), "r") as f:
+        names = []
+        f.visititems(lambda n, o: names.append(n) if isinstance(o, fake_h5py.Dataset) else None)
+        assert {"spectra/cofm", "spectra/axis", "tau/H/1/1215", "tau/H/1/1025", "colden/H/1", "temperature/H/1"} <= set(names)
+        assert set(f["Header"].attrs) == {"redshift", "nbins", "hubble", "box", "omegam", "omegab", "omegal", "discarded", "npart", "Hz"}
+        assert set(f.keys()) >= {"Header", "spectra", "tau_obs", "tau", "colden", "velocity", "temperature", "num_important",
+                                 "density_weight_density"}
+    back = spectra.Spectra(0, rs.snapshot_set, None, None, savefile="spectra.hdf5", savedir=str(tmp_path), res=None, quiet=True,
+                           backend=backend)
+    assert back.nbins == rs.nbins and np.array_equal(back.cofm, rs.cofm) and np.array_equal(back.axis, rs.axis)
+    assert np.size(back.tau[("H", 1, 1215)]) == 1  # a lazy placeholder until it is asked for
+    assert np.array_equal(back.get_tau("H", 1, 1215), tau) and np.array_equal(back.get_tau("H", 1, 1025), taub)
+    assert np.array_equal(back.get_col_density("H", 1), col) and np.array_equal(back.get_temp("H", 1), temp)
+    back.save_file()  # the first file becomes the backup; every array, loaded or not, is written again
+    assert os.path.exists(os.path.join(str(tmp_path), "spectra.hdf5.backup"))
+    again = spectra.Spectra(0, rs.snapshot_set, None, None, savefile="spectra.hdf5", savedir=str(tmp_path), res=None, quiet=True,
+                            backend=backend)
+    assert np.array_equal(again.get_tau("H", 1, 1025), taub)
+    with pytest.raises(IOError):
+        spectra.Spectra(0, rs.snapshot_set, None, None, savefile="missing.hdf5", savedir=str(tmp_path), quiet=True, backend=backend)
+
+
 def test_unitsystem_hubble_takes_arrays():
     from fake_spectra_b200 import unitsystem
     u = unitsystem.UnitSystem()

@@ -112,3 +112,46 @@ def test_spectra_from_a_bigfile_snapshot(on_disc, oracle):
     a, b = disc.get_tau("H", 1, 1215), mem.get_tau("H", 1, 1215)
     big = b > 1e-6 * b.max()
     assert np.max(np.abs(a[big] - b[big]) / b[big]) < 1e-4
+
+
+def test_hdf5_snapshot_reader_through_a_stand_in(tmp_path, monkeypatch, oracle):
+    """HDF5Snapshot (Gadget / Arepo files, one segment per file, abstractsnapshot.py:156-301) driven through the
+    dictionary-backed stand-in for h5py (tests/fake_h5py.py; h5py itself is absent here): file discovery, name translation,
+    all-segments reads, kernel detection, header access, and the host classes on top of it."""
+    import fake_h5py
+    monkeypatch.setitem(sys.modules, "h5py", fake_h5py)
+    snap = hostcases.snapshot(10, 1)
+    n = snap.fields["Density"].shape[0]
+    edges = [0, n // 3, n]
+    snapdir = tmp_path / "snapdir_007"
+    snapdir.mkdir()
+    for k in range(2):
+        with fake_h5py.File(str(snapdir / ("snap_007.%d.hdf5" % k)), "w") as f:
+            head = f.create_group("Header")
+            for key, value in snap.header.items():
+                head.attrs[key] = np.asarray(value) if isinstance(value, np.ndarray) else value
+            head.attrs["NumPart_Total_HighWord"] = np.zeros(6, dtype=np.int64)
+            nk = edges[k + 1] - edges[k]
+            head.attrs["NumPart_ThisFile"] = np.array([nk, nk, 0, 0, 0, 0])
+            head.attrs["MassTable"] = np.array([0., 5.0, 0., 0., 0., 0.])      # dark matter particle mass
+            for name, data in snap.fields.items():
+                f.create_dataset("PartType0/" + name, data=data[edges[k]:edges[k + 1]])
+            f.create_dataset("PartType0/Masses", data=np.ones(nk, dtype=np.float32))
+    hs = absn.AbstractSnapshotFactory(7, str(tmp_path))
+    assert isinstance(hs, absn.HDF5Snapshot) and hs.get_n_segments() == 2 and hs.get_kernel() == 1
+    assert hs.get_header_attr("BoxSize") == snap.get_header_attr("BoxSize") and int(hs.get_npart()[0]) == n
+    assert np.isclose(hs.get_omega_baryon(), 1. / 6. * snap.get_header_attr("Omega0"))  # gas 1 : dark matter 5 per particle
+    whole = hs.get_data(0, "Position", segment=-1)                       # BigFile name, every file (reverse-sorted like the reference)
+    assert whole.shape == (n, 3) and np.array_equal(np.sort(whole, axis=0), np.sort(snap.fields["Coordinates"], axis=0))
+    lens = [hs.get_blocklen(0, "Density", s) for s in range(2)]
+    assert sorted(lens) == sorted(np.diff(edges).tolist())
+    assert np.array_equal(hs.get_smooth_length(0, 0), hs.get_data(0, "SmoothingLength", segment=0) / 2)
+    with pytest.raises(KeyError):
+        hs.get_data(0, "Volume", segment=0)
+    kw = dict(numlos=10, thresh=0., res=2., quiet=True, backend=hostcases.OracleBackend(oracle))
+    disc, mem = randspectra.RandSpectra(7, str(tmp_path), **kw), randspectra.RandSpectra(7, snap, **kw)
+    assert isinstance(disc.snapshot_set, absn.HDF5Snapshot) and np.array_equal(disc.cofm, mem.cofm)
+    a, b = disc.get_tau("H", 1, 1215), mem.get_tau("H", 1, 1215)  # two segments in another particle order: summation order only
+    assert np.allclose(a, b, rtol=1e-12, atol=0) and np.array_equal(a == 0, b == 0)
+    rel, same = cases.rel_err(disc.get_col_density("H", 1), mem.get_col_density("H", 1))
+    assert same and rel < 1e-12
