@@ -97,3 +97,34 @@ def test_line_table_matches_the_reference(gold):
     for (elem, ion), entries in line_data._BUILTIN.items():
         for lam, fosc, gam in entries:
             assert tuple(ref[(elem, ion, int(lam))]) == (lam, fosc, gam), (elem, ion, lam)
+
+
+# ---- the known answers of the reference's own Python tests (fake_spectra/tests/test_spectra.py:92-131) ----------------
+def test_reference_kat_rho_crit_and_absorption_distance():
+    units = unitsystem.UnitSystem()
+    assert units.rho_crit(0.7) == 9.204285430050004e-30          # testRhoCrit
+    assert units.rho_crit(1.0) == 1.8784255979693885e-29
+    assert units.absorption_distance(25000, 3) == 0.13377926628219666   # testAbsDist
+    assert units.absorption_distance(25000, 2) == 0.07525083728373562
+    assert units.absorption_distance(25000, 3) / units.absorption_distance(12500, 3) == 2.
+
+
+def test_reference_kat_rolled_spectra():
+    tau = np.zeros((2, 50))                                       # testRolledSpectra
+    tau[0, 0] = 1
+    tau[1, 0] = 1
+    tau[1, -1] = 2
+    roll, tau_new = spec_utils.get_rolled_spectra(tau)
+    assert np.all(roll == np.array([25, -24]))
+    assert tau_new[0, 25] == 1 and tau_new[1, 25] == 2 and tau_new[1, 26] == 1
+    assert np.sum(np.abs(tau_new)) == 4
+
+
+def test_reference_kat_res_corr():
+    tau = np.zeros((2, 50))                                       # testrescorr
+    tau[0, 25] = 2
+    tau[1, 23] = 3
+    tau2 = spec_utils.res_corr(tau, 2, 8)
+    assert abs(np.sum(tau2[0, :]) / np.sum(tau[0, :]) - 1) < 1e-6 and abs(np.sum(tau2[1, :]) / np.sum(tau[1, :]) - 1) < 1e-6
+    for i in (0, 1):
+        assert np.size(np.where(tau2[i, :] > 0)) == 15
