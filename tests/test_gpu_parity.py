@@ -351,7 +351,7 @@ def test_several_ions_in_one_host_call(priv, oracle):
 
 def test_host_entry_delivers_rows_by_sightline_range(priv, torch_cuda):
     """Many sightlines through the host boundary: the pass runs as sightline ranges whose rows leave while the next
-    range is computed (fsb_api.cu); rows equal the device-resident pass bit for bit, for one line and for fused lines."""
+    range is computed (fsb_api.cu); the fused lines equal the device-resident pass bit for bit, a single line to 1e-13."""
     from fake_spectra_b200 import _lib, native
     d = cases.random_case(nside=10, nlos=9000, axis="cycle", seed=31)
     pa, pb = cases.params(d, line="HI1215", res=4.0), cases.params(d, line="HI1025", res=4.0)
